@@ -1,0 +1,124 @@
+"""ctypes binding of libautometa_b200.so (the C ABI in include/autometa_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import fails
+loudly, and every device entry point raises when CUDA is unusable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libautometa_b200.so")
+
+AM_OK, AM_EINVAL, AM_ECUDA, AM_ECAPACITY, AM_EFORMAT = 0, -1, -2, -3, -4
+NORM_METHODS = {"am_clr": 0, "clr": 1, "ilr": 2}
+GROUP_BASES = 64
+TILE_BASES = 2048
+
+
+class AutometaB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libautometa_b200 error {code}: {msg}")
+        self.code = code
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
+        "`python -c 'import __graft_entry__ as g; g.build()'` (or `python autometa_b200/build.py`). "
+        "autometa_b200 has no CPU fallback."
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int
+_f64 = C.c_double
+
+_SIGS = {
+    "am_version": (C.c_int, []),
+    "am_last_error": (C.c_char_p, []),
+    "am_launch_count": (_i64, []),
+    "am_kmer_num_columns": (C.c_int, [_i32]),
+    "am_kmer_column_lut": (C.c_int, [_i32, _p]),
+    "am_kmer_column_names": (C.c_int, [_i32, _p]),
+    "am_fasta_index": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _p]),
+    "am_pack_plan": (C.c_int, [_p, _i64, _p, _p, _p]),
+    "am_pack_code_words": (_i64, [_i64]),
+    "am_pack_bitmap_words": (_i64, [_i64]),
+    "am_pack_host": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _i32]),
+    "am_pack_device": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p, _p]),
+    "am_count_plan": (C.c_int, [_p, _i64, _i32, _i32, _p, _i64, _p, _p, _i64, _p]),
+    "am_count_kmers": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p]),
+    "am_normalize_work_bytes": (_i64, [_i32]),
+    "am_normalize": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _i32, _p, _p, _p, _p]),
+    "am_colsum_work_bytes": (_i64, [_i32]),
+    "am_colsum": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
+    "am_gram_work_bytes": (_i64, [_i32]),
+    "am_gram": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
+    "am_eigh_work_bytes": (_i64, [_i32]),
+    "am_eigh": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _f64, _p]),
+    "am_project": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _p, _p]),
+    "am_dbscan_work_bytes": (_i64, [_i64]),
+    "am_eps_union": (C.c_int, [_p, _i64, _i32, _f64, _p, _p, _p, _p, _p]),
+    "am_labels_from_parent": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
+    "am_iota_i32": (C.c_int, [_p, _i64, _p]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)  # AttributeError here = header/library mismatch: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(rc: int) -> None:
+    if rc != AM_OK:
+        raise AutometaB200Error(rc, lib.am_last_error().decode(errors="replace"))
+
+
+def np_ptr(a: np.ndarray) -> int:
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def t_ptr(t) -> int:
+    """data pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous()
+    return t.data_ptr()
+
+
+def require_cuda(device=None):
+    """Resolve the CUDA device for a call; raise if CUDA is unusable (no fallback)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "autometa_b200 needs a CUDA device (sm_100a); torch.cuda.is_available() is False "
+            "and there is no CPU fallback."
+        )
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"autometa_b200 runs on CUDA devices only, got {device}")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def stream_ptr(device) -> int:
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib.am_launch_count())

@@ -1,0 +1,192 @@
+"""Drop-in for the DBSCAN eps step and sweep of ``autometa.binning.recursive_dbscan``.
+
+``run_dbscan`` (reference recursive_dbscan.py:47-111) and ``recursive_dbscan``
+(:114-234) keep their signatures, in-place column drop, cluster numbering,
+schedule, tie rule and termination; the clustering itself runs on the GPU
+(``am_eps_union`` / ``am_labels_from_parent``).  The reference uses
+``DBSCAN(min_samples=1)``: every point is a core point, there are no border or
+noise points, and each eps is the connected components of the eps-graph — so the
+sweep keeps ONE union-find forest on the device and only adds merges as eps grows.
+"""
+from __future__ import annotations
+
+import logging
+from typing import List, Tuple
+
+import numpy as np
+import pandas as pd
+
+from .. import _lib as L
+from .. import device as _dev
+from ..common.exceptions import TableFormatError
+from .utilities import (
+    METRICS,
+    add_metrics,
+    apply_binning_metrics_filter,
+    cluster_metrics_arrays,
+    markers_coo,
+    passing_mask,
+)
+
+logger = logging.getLogger(__name__)
+
+_DROPCOLS = ["cluster", "purity", "completeness", "coverage_stddev", "gc_content_stddev"]
+
+
+def _feature_matrix(df: pd.DataFrame) -> np.ndarray:
+    # recursive_dbscan.py:105-107: every column containing "x_" plus "coverage", in frame order
+    cols = [col for col in df.columns if "x_" in col or col == "coverage"]
+    return np.ascontiguousarray(df.loc[:, cols].to_numpy(dtype=np.float64))
+
+
+def _upload(X: np.ndarray, device=None):
+    import torch
+
+    dev = L.require_cuda(device)
+    if X.shape[1] < 1 or X.shape[1] > 4:
+        raise ValueError(f"the GPU eps step supports 1..4 clustering features, got {X.shape[1]}")
+    return torch.from_numpy(X).to(dev)
+
+
+def run_dbscan(
+    df: pd.DataFrame, eps: float, n_jobs: int = -1, dropcols: List[str] = _DROPCOLS, device=None
+) -> pd.DataFrame:
+    """Cluster ``df`` at ``eps`` (reference recursive_dbscan.py:47-111).
+
+    Drops ``dropcols`` from the caller's frame in place, raises
+    ``TableFormatError`` on nulls, returns ``df`` + int64 ``cluster`` column
+    (``pd.NA`` when there is a single contig).  ``n_jobs`` is accepted and ignored.
+    """
+    df.drop(columns=dropcols, inplace=True, errors="ignore")
+    n_samples = df.shape[0]
+    if n_samples == 1:
+        clusters = pd.Series([pd.NA], index=df.index, name="cluster")
+        return pd.merge(df, clusters, how="left", left_index=True, right_index=True)
+    if np.any(df.isnull()):
+        raise TableFormatError(f"df is missing {df.isnull().sum().sum()} kmer/coverage annotations")
+    X = _feature_matrix(df)
+    if n_samples == 0:
+        labels = np.zeros(0, dtype=np.int64)
+    else:
+        sweep = _dev.EpsSweep(_upload(X, device))
+        labels = sweep.step(float(eps)).cpu().numpy()
+    clusters = pd.Series(labels, index=df.index, name="cluster")
+    return pd.merge(df, clusters, how="left", left_index=True, right_index=True)
+
+
+def recursive_dbscan(
+    table: pd.DataFrame,
+    markers_df: pd.DataFrame,
+    completeness_cutoff: float,
+    purity_cutoff: float,
+    coverage_stddev_cutoff: float,
+    gc_content_stddev_cutoff: float,
+    n_jobs: int = -1,
+    verbose: bool = False,
+    device=None,
+) -> Tuple[pd.DataFrame, pd.DataFrame]:
+    """The eps sweep (reference recursive_dbscan.py:114-234): eps = 0.3, += step (0.1,
+    x10 each time the current cluster count has been seen > 10 times), keep the
+    last eps whose median completeness of passing clusters is >= the best so far,
+    stop at <= 1 cluster (or median == 0 ten times).  Returns
+    ``(clustered_df, unclustered_df)``.
+    """
+    n_samples = table.shape[0]
+    if n_samples <= 1 or "coverage" not in table.columns or "gc_content" not in table.columns:
+        return _recursive_dbscan_frames(
+            table, markers_df, completeness_cutoff, purity_cutoff, coverage_stddev_cutoff,
+            gc_content_stddev_cutoff, verbose, device,
+        )
+    # run_dbscan's side effects and checks (:95-103), once
+    table.drop(columns=_DROPCOLS, inplace=True, errors="ignore")
+    if np.any(table.isnull()):
+        raise TableFormatError(f"df is missing {table.isnull().sum().sum()} kmer/coverage annotations")
+    X = _feature_matrix(table)
+    sweep = _dev.EpsSweep(_upload(X, device))
+    coverage = table["coverage"].to_numpy(dtype=np.float64)
+    gc = table["gc_content"].to_numpy(dtype=np.float64)
+    rows, cols, vals = markers_coo(markers_df, table.index)
+    n_ref = markers_df.shape[1]
+
+    eps, step = 0.3, 0.1
+    clustering_rounds = {0: 0}
+    n_clusters = float("inf")
+    best_median = float("-inf")
+    best = None  # (labels, metrics)
+    while n_clusters > 1:
+        labels_d = sweep.step(eps)
+        labels = labels_d.cpu().numpy()
+        n_clusters = int(sweep.n_clusters.item())
+        m = cluster_metrics_arrays(labels, n_clusters, rows, cols, vals, n_ref, coverage, gc)
+        ok = passing_mask(m, completeness_cutoff, purity_cutoff, coverage_stddev_cutoff, gc_content_stddev_cutoff)
+        median_completeness = float(np.median(m["completeness"][ok])) if ok.any() else float("-inf")
+        if median_completeness >= best_median:
+            best_median = median_completeness
+            best = (labels, m)
+        clustering_rounds[n_clusters] = clustering_rounds.get(n_clusters, 0) + 1
+        if clustering_rounds[n_clusters] > 10:
+            step *= 10
+        if median_completeness == 0:
+            clustering_rounds[0] += 1
+        if clustering_rounds[0] >= 10:
+            break
+        if verbose:
+            logger.debug(
+                f"EPS: {eps:3.2f} Clusters: {n_clusters:,}"
+                f" Completeness: Median={median_completeness:4.2f} Best={best_median:4.2f}"
+            )
+        eps += step
+    labels, m = best
+    best_df = table.copy()
+    best_df["cluster"] = labels
+    for name in METRICS:
+        best_df[name] = m[name][labels]
+    clustered_df = apply_binning_metrics_filter(
+        df=best_df,
+        completeness_cutoff=completeness_cutoff,
+        purity_cutoff=purity_cutoff,
+        coverage_stddev_cutoff=coverage_stddev_cutoff,
+        gc_content_stddev_cutoff=gc_content_stddev_cutoff,
+    )
+    unclustered_df = best_df.loc[~best_df.index.isin(clustered_df.index)]
+    if verbose:
+        logger.debug(f"Best completeness median: {best_median:4.2f}")
+    logger.debug(f"clustered: {clustered_df.shape[0]:,} unclustered: {unclustered_df.shape[0]:,}")
+    return clustered_df, unclustered_df
+
+
+def _recursive_dbscan_frames(table, markers_df, completeness_cutoff, purity_cutoff,
+                             coverage_stddev_cutoff, gc_content_stddev_cutoff, verbose, device):
+    """Literal frame-by-frame form of the loop for degenerate inputs (a single
+    contig, missing columns): same control flow as recursive_dbscan.py:172-234."""
+    eps, step = 0.3, 0.1
+    clustering_rounds = {0: 0}
+    n_clusters = float("inf")
+    best_median = float("-inf")
+    best_df = pd.DataFrame()
+    while n_clusters > 1:
+        binned_df = run_dbscan(df=table, eps=eps, device=device)
+        df, metrics_df = add_metrics(df=binned_df, markers_df=markers_df)
+        filtered_df = apply_binning_metrics_filter(
+            metrics_df, completeness_cutoff, purity_cutoff, coverage_stddev_cutoff, gc_content_stddev_cutoff
+        )
+        median_completeness = float("-inf") if filtered_df.empty else filtered_df.completeness.median()
+        if median_completeness >= best_median:
+            best_median = median_completeness
+            best_df = df
+        n_clusters = df["cluster"].nunique()
+        clustering_rounds[n_clusters] = clustering_rounds.get(n_clusters, 0) + 1
+        if clustering_rounds[n_clusters] > 10:
+            step *= 10
+        if median_completeness == 0:
+            clustering_rounds[0] += 1
+        if clustering_rounds[0] >= 10:
+            break
+        eps += step
+    if best_df.empty:
+        return pd.DataFrame(), table
+    clustered_df = apply_binning_metrics_filter(
+        best_df, completeness_cutoff, purity_cutoff, coverage_stddev_cutoff, gc_content_stddev_cutoff
+    )
+    unclustered_df = best_df.loc[~best_df.index.isin(clustered_df.index)]
+    return clustered_df, unclustered_df

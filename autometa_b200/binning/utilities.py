@@ -1,0 +1,137 @@
+"""Per-eps cluster metrics and the cutoff filter used by the eps sweep.
+
+Host-side mirror of ``autometa.binning.utilities.add_metrics`` /
+``apply_binning_metrics_filter`` (reference binning/utilities.py:125-262) with the
+same inputs, outputs and NA conventions, computed with array reductions over
+the label vector instead of a pandas join + groupby.  ``cluster_metrics_arrays``
+is the array-level core the sweep calls once per eps without building frames.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import numpy as np
+import pandas as pd
+
+METRICS = [
+    "completeness",
+    "purity",
+    "coverage_stddev",
+    "gc_content_stddev",
+    "present_marker_count",
+    "single_copy_marker_count",
+]
+
+
+def cluster_metrics_arrays(
+    labels: np.ndarray, n_clusters: int, marker_rows: np.ndarray, marker_cols: np.ndarray,
+    marker_vals: np.ndarray, n_ref_markers: int, coverage: np.ndarray, gc_content: np.ndarray,
+) -> Dict[str, np.ndarray]:
+    """Metrics per cluster 0..n_clusters-1 (reference utilities.py:176-192).
+
+    ``marker_*`` is the non-zero part of the contig x marker count table in COO form
+    (rows index into ``labels``).  completeness = present / M * 100; purity =
+    single-copy / present * 100 (NaN when nothing is present); std with ddof=1
+    (NaN for single-contig clusters).
+    """
+    M = int(n_ref_markers)
+    if len(marker_rows):
+        key = labels[marker_rows].astype(np.int64) * M + marker_cols
+        uk, inv = np.unique(key, return_inverse=True)
+        sums = np.bincount(inv, weights=marker_vals, minlength=len(uk))
+        clu = uk // M
+        present = np.bincount(clu[sums >= 1], minlength=n_clusters)
+        single = np.bincount(clu[sums == 1], minlength=n_clusters)
+    else:
+        present = np.zeros(n_clusters, dtype=np.int64)
+        single = np.zeros(n_clusters, dtype=np.int64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        completeness = present / M * 100
+        purity = single / present * 100
+    cnt = np.bincount(labels, minlength=n_clusters).astype(np.float64)
+
+    def _std(v):
+        mean = np.bincount(labels, weights=v, minlength=n_clusters) / cnt
+        d = v - mean[labels]
+        ss = np.bincount(labels, weights=d * d, minlength=n_clusters)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.sqrt(ss / (cnt - 1.0))
+
+    return dict(
+        completeness=completeness,
+        purity=purity,
+        coverage_stddev=_std(coverage),
+        gc_content_stddev=_std(gc_content),
+        present_marker_count=present.astype(np.int64),
+        single_copy_marker_count=single.astype(np.int64),
+    )
+
+
+def passing_mask(m: Dict[str, np.ndarray], completeness_cutoff, purity_cutoff, coverage_stddev_cutoff,
+                 gc_content_stddev_cutoff) -> np.ndarray:
+    """utilities.py:257-262: >=, >=, <=, <= ; comparisons with NaN are False."""
+    with np.errstate(invalid="ignore"):
+        return (
+            (m["completeness"] >= completeness_cutoff)
+            & (m["purity"] >= purity_cutoff)
+            & (m["coverage_stddev"] <= coverage_stddev_cutoff)
+            & (m["gc_content_stddev"] <= gc_content_stddev_cutoff)
+        )
+
+
+def markers_coo(markers_df: pd.DataFrame, index: pd.Index):
+    """Non-zero entries of ``markers_df`` restricted/aligned to ``index`` (contigs
+    absent from the marker table count as zero, as the outer join + sum does)."""
+    pos = index.get_indexer(markers_df.index)
+    ok = pos >= 0
+    vals = markers_df.to_numpy(dtype=np.float64, na_value=0.0)[ok]
+    vals = np.nan_to_num(vals, nan=0.0)
+    r, c = np.nonzero(vals)
+    return pos[ok][r].astype(np.int64), c.astype(np.int64), vals[r, c]
+
+
+def add_metrics(df: pd.DataFrame, markers_df: pd.DataFrame) -> Tuple[pd.DataFrame, pd.DataFrame]:
+    """Add per-cluster metrics to each contig of ``df`` (reference utilities.py:125-207).
+
+    Returns ``(contig_metrics_df, cluster_metrics_df)`` with the reference's columns.
+    """
+    n_ref = markers_df.shape[1]
+    if "cluster" not in df.columns:
+        cluster_metrics_df = pd.DataFrame(data={m: pd.NA for m in METRICS}, index=df.index)
+        contig_metrics_df = df.copy().convert_dtypes().drop(columns=METRICS, errors="ignore")
+        contig_metrics_df[METRICS] = pd.NA
+        return contig_metrics_df, cluster_metrics_df
+    df = df.drop(columns=METRICS, errors="ignore")
+    codes, uniques = pd.factorize(df["cluster"], sort=True)  # NA -> -1 (groupby drops NA keys)
+    valid = codes >= 0
+    n_clusters = len(uniques)
+    sub_index = df.index[valid]
+    rows, cols, vals = markers_coo(markers_df, sub_index)
+    m = cluster_metrics_arrays(
+        codes[valid], n_clusters, rows, cols, vals, n_ref,
+        df["coverage"].to_numpy(dtype=np.float64, na_value=np.nan)[valid],
+        df["gc_content"].to_numpy(dtype=np.float64, na_value=np.nan)[valid],
+    )
+    cluster_metrics_df = pd.DataFrame(m, index=pd.Index(uniques, name="cluster"))[METRICS]
+    contig_metrics_df = pd.merge(df, cluster_metrics_df, how="left", left_on="cluster", right_index=True)
+    return contig_metrics_df, cluster_metrics_df
+
+
+def apply_binning_metrics_filter(
+    df: pd.DataFrame,
+    completeness_cutoff: float = 20.0,
+    purity_cutoff: float = 95.00,
+    coverage_stddev_cutoff: float = 25.0,
+    gc_content_stddev_cutoff: float = 5.0,
+) -> pd.DataFrame:
+    """Rows of ``df`` passing the four cutoffs (reference utilities.py:210-262)."""
+    metrics = ["completeness", "purity", "coverage_stddev", "gc_content_stddev"]
+    for metric in metrics:
+        if metric not in df.columns:
+            raise KeyError(f"{metric} not in `df` columns: {df.columns}")
+    return df[
+        df.completeness.ge(completeness_cutoff)
+        & df.purity.ge(purity_cutoff)
+        & df.coverage_stddev.le(coverage_stddev_cutoff)
+        & df.gc_content_stddev.le(gc_content_stddev_cutoff)
+    ]

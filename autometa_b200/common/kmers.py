@@ -1,0 +1,377 @@
+"""Drop-in for the k-mer featurisation functions of ``autometa.common.kmers``.
+
+Same names, arguments, DataFrame schemas, TSV formats and error behaviour as the
+reference (autometa/common/kmers.py), with the arithmetic done by the sm_100a
+kernels behind ``libautometa_b200.so``:
+
+================  =====================================  ======================
+function          reference                              kernel
+================  =====================================  ======================
+``init_kmers``    kmers.py:56-89                         host table (C ABI)
+``count``         kmers.py:268-330 (+122-265 workers)    am_count_kmers
+``autometa_clr``  kmers.py:333-373                       am_normalize (am_clr)
+``normalize``     kmers.py:376-432                       am_normalize
+``pca``           kmers.py:588-607 (sklearn PCA inside)  am_gram / am_eigh / am_project
+``embed``         kmers.py:435-706                       PCA stage on GPU; manifold step passed through
+================  =====================================  ======================
+
+There is no CPU fallback: without a CUDA device these functions raise.
+"""
+from __future__ import annotations
+
+import logging
+import multiprocessing as mp
+import os
+from typing import Any, Dict, Union
+
+import numpy as np
+import pandas as pd
+
+from .. import _lib as L
+from .. import assembly as _asm
+from .. import device as _dev
+from .exceptions import TableFormatError
+
+logger = logging.getLogger(__name__)
+
+
+def _revcomp(string: str) -> str:
+    """Reverse complement of an upper-case ACGT string (reference kmers.py:38-53)."""
+    comp = {"A": "T", "T": "A", "C": "G", "G": "C"}
+    return "".join(comp.get(ch) for ch in reversed(string))
+
+
+def init_kmers(kmer_size: int = 5) -> Dict[str, int]:
+    """``{kmer: column}`` in the reference's column order (kmers.py:56-89): k-mers
+    enumerated over the letters A,T,C,G, one representative per reverse-complement
+    pair (the first one met).  The table comes from ``am_kmer_column_names``."""
+    if not isinstance(kmer_size, int) or isinstance(kmer_size, bool):
+        raise TypeError(f"kmer_size must be an int! Given: {type(kmer_size)}")
+    return {name: i for i, name in enumerate(_dev.column_names(kmer_size))}
+
+
+def load(kmers_fpath: str) -> pd.DataFrame:
+    """Load a k-mer table written by :func:`count` / :func:`normalize` (kmers.py:92-119)."""
+    if not os.path.exists(kmers_fpath) or not os.path.getsize(kmers_fpath):
+        raise FileNotFoundError(kmers_fpath)
+    try:
+        df = pd.read_csv(kmers_fpath, sep="\t", index_col="contig")
+    except (ValueError, TypeError):
+        raise TableFormatError(f"contig column not found in {kmers_fpath}!")
+    return df
+
+
+def _counts_frame(ids, counts: np.ndarray, countable: np.ndarray, names) -> pd.DataFrame:
+    """Frame with the reference's schema (kmers.py:205,325-326): index 'contig',
+    k-mer columns, zero counts stored as ``pd.NA``.  Nullable Int32 columns are
+    used instead of object dtype; contigs with L <= k are all-NA rows."""
+    mask = counts == 0
+    if not countable.all():
+        mask[~countable] = True
+    # duplicate ids: the reference merges per-record dicts with dict.update (kmers.py:155-157),
+    # so a later record overwrites the values but keeps the first record's position
+    index = pd.Index(ids, name="contig")
+    if not index.is_unique:
+        first, last = {}, {}
+        for pos, cid in enumerate(ids):
+            first.setdefault(cid, pos)
+            last[cid] = pos
+        keep = sorted(first.values())
+        src = [last[ids[p]] for p in keep]
+        counts, mask = counts[src], mask[src]
+        index = pd.Index([ids[p] for p in keep], name="contig")
+    cols = {
+        name: pd.arrays.IntegerArray(np.ascontiguousarray(counts[:, j]), np.ascontiguousarray(mask[:, j]))
+        for j, name in enumerate(names)
+    }
+    return pd.DataFrame(cols, index=index)
+
+
+def count(
+    assembly: str,
+    size: int = 5,
+    out: str = None,
+    force: bool = False,
+    verbose: bool = True,
+    cpus: int = mp.cpu_count(),
+    device=None,
+) -> pd.DataFrame:
+    """Count canonical k-mers of every contig of ``assembly`` (reference kmers.py:268-330).
+
+    ``cpus`` only sizes the host packing threads; the counting runs on the GPU.
+    Returns index='contig' (FASTA order), columns = :func:`init_kmers` order, zero ->
+    ``pd.NA``; contigs with ``len <= size`` give an all-NA row and a warning
+    (kmers.py:187-192).  ``out``/``force`` caching as in the reference (:310-314,327-329).
+    """
+    out_specified = out is not None
+    out_exists = os.path.exists(out) if out else False
+    if out_specified and out_exists and not force:
+        logger.warning(f"counts already exist: {out} force to overwrite. [retrieving]")
+        df = pd.read_csv(out, sep="\t", index_col="contig")
+    else:
+        if not isinstance(size, int) or isinstance(size, bool):
+            raise TypeError(f"size must be an int! Given: {type(size)}")
+        names = _dev.column_names(size)
+        logger.info(f"Counting {size}-mers.")
+        host = _asm.read_fasta(assembly)
+        packed = _asm.pack_to_device(host, device=device, threads=int(cpus) if cpus else 0)
+        counts_d, _, _ = _dev.count_packed(packed, size)
+        counts = counts_d.cpu().numpy()
+        lengths = host.lengths
+        countable = lengths > size
+        for cid, ln in zip(np.asarray(host.ids, dtype=object)[~countable], lengths[~countable]):
+            logger.warning(f"{cid} can not be counted! k-mer size exceeds length. {ln}")
+        df = _counts_frame(host.ids, counts, countable, names)
+    if out:
+        df.to_csv(out, sep="\t", index=True, header=True)
+        logger.debug(f"Wrote {df.shape[0]} contigs {size}-mers frequencies to {out}.")
+    return df
+
+
+def _counts_matrix(df: pd.DataFrame):
+    """(int32 counts with NA -> 0, isna mask) from an object/NA, nullable-int or float/NaN frame."""
+    try:
+        X = df.to_numpy(dtype=np.float64, na_value=np.nan)
+    except (ValueError, TypeError):
+        raise TableFormatError("k-mer table holds non-numeric values")
+    isna = np.isnan(X)
+    X = np.where(isna, 0.0, X)
+    if X.size and (np.any(X < 0) or np.any(X > 2**31 - 1) or np.any(X != np.rint(X))):
+        raise TableFormatError("k-mer counts must be non-negative integers")
+    return np.ascontiguousarray(X.astype(np.int32)), isna
+
+
+def _normalize_array(counts: np.ndarray, isna: np.ndarray, method: str, device=None):
+    """Run kernel 2 on a host count matrix; returns (values, row_keep, col_keep)."""
+    import torch
+
+    dev = L.require_cuda(device)
+    n, D = counts.shape
+    if method == "am_clr":
+        # kmers.py:369: drop all-NA columns, then all-NA rows, then fill with 0
+        col_keep = ~isna.all(axis=0) if n else np.zeros(D, dtype=bool)
+        row_keep = ~isna[:, col_keep].all(axis=1) if col_keep.any() else np.zeros(n, dtype=bool)
+    else:
+        col_keep = np.ones(D, dtype=bool)
+        row_keep = np.ones(n, dtype=bool)
+        if n and np.any(counts.sum(axis=1) == 0):
+            # skbio closure() inside multiplicative_replacement (kmers.py:420)
+            raise ValueError("Input matrix cannot have rows with all zeros")
+    n_out, d_keep = int(row_keep.sum()), int(col_keep.sum())
+    d_out = d_keep - 1 if method == "ilr" else d_keep
+    if n_out == 0 or d_keep == 0 or d_out <= 0:
+        return np.zeros((n_out, max(d_out, 0))), row_keep, col_keep
+    with torch.cuda.device(dev):
+        d_counts = torch.from_numpy(counts).to(dev)
+        ridx = None if row_keep.all() else torch.from_numpy(np.nonzero(row_keep)[0].astype(np.int64)).to(dev)
+        cidx = None if col_keep.all() else torch.from_numpy(np.nonzero(col_keep)[0].astype(np.int32)).to(dev)
+        out = _dev.normalize_counts(d_counts, method, ridx, cidx)
+        return out.cpu().numpy(), row_keep, col_keep
+
+
+def autometa_clr(df: pd.DataFrame, device=None) -> pd.DataFrame:
+    """Autometa's CLR (reference kmers.py:333-373): drop k-mers absent from every
+    contig and contigs without counts, then ``log((x+1)/sum / gmean((x+1)/sum))``."""
+    counts, isna = _counts_matrix(df)
+    vals, row_keep, col_keep = _normalize_array(counts, isna, "am_clr", device)
+    return pd.DataFrame(vals, index=df.index[row_keep], columns=df.columns[col_keep])
+
+
+def normalize(
+    df: pd.DataFrame, method: str = "am_clr", out: str = None, force: bool = False, device=None
+) -> pd.DataFrame:
+    """Normalise raw k-mer counts by ``am_clr``, ``clr`` or ``ilr`` (reference kmers.py:376-432)."""
+    method = method.lower()
+    out_specified = out is not None
+    out_exists = os.path.exists(out) if out else False
+    if out_specified and out_exists and not force:
+        logger.debug(f"{out} already exists. Use force to overwrite. retrieving...")
+        return pd.read_csv(out, sep="\t", index_col="contig")
+    logger.debug(f"Transforming k-mer counts using {method}")
+    choices = {"ilr", "clr", "am_clr"}
+    if method == "am_clr":
+        norm_df = autometa_clr(df, device=device)
+    elif method in choices:
+        counts, isna = _counts_matrix(df)
+        vals, _, _ = _normalize_array(counts, isna, method, device)
+        norm_df = pd.DataFrame(vals, index=df.index)  # integer column labels (kmers.py:422)
+    else:
+        raise ValueError(f"Normalize Method not available! {method}. choices: {', '.join(choices)}")
+    if out_specified and (force or not out_exists):
+        norm_df.to_csv(out, sep="\t", index=True, header=True)
+    return norm_df
+
+
+def pca(X, n_components: int = 50, seed: int = 42, device=None, as_numpy: bool = True) -> Dict[str, Any]:
+    """PCA scores of ``X`` [N x D] exactly as sklearn 1.9's
+    ``PCA(n_components, svd_solver="covariance_eigh").fit_transform`` computes them
+    (the branch reference kmers.py:605 takes when N >= 10*D; sklearn/decomposition/_pca.py:560,604-646):
+    mean, covariance from the centred Gram, symmetric eigensolve, descending order,
+    negative eigenvalues clipped, svd_flip sign rule, scores = (X - mean) @ components.T.
+    ``seed`` is accepted for signature parity; this exact solver uses no randomness.
+    """
+    import torch
+
+    dev = L.require_cuda(device)
+    with torch.cuda.device(dev):
+        if isinstance(X, torch.Tensor):
+            Xd = X.to(device=dev, dtype=torch.float64).contiguous()
+        else:
+            Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(dev)
+        n, D = Xd.shape
+        if not 1 <= n_components <= min(n, D):
+            raise ValueError(
+                f"n_components={n_components!r} must be between 1 and min(n_samples, n_features)={min(n, D)}"
+            )
+        res = pca_device(Xd, n_components)
+    if as_numpy:
+        res = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in res.items()}
+    return res
+
+
+def pca_device(Xd, n_components: int, group=None) -> Dict[str, Any]:
+    """PCA on a device-resident fp64 matrix (rows may be sharded over the ranks of
+    ``group``: column sums, row count and the Gram are all-reduced)."""
+    import torch
+
+    n_local, D = Xd.shape
+    cs = _dev.colsum(Xd)
+    n_t = torch.tensor([float(n_local)], dtype=torch.float64, device=Xd.device)
+    if group is not None:
+        import torch.distributed as dist
+
+        dist.all_reduce(cs, group=group if group is not True else None)
+        dist.all_reduce(n_t, group=group if group is not True else None)
+    n = n_t  # stays on device: no host sync in the fit
+    mu = cs / n
+    G = _dev.gram_centered(Xd, mu)
+    if group is not None:
+        import torch.distributed as dist
+
+        dist.all_reduce(G, group=group if group is not True else None)
+    C = G / (n - 1.0)
+    evals, evecs = _dev.eigh_desc(C)
+    evals = torch.clamp(evals, min=0.0)  # _pca.py:630
+    total = evals.sum()
+    comps = evecs[:n_components].contiguous()
+    scores = _dev.project(Xd, mu, comps)
+    return dict(
+        scores=scores,
+        mean=mu,
+        components=comps,
+        explained_variance=evals[:n_components].clone(),
+        explained_variance_ratio=evals[:n_components] / total,
+        total_variance=total,
+        covariance=C,
+    )
+
+
+def embed(
+    kmers: Union[str, pd.DataFrame],
+    out: str = None,
+    force: bool = False,
+    embed_dimensions: int = 2,
+    pca_dimensions: int = 50,
+    method: str = "bhsne",
+    perplexity: float = 30.0,
+    seed: int = 42,
+    n_jobs: int = -1,
+    device=None,
+    **method_kwargs: Dict[str, Any],
+) -> pd.DataFrame:
+    """Embed normalised k-mer frequencies (reference kmers.py:435-706).
+
+    Only the PCA stage (kmers.py:588-607) runs on the GPU here; the manifold step
+    is handed to whichever embedder is installed (sklearn's TSNE for ``sksne``;
+    ``tsne``/``umap``/``trimap`` packages for the others) with the reference's arguments.
+    """
+    if isinstance(kmers, str) and os.path.exists(kmers) and os.path.getsize(kmers):
+        try:
+            df = pd.read_csv(kmers, sep="\t", index_col="contig")
+        except ValueError:
+            raise TableFormatError(f"contig column not found in {kmers}")
+    elif isinstance(kmers, pd.DataFrame):
+        df = kmers
+    else:
+        raise TypeError(kmers)
+    if out and os.path.exists(out) and os.path.getsize(out) and not force:
+        logger.debug(f"k-mers frequency embedding already exists {out}")
+        try:
+            return pd.read_csv(out, sep="\t", index_col="contig")
+        except ValueError:
+            raise TableFormatError(f"contig column not found in {out}")
+    if df.empty:
+        raise FileNotFoundError(
+            f"kmers:{kmers} type:{type(kmers)} out:{out} type:{type(out)} Given pd.DataFrame is empty!"
+        )
+    method = method.lower()
+    choices = {"umap", "sksne", "bhsne", "densmap", "trimap"}
+    if method not in choices:
+        raise ValueError(f"{method} not in embedding methods. Choices: {', '.join(choices)}")
+    n_samples, n_components = df.shape
+    X = df.dropna(axis="index", how="all").fillna(0).to_numpy(dtype=np.float64)
+    random_state = np.random.RandomState(seed)
+    if isinstance(pca_dimensions, str):
+        try:
+            pca_dimensions = int(pca_dimensions)
+        except Exception:
+            raise TypeError(f"pca_dimensions must be an integer! given: {pca_dimensions}")
+    if n_components > pca_dimensions and pca_dimensions != 0:
+        logger.debug(f"Performing decomposition with PCA (seed {seed}): {n_components} to {pca_dimensions} dims")
+        X = pca(X, n_components=pca_dimensions, seed=seed, device=device)["scores"]
+        n_samples, n_components = X.shape
+    logger.debug(f"{method}: {n_samples} data points and {n_components} dimensions")
+    n_rows = n_samples - 1
+    scaler = 3.0
+    if n_rows < (scaler * perplexity):
+        perplexity = (n_rows / scaler) - 1
+
+    def do_sksne():
+        from sklearn.manifold import TSNE
+
+        return TSNE(
+            n_components=embed_dimensions, perplexity=perplexity, random_state=random_state,
+            n_jobs=n_jobs, **method_kwargs,
+        ).fit_transform(X)
+
+    def do_bhsne():
+        from tsne import bh_sne  # not part of this package: passed through when installed
+
+        return bh_sne(data=X, d=embed_dimensions, perplexity=perplexity, random_state=random_state, **method_kwargs)
+
+    def do_umap():
+        from umap import UMAP
+
+        return UMAP(
+            n_neighbors=15, n_components=embed_dimensions, metric="euclidean", random_state=random_state,
+            densmap=(method == "densmap"), n_jobs=n_jobs, **method_kwargs,
+        ).fit_transform(X)
+
+    def do_trimap():
+        from trimap import TRIMAP
+
+        return TRIMAP(n_dims=embed_dimensions, verbose=False, **method_kwargs).fit_transform(X)
+
+    dispatcher = {"sksne": do_sksne, "bhsne": do_bhsne, "umap": do_umap, "densmap": do_umap, "trimap": do_trimap}
+    logger.debug(f"Performing embedding with {method} (seed {seed})")
+    try:
+        X = dispatcher[method]()
+    except ValueError as err:
+        if method == "sksne":
+            logger.warning(f"embed_dimensions ({embed_dimensions}) is too high for sksne. Reducing to 3.")
+            embed_dimensions = 3
+            X = dispatcher[method]()
+        else:
+            raise err
+    embed_cols = [f"x_{col}" for col in range(1, embed_dimensions + 1)]
+    if isinstance(X, tuple):
+        cols = [embed_cols, ["original_local_radius"], ["embedded_local_radius"]]
+        embedded_df = pd.concat(
+            [pd.DataFrame(res, index=df.index, columns=c) for res, c in zip(X, cols)], axis=1
+        )
+    else:
+        embedded_df = pd.DataFrame(X, index=df.index, columns=embed_cols)
+    if out:
+        embedded_df.to_csv(out, sep="\t", index=True, header=True)
+        logger.debug(f"embedded.shape {embedded_df.shape} : Written {out}")
+    return embedded_df

@@ -1,0 +1,71 @@
+// Shared helpers for libautometa_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <algorithm>
+#include <vector>
+
+#include "../../include/autometa_b200.h"
+
+namespace am {
+
+extern thread_local char g_err[512];
+extern std::atomic<int64_t> g_launches;
+
+inline int fail(int code, const char *fmt, const char *a = "", const char *b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+inline int cuda_fail(cudaError_t e, const char *where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return AM_ECUDA;
+}
+
+#define AM_CUDA(call)                                         \
+  do {                                                        \
+    cudaError_t _e = (call);                                  \
+    if (_e != cudaSuccess) return am::cuda_fail(_e, #call);   \
+  } while (0)
+
+// after every kernel launch: count it and surface launch-configuration errors
+#define AM_LAUNCHED(name)                                     \
+  do {                                                        \
+    am::g_launches.fetch_add(1, std::memory_order_relaxed);   \
+    cudaError_t _e = cudaGetLastError();                      \
+    if (_e != cudaSuccess) return am::cuda_fail(_e, name);    \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// reverse complement of an MSB-first base-4 code with A=0,T=1,C=2,G=3
+inline uint32_t revcomp_code(uint32_t code, int k) {
+  uint32_t rc = 0;
+  for (int i = 0; i < k; ++i) {
+    rc = (rc << 2) | ((code & 3u) ^ 1u);
+    code >>= 2;
+  }
+  return rc;
+}
+// reverse the base-4 digits (MSB-first code <-> LSB-first window value)
+inline uint32_t digit_reverse(uint32_t code, int k) {
+  uint32_t r = 0;
+  for (int i = 0; i < k; ++i) {
+    r = (r << 2) | (code & 3u);
+    code >>= 2;
+  }
+  return r;
+}
+
+}  // namespace am

@@ -1,0 +1,306 @@
+// Kernel 4 — DBSCAN(min_samples=1) eps step as connected components (sm_100a).
+//
+// Replaces DBSCAN(eps, min_samples=1, n_jobs).fit(X).labels_ at
+// autometa/binning/recursive_dbscan.py:109.  With min_samples=1 every point is a
+// core point: labels are the connected components of the eps-graph, numbered by
+// ascending minimum member row (the order sklearn/cluster/_dbscan_inner.pyx visits).
+// Pair predicate restates sklearn's KD-tree leaf test
+// (sklearn/neighbors/_binary_tree.pxi.tp:1952-1957 + euclidean rdist): fp64,
+// d = sum_j (a_j - b_j)^2 accumulated in column order WITHOUT fma contraction,
+// joined iff d <= eps*eps.
+//
+// Per eps: points are binned into a hashed uniform grid of cell edge eps*(1+2^-20)
+// (counting sort by bucket), then every point scans the 3^F neighbouring cells and
+// unions itself (lock-free union-find, root = smallest row index) with every
+// neighbour of smaller row index that passes the predicate.  The forest persists
+// across the sweep's increasing eps values, so each step only adds merges.
+#include "am_common.cuh"
+#include "am_scan.cuh"
+
+namespace {
+
+constexpr int MAXF = 4;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct GridParams {
+  double mn[MAXF];
+  double inv_cell;
+  int F;
+  unsigned nbuckets_mask;
+};
+
+__device__ __forceinline__ unsigned hash_cell(const int *c, int F, unsigned mask) {
+  unsigned h = 0x9E3779B9u;
+  for (int d = 0; d < F; ++d) {
+    h ^= (unsigned)c[d] + 0x9E3779B9u + (h << 6) + (h >> 2);
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+  }
+  return h & mask;
+}
+
+__device__ __forceinline__ void cell_of(const double *x, const GridParams &gp, int *c) {
+  for (int d = 0; d < gp.F; ++d) c[d] = (int)floor((x[d] - gp.mn[d]) * gp.inv_cell);
+}
+
+__global__ void bucket_count_kernel(const double *__restrict__ X, int n, GridParams gp,
+                                    unsigned *__restrict__ bucket_of, unsigned *__restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x[MAXF];
+  int c[MAXF];
+  for (int d = 0; d < gp.F; ++d) x[d] = __ldg(X + (int64_t)i * gp.F + d);
+  cell_of(x, gp, c);
+  const unsigned b = hash_cell(c, gp.F, gp.nbuckets_mask);
+  bucket_of[i] = b;
+  atomicAdd(counts + b, 1u);
+}
+
+__global__ void bucket_scatter_kernel(const double *__restrict__ X, int n, int F,
+                                      const unsigned *__restrict__ bucket_of,
+                                      const unsigned *__restrict__ bucket_start,
+                                      unsigned *__restrict__ fill, int *__restrict__ sorted_idx,
+                                      double *__restrict__ sorted_x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned b = bucket_of[i];
+  const unsigned pos = bucket_start[b] + atomicAdd(fill + b, 1u);
+  sorted_idx[pos] = i;
+  for (int d = 0; d < F; ++d) sorted_x[(int64_t)d * n + pos] = __ldg(X + (int64_t)i * F + d);
+}
+
+__device__ __forceinline__ int uf_find(int *parent, int x) {
+  int p = *((volatile int *)(parent + x));
+  while (p != x) {
+    const int gp = *((volatile int *)(parent + p));
+    if (gp != p) atomicMin(parent + x, gp);  // path halving (monotone: parents only decrease)
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+
+__device__ __forceinline__ void uf_union(int *parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }  // a > b: hook the larger root under the smaller
+    const int old = atomicCAS(parent + a, a, b);
+    if (old == a) return;
+  }
+}
+
+// one thread per point (in bucket-sorted order)
+__global__ void __launch_bounds__(128)
+eps_union_kernel(int n, GridParams gp, double eps2, const unsigned *__restrict__ bucket_start,
+                 const int *__restrict__ sorted_idx, const double *__restrict__ sorted_x,
+                 int *__restrict__ parent) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n) return;
+  const int F = gp.F;
+  double x[MAXF];
+  int c[MAXF];
+  for (int d = 0; d < F; ++d) x[d] = sorted_x[(int64_t)d * n + pos];
+  cell_of(x, gp, c);
+  const int me = sorted_idx[pos];
+  int ncomb = 1;
+  for (int d = 0; d < F; ++d) ncomb *= 3;
+  unsigned seen[81];  // buckets already scanned by this thread (3^4 max)
+  int nseen = 0;
+  for (int comb = 0; comb < ncomb; ++comb) {
+    int cc[MAXF];
+    int t = comb;
+    for (int d = 0; d < F; ++d) {
+      cc[d] = c[d] + (t % 3) - 1;
+      t /= 3;
+    }
+    const unsigned b = hash_cell(cc, F, gp.nbuckets_mask);
+    bool dup = false;
+    for (int s = 0; s < nseen; ++s) dup |= (seen[s] == b);
+    if (dup) continue;
+    seen[nseen++] = b;
+    const unsigned beg = bucket_start[b], end = bucket_start[b + 1];
+    for (unsigned j = beg; j < end; ++j) {
+      const int other = sorted_idx[j];
+      if (other >= me) continue;  // each unordered pair once, from its larger row
+      double dist = 0.0;
+      for (int d = 0; d < F; ++d) {
+        const double tmp = __dsub_rn(x[d], sorted_x[(int64_t)d * n + j]);
+        dist = __dadd_rn(dist, __dmul_rn(tmp, tmp));
+      }
+      if (dist <= eps2) uf_union(parent, me, other);
+    }
+  }
+}
+
+__global__ void compress_kernel(int *__restrict__ parent, int n, unsigned *__restrict__ is_root) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int r = i;
+  while (true) {
+    const int p = *((volatile int *)(parent + r));
+    if (p == r) break;
+    r = p;
+  }
+  is_root[i] = (r == i) ? 1u : 0u;
+  // do not write parent[i] here: another thread may still be walking through i
+}
+
+__global__ void relabel_kernel(int *__restrict__ parent, int n, const unsigned *__restrict__ root_rank,
+                               int64_t *__restrict__ labels, int *__restrict__ n_clusters) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) n_clusters[0] = (int)root_rank[n];
+  if (i >= n) return;
+  int r = i;
+  while (true) {
+    const int p = __ldg(parent + r);
+    if (p == r) break;
+    r = p;
+  }
+  labels[i] = (int64_t)root_rank[r];
+}
+
+__global__ void flatten_kernel(int *__restrict__ parent, const int64_t *__restrict__ labels,
+                               const unsigned *__restrict__ is_root, int n, int *__restrict__ root_of_label) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (is_root[i]) root_of_label[labels[i]] = i;
+}
+
+__global__ void flatten2_kernel(int *__restrict__ parent, const int64_t *__restrict__ labels, int n,
+                                const int *__restrict__ root_of_label) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  parent[i] = root_of_label[labels[i]];
+}
+
+__global__ void iota_kernel(int *v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    v[i] = (int)i;
+}
+
+unsigned pick_buckets(int64_t n) {
+  unsigned b = 1024;
+  while ((int64_t)b < 2 * n && b < (1u << 26)) b <<= 1;
+  return b;
+}
+
+struct Work {
+  unsigned *bucket_of;     // n
+  unsigned *counts;        // nb
+  unsigned *fill;          // nb
+  unsigned *bucket_start;  // nb + 1
+  int *sorted_idx;         // n
+  double *sorted_x;        // MAXF * n
+  unsigned *is_root;       // n
+  unsigned *root_rank;     // n + 1
+  int *root_of_label;      // n
+};
+
+inline int64_t align_up(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+int64_t carve(void *base, int64_t n, Work *w) {
+  const unsigned nb = pick_buckets(n);
+  int64_t off = 0;
+  char *p = (char *)base;
+  auto take = [&](int64_t bytes) {
+    char *q = p ? p + off : nullptr;
+    off += align_up(bytes);
+    return q;
+  };
+  Work t;
+  t.bucket_of = (unsigned *)take(n * 4);
+  t.counts = (unsigned *)take((int64_t)nb * 4);
+  t.fill = (unsigned *)take((int64_t)nb * 4);
+  t.bucket_start = (unsigned *)take(((int64_t)nb + 1) * 4);
+  t.sorted_idx = (int *)take(n * 4);
+  t.sorted_x = (double *)take((int64_t)MAXF * n * 8);
+  t.is_root = (unsigned *)take(n * 4);
+  t.root_rank = (unsigned *)take((n + 1) * 4);
+  t.root_of_label = (int *)take(n * 4);
+  if (w) *w = t;
+  return off;
+}
+
+}  // namespace
+
+extern "C" int64_t am_dbscan_work_bytes(int64_t n_points) {
+  if (n_points < 0) return 0;
+  return carve(nullptr, n_points, nullptr);
+}
+
+extern "C" int am_iota_i32(int32_t *d_v, int64_t n, void *stream) {
+  if (n == 0) return AM_OK;
+  if (!d_v || n < 0) return am::fail(AM_EINVAL, "am_iota_i32: bad args");
+  iota_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, (cudaStream_t)stream>>>(d_v, n);
+  AM_LAUNCHED("iota_kernel");
+  return AM_OK;
+}
+
+extern "C" int am_eps_union(const double *d_X, int64_t n_points, int F, double eps,
+                            const double *h_min, const double *h_max, int32_t *d_parent,
+                            void *d_work, void *stream) {
+  if (F < 1 || F > MAXF) return am::fail(AM_EINVAL, "am_eps_union: F must be in 1..4");
+  if (n_points < 0 || n_points > 0x7fffffff) return am::fail(AM_EINVAL, "am_eps_union: bad n_points");
+  if (!(eps > 0.0)) return am::fail(AM_EINVAL, "am_eps_union: eps must be > 0");
+  if (n_points == 0) return AM_OK;
+  if (!d_X || !h_min || !h_max || !d_parent || !d_work) return am::fail(AM_EINVAL, "am_eps_union: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = (int)n_points;
+  Work w;
+  carve(d_work, n_points, &w);
+  const unsigned nb = pick_buckets(n_points);
+  GridParams gp;
+  // cell edge slightly above eps so that |a-b| <= eps implies cell indices differ by <= 1
+  // even after rounding; cap the cell count per axis so indices stay well inside int range
+  double cell = eps * (1.0 + 1.0 / 1048576.0);
+  for (int d = 0; d < F; ++d) {
+    const double span = h_max[d] - h_min[d];
+    if (!(span >= 0.0)) return am::fail(AM_EINVAL, "am_eps_union: bad bounds (NaN?)");
+    if (span / cell > 1.0e9) cell = span / 1.0e9;
+  }
+  for (int d = 0; d < MAXF; ++d) gp.mn[d] = d < F ? h_min[d] : 0.0;
+  gp.inv_cell = 1.0 / cell;
+  gp.F = F;
+  gp.nbuckets_mask = nb - 1;
+  AM_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)nb * 4, st));
+  AM_CUDA(cudaMemsetAsync(w.fill, 0, (size_t)nb * 4, st));
+  const int blocks = (n + 255) / 256;
+  bucket_count_kernel<<<blocks, 256, 0, st>>>(d_X, n, gp, w.bucket_of, w.counts);
+  AM_LAUNCHED("bucket_count_kernel");
+  am::exclusive_scan_kernel<<<1, 1024, 0, st>>>(w.counts, w.bucket_start, (int)nb);
+  AM_LAUNCHED("exclusive_scan_kernel");
+  bucket_scatter_kernel<<<blocks, 256, 0, st>>>(d_X, n, F, w.bucket_of, w.bucket_start, w.fill,
+                                                w.sorted_idx, w.sorted_x);
+  AM_LAUNCHED("bucket_scatter_kernel");
+  eps_union_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, gp, eps * eps, w.bucket_start, w.sorted_idx,
+                                                    w.sorted_x, d_parent);
+  AM_LAUNCHED("eps_union_kernel");
+  return AM_OK;
+}
+
+extern "C" int am_labels_from_parent(int32_t *d_parent, int64_t n_points, int64_t *d_labels,
+                                     int32_t *d_n_clusters, void *d_work, void *stream) {
+  if (n_points < 0 || n_points > 0x7fffffff) return am::fail(AM_EINVAL, "am_labels_from_parent: bad n");
+  if (n_points == 0) return AM_OK;
+  if (!d_parent || !d_labels || !d_n_clusters || !d_work)
+    return am::fail(AM_EINVAL, "am_labels_from_parent: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = (int)n_points;
+  Work w;
+  carve(d_work, n_points, &w);
+  const int blocks = (n + 255) / 256;
+  compress_kernel<<<blocks, 256, 0, st>>>(d_parent, n, w.is_root);
+  AM_LAUNCHED("compress_kernel");
+  am::exclusive_scan_kernel<<<1, 1024, 0, st>>>(w.is_root, w.root_rank, n);
+  AM_LAUNCHED("exclusive_scan_kernel");
+  relabel_kernel<<<blocks, 256, 0, st>>>(d_parent, n, w.root_rank, d_labels, d_n_clusters);
+  AM_LAUNCHED("relabel_kernel");
+  // flatten the forest (parent[i] = root) so the next, larger eps starts from depth-1 trees
+  flatten_kernel<<<blocks, 256, 0, st>>>(d_parent, d_labels, w.is_root, n, w.root_of_label);
+  AM_LAUNCHED("flatten_kernel");
+  flatten2_kernel<<<blocks, 256, 0, st>>>(d_parent, d_labels, n, w.root_of_label);
+  AM_LAUNCHED("flatten2_kernel");
+  return AM_OK;
+}

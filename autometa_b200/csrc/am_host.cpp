@@ -1,0 +1,252 @@
+// Host-side pieces of libautometa_b200: error state, k-mer column table, FASTA
+// indexing, 2-bit packing, count work list.  No reference code is used; the
+// behaviour restated here is cited per function in include/autometa_b200.h.
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+#include "am_common.cuh"
+
+namespace am {
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+}  // namespace am
+
+extern "C" {
+
+int am_version(void) { return 100; }
+const char *am_last_error(void) { return am::g_err; }
+int64_t am_launch_count(void) { return am::g_launches.load(); }
+
+// ---- k-mer column table (kmers.py:56-89) ------------------------------------
+static int build_columns(int k, std::vector<uint32_t> &canon_sorted, std::vector<int32_t> &lut) {
+  if (k < 1 || k > 7) return am::fail(AM_EINVAL, "k must be in 1..7");
+  const uint32_t n = 1u << (2 * k);
+  std::vector<uint32_t> canon(n);
+  for (uint32_t c = 0; c < n; ++c) canon[c] = std::min(c, am::revcomp_code(c, k));
+  canon_sorted = canon;
+  std::sort(canon_sorted.begin(), canon_sorted.end());
+  canon_sorted.erase(std::unique(canon_sorted.begin(), canon_sorted.end()), canon_sorted.end());
+  lut.resize(n);
+  for (uint32_t c = 0; c < n; ++c)
+    lut[c] = (int32_t)(std::lower_bound(canon_sorted.begin(), canon_sorted.end(), canon[c]) -
+                       canon_sorted.begin());
+  return AM_OK;
+}
+
+int am_kmer_num_columns(int k) {
+  std::vector<uint32_t> cs;
+  std::vector<int32_t> lut;
+  int rc = build_columns(k, cs, lut);
+  if (rc) return rc;
+  return (int)cs.size();
+}
+
+int am_kmer_column_lut(int k, int32_t *h_lut) {
+  std::vector<uint32_t> cs;
+  std::vector<int32_t> lut;
+  int rc = build_columns(k, cs, lut);
+  if (rc) return rc;
+  memcpy(h_lut, lut.data(), lut.size() * sizeof(int32_t));
+  return AM_OK;
+}
+
+int am_kmer_column_names(int k, char *h_names) {
+  std::vector<uint32_t> cs;
+  std::vector<int32_t> lut;
+  int rc = build_columns(k, cs, lut);
+  if (rc) return rc;
+  static const char L[4] = {'A', 'T', 'C', 'G'};
+  for (size_t i = 0; i < cs.size(); ++i) {
+    char *s = h_names + i * (k + 1);
+    for (int j = 0; j < k; ++j) s[j] = L[(cs[i] >> (2 * (k - 1 - j))) & 3u];
+    s[k] = 0;
+  }
+  return AM_OK;
+}
+
+// ---- FASTA index (Bio.SeqIO.parse semantics used at kmers.py:143-148) ---------
+int am_fasta_index(const uint8_t *buf, int64_t len, uint8_t *seq_out, int64_t *offsets,
+                   int64_t *id_begin, int64_t *id_end, int64_t cap, int64_t *n_records) {
+  if (!buf || len < 0 || !n_records) return am::fail(AM_EINVAL, "am_fasta_index: bad args");
+  int64_t n = 0, out = 0, p = 0;
+  bool in_record = false;
+  while (p < len) {
+    const uint8_t *nl = (const uint8_t *)memchr(buf + p, '\n', (size_t)(len - p));
+    int64_t e = nl ? (int64_t)(nl - buf) : len;  // line = [p, e)
+    if (e > p && buf[p] == '>') {
+      if (n < cap) {
+        int64_t b = p + 1;
+        while (b < e && (buf[b] == ' ' || buf[b] == '\t')) ++b;  // str.split() skips leading blanks
+        int64_t t = b;
+        while (t < e && buf[t] != ' ' && buf[t] != '\t' && buf[t] != '\r' && buf[t] != '\v' && buf[t] != '\f') ++t;
+        id_begin[n] = b;
+        id_end[n] = t;
+        offsets[n] = out;
+      }
+      ++n;
+      in_record = true;
+    } else if (in_record) {
+      if (n <= cap) {
+        // Biopython: line.rstrip() per line, then remove ' ' and '\r' from the joined string
+        int64_t e2 = e;
+        while (e2 > p && (buf[e2 - 1] == ' ' || buf[e2 - 1] == '\t' || buf[e2 - 1] == '\r' ||
+                          buf[e2 - 1] == '\v' || buf[e2 - 1] == '\f'))
+          --e2;
+        for (int64_t q = p; q < e2; ++q) {
+          uint8_t c = buf[q];
+          if (c == ' ' || c == '\r') continue;
+          seq_out[out++] = c;
+        }
+      }
+    }
+    p = e + 1;
+  }
+  *n_records = n;
+  if (n > cap) return am::fail(AM_ECAPACITY, "am_fasta_index: record capacity too small");
+  offsets[n] = out;
+  return AM_OK;
+}
+
+// ---- packing -----------------------------------------------------------------
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+int am_pack_plan(const int64_t *offsets, int64_t n, int64_t *starts, int32_t *lengths,
+                 int64_t *total) {
+  if (!offsets || n < 0 || !starts || !lengths || !total) return am::fail(AM_EINVAL, "am_pack_plan: bad args");
+  int64_t pos = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t L = offsets[i + 1] - offsets[i];
+    if (L < 0 || L > 0x7fffffff) return am::fail(AM_EINVAL, "am_pack_plan: contig length out of range");
+    starts[i] = pos;
+    lengths[i] = (int32_t)L;
+    pos += round_up(L, AM_GROUP_BASES);
+  }
+  // trailing pad: kernels may read one 16-byte vector plus one word past a contig's end
+  *total = pos + 2 * AM_GROUP_BASES;
+  return AM_OK;
+}
+
+int64_t am_pack_code_words(int64_t total_packed_bases) { return total_packed_bases / 16; }
+int64_t am_pack_bitmap_words(int64_t total_packed_bases) {
+  return (total_packed_bases / AM_GROUP_BASES + 31) / 32 + 1;
+}
+
+static uint8_t g_b2c[256];
+static bool g_b2c_init = false;
+static void init_b2c() {
+  if (g_b2c_init) return;
+  for (int i = 0; i < 256; ++i) g_b2c[i] = 255;
+  g_b2c['A'] = 0; g_b2c['T'] = 1; g_b2c['C'] = 2; g_b2c['G'] = 3;
+  g_b2c_init = true;
+}
+
+int am_pack_host(const uint8_t *seq, const int64_t *offsets, int64_t n, const int64_t *starts,
+                 int64_t total, uint32_t *codes, uint32_t *bitmap, uint32_t *rank,
+                 uint64_t *exc_mask, int64_t exc_capacity, int64_t *n_exc, int n_threads) {
+  if (!seq || !offsets || !starts || !codes || !bitmap || !rank || !n_exc)
+    return am::fail(AM_EINVAL, "am_pack_host: bad args");
+  init_b2c();
+  const int64_t n_groups = total / AM_GROUP_BASES;
+  const int64_t n_bw = am_pack_bitmap_words(total);
+  memset(codes, 0, (size_t)am_pack_code_words(total) * sizeof(uint32_t));
+  memset(bitmap, 0, (size_t)n_bw * sizeof(uint32_t));
+  // full-size temporary masks only for flagged groups: collect per thread
+  if (n_threads < 1) n_threads = 1;
+  n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n));
+  struct Exc { int64_t group; uint64_t mask; };
+  std::vector<std::vector<Exc>> found(n_threads);
+  // contiguous contig ranges balanced by bases
+  std::vector<int64_t> cut(n_threads + 1, n);
+  cut[0] = 0;
+  {
+    int64_t tot = offsets[n] - offsets[0];
+    int t = 1;
+    for (int64_t i = 0; i < n && t < n_threads; ++i)
+      while (t < n_threads && offsets[i] - offsets[0] >= tot * t / n_threads) cut[t++] = i;
+  }
+  auto work = [&](int t) {
+    auto &ex = found[t];
+    for (int64_t i = cut[t]; i < cut[t + 1]; ++i) {
+      const uint8_t *s = seq + offsets[i];
+      const int64_t L = offsets[i + 1] - offsets[i];
+      const int64_t g0 = starts[i] / AM_GROUP_BASES;
+      for (int64_t b = 0; b < L; b += AM_GROUP_BASES) {
+        const int64_t m = std::min<int64_t>(AM_GROUP_BASES, L - b);
+        uint32_t w[4] = {0, 0, 0, 0};
+        uint64_t bad = 0;
+        for (int64_t j = 0; j < m; ++j) {
+          uint8_t c = g_b2c[s[b + j]];
+          if (c == 255) { bad |= 1ull << j; c = 0; }
+          w[j >> 4] |= (uint32_t)c << (2 * (j & 15));
+        }
+        const int64_t g = g0 + b / AM_GROUP_BASES;
+        uint32_t *dst = codes + g * 4;
+        dst[0] = w[0]; dst[1] = w[1]; dst[2] = w[2]; dst[3] = w[3];
+        if (bad) ex.push_back({g, bad});
+      }
+    }
+  };
+  if (n_threads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+    for (auto &x : th) x.join();
+  }
+  int64_t cnt = 0;
+  for (auto &v : found) cnt += (int64_t)v.size();
+  *n_exc = cnt;
+  if (cnt > exc_capacity) return am::fail(AM_ECAPACITY, "am_pack_host: exception capacity too small");
+  int64_t r = 0;
+  for (auto &v : found)  // thread ranges are in contig order, groups ascending
+    for (auto &e : v) {
+      bitmap[e.group >> 5] |= 1u << (e.group & 31);
+      exc_mask[r++] = e.mask;
+    }
+  uint32_t acc = 0;
+  for (int64_t w = 0; w < n_bw; ++w) {
+    rank[w] = acc;
+    acc += (uint32_t)__builtin_popcount(bitmap[w]);
+  }
+  (void)n_groups;
+  return AM_OK;
+}
+
+// ---- count work list -----------------------------------------------------------
+int am_count_plan(const int32_t *lengths, int64_t n, int k, int32_t max_item_bases,
+                  int32_t *items, int64_t item_cap, int64_t *n_items, int32_t *multi_rows,
+                  int64_t multi_cap, int64_t *n_multi) {
+  if (!lengths || !n_items || !n_multi || k < 1 || k > 7 || max_item_bases < AM_TILE_BASES ||
+      max_item_bases % AM_TILE_BASES)
+    return am::fail(AM_EINVAL, "am_count_plan: bad args");
+  if (n > 0x7fffffff) return am::fail(AM_EINVAL, "am_count_plan: too many contigs");
+  int64_t ni = 0, nm = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t nwin = (int64_t)lengths[i] - k;  // kmers.py:186 max_length = L - k
+    if (nwin <= 0) {
+      // still emit an empty item so the kernel writes the all-zero row
+      if (ni < item_cap) { int32_t *it = items + 4 * ni; it[0] = (int32_t)i; it[1] = 0; it[2] = 0; it[3] = 0; }
+      ++ni;
+      continue;
+    }
+    const bool multi = nwin > max_item_bases;
+    if (multi) { if (nm < multi_cap) multi_rows[nm] = (int32_t)i; ++nm; }
+    for (int64_t w = 0; w < nwin; w += max_item_bases) {
+      if (ni < item_cap) {
+        int32_t *it = items + 4 * ni;
+        it[0] = (int32_t)i;
+        it[1] = (int32_t)w;
+        it[2] = (int32_t)std::min<int64_t>(max_item_bases, nwin - w);
+        it[3] = multi ? 1 : 0;
+      }
+      ++ni;
+    }
+  }
+  *n_items = ni;
+  *n_multi = nm;
+  if (ni > item_cap || nm > multi_cap) return am::fail(AM_ECAPACITY, "am_count_plan: capacity too small");
+  return AM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+// Kernel 2 — fused row-wise log-ratio normalisation (sm_100a).
+//
+// Replaces autometa_clr (autometa/common/kmers.py:333-373) and the scikit-bio
+// multiplicative_replacement + clr / ilr calls (kmers.py:418-421).
+// One warp per output row.  Counts are small integers, so log(n) comes from a
+// shared-memory table of fp64 logs (built per CTA with the same log() the slow
+// path uses, so both paths give identical bits); only counts beyond the table
+// call log().  Row/column drops of am_clr (kmers.py:369) are fused as gathers.
+// Column sums of the output (the PCA mean, sklearn _pca.py:560) are produced
+// deterministically: per-CTA partials in d_work, reduced in fixed order.
+#include "am_common.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int LOGT = 2048;   // table holds log(1..LOGT)
+constexpr int NWARPS = 8;
+constexpr int MAXD = 8192;   // 4^7 / 2
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double log_int(const double *logt, int n) {
+  // n >= 1
+  return n <= LOGT ? logt[n - 1] : log((double)n);
+}
+
+// METHOD 0: am_clr   out_j = log(x_j + 1) - mean_j log(x_j + 1)
+// METHOD 1: clr      p = x/S; q = (p==0 ? delta : p (1 - z delta)); q /= sum q; log; centre
+template <int METHOD>
+__global__ void __launch_bounds__(NWARPS * 32)
+normalize_kernel(const int32_t *__restrict__ counts, int64_t n_out, int D,
+                 const int64_t *__restrict__ row_index, const int32_t *__restrict__ col_index,
+                 int Dk, double *__restrict__ out, double *__restrict__ partials) {
+  extern __shared__ double sm[];
+  double *logt = sm;               // LOGT
+  double *csum = sm + LOGT;        // NWARPS * Dk (only when partials != nullptr)
+  for (int i = threadIdx.x; i < LOGT; i += blockDim.x) logt[i] = log((double)(i + 1));
+  if (partials)
+    for (int i = threadIdx.x; i < NWARPS * Dk; i += blockDim.x) csum[i] = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *mysum = csum + warp * Dk;
+  const int64_t wstride = (int64_t)gridDim.x * NWARPS;
+  for (int64_t r = (int64_t)blockIdx.x * NWARPS + warp; r < n_out; r += wstride) {
+    const int64_t src = row_index ? row_index[r] : r;
+    const int32_t *x = counts + src * D;
+    double *o = out + r * Dk;
+    if (METHOD == 0) {
+      double s = 0.0;
+      for (int j = lane; j < Dk; j += 32) {
+        const int c = col_index ? col_index[j] : j;
+        s += log_int(logt, __ldg(x + c) + 1);
+      }
+      const double mean = warp_sum(s) / (double)Dk;
+      for (int j = lane; j < Dk; j += 32) {
+        const int c = col_index ? col_index[j] : j;
+        const double v = log_int(logt, __ldg(x + c) + 1) - mean;
+        __stcs(o + j, v);
+        if (partials) mysum[j] += v;
+      }
+    } else {
+      // closure + multiplicative replacement (delta = 1/D^2 over the retained columns)
+      double S = 0.0;
+      int z = 0;
+      for (int j = lane; j < Dk; j += 32) {
+        const int c = col_index ? col_index[j] : j;
+        const int v = __ldg(x + c);
+        S += (double)v;
+        z += (v == 0);
+      }
+      S = warp_sum(S);
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) z += __shfl_xor_sync(FULL, z, o2);
+      const double delta = (1.0 / (double)Dk) * (1.0 / (double)Dk);
+      const double scale = 1.0 - (double)z * delta;
+      // second closure inside clr(): sum of q
+      double Q = 0.0;
+      for (int j = lane; j < Dk; j += 32) {
+        const int c = col_index ? col_index[j] : j;
+        const int v = __ldg(x + c);
+        Q += v == 0 ? delta : scale * ((double)v / S);
+      }
+      Q = warp_sum(Q);
+      const double lzero = log(delta / Q);
+      const double lscale = log(scale / S / Q);
+      double sl = 0.0;
+      for (int j = lane; j < Dk; j += 32) {
+        const int c = col_index ? col_index[j] : j;
+        const int v = __ldg(x + c);
+        sl += v == 0 ? lzero : (log_int(logt, v) + lscale);
+      }
+      const double mean = warp_sum(sl) / (double)Dk;
+      for (int j = lane; j < Dk; j += 32) {
+        const int c = col_index ? col_index[j] : j;
+        const int v = __ldg(x + c);
+        const double l = (v == 0 ? lzero : (log_int(logt, v) + lscale)) - mean;
+        __stcs(o + j, l);
+        if (partials) mysum[j] += l;
+      }
+    }
+  }
+  if (partials) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < Dk; j += blockDim.x) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NWARPS; ++w) s += csum[w * Dk + j];
+      partials[(int64_t)blockIdx.x * Dk + j] = s;
+    }
+  }
+}
+
+// ilr: l_j as in clr (before centring; centring cancels), then
+//   out_{i-1} = sqrt(i/(i+1)) * (mean(l[0:i]) - l[i]),  i = 1..Dk-1
+__global__ void __launch_bounds__(NWARPS * 32)
+ilr_kernel(const int32_t *__restrict__ counts, int64_t n_out, int D,
+           const int64_t *__restrict__ row_index, const int32_t *__restrict__ col_index, int Dk,
+           double *__restrict__ out) {
+  extern __shared__ double sm[];
+  double *logt = sm;  // LOGT
+  const int chunk = (Dk + 31) / 32;
+  const int pitch = Dk + Dk / 16 + 2;  // padded: slot(j) = j + j/16
+  double *lbuf = sm + LOGT + (threadIdx.x >> 5) * 2 * pitch;
+  double *obuf = lbuf + pitch;
+  for (int i = threadIdx.x; i < LOGT; i += blockDim.x) logt[i] = log((double)(i + 1));
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * NWARPS;
+  for (int64_t r = (int64_t)blockIdx.x * NWARPS + warp; r < n_out; r += wstride) {
+    const int64_t src = row_index ? row_index[r] : r;
+    const int32_t *x = counts + src * D;
+    double S = 0.0;
+    int z = 0;
+    for (int j = lane; j < Dk; j += 32) {
+      const int c = col_index ? col_index[j] : j;
+      const int v = __ldg(x + c);
+      S += (double)v;
+      z += (v == 0);
+    }
+    S = warp_sum(S);
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) z += __shfl_xor_sync(FULL, z, o2);
+    const double delta = (1.0 / (double)Dk) * (1.0 / (double)Dk);
+    const double scale = 1.0 - (double)z * delta;
+    double Q = 0.0;
+    for (int j = lane; j < Dk; j += 32) {
+      const int c = col_index ? col_index[j] : j;
+      const int v = __ldg(x + c);
+      Q += v == 0 ? delta : scale * ((double)v / S);
+    }
+    Q = warp_sum(Q);
+    const double lzero = log(delta / Q);
+    const double lscale = log(scale / S / Q);
+    for (int j = lane; j < Dk; j += 32) {
+      const int c = col_index ? col_index[j] : j;
+      const int v = __ldg(x + c);
+      lbuf[j + (j >> 4)] = v == 0 ? lzero : (log_int(logt, v) + lscale);
+    }
+    __syncwarp();
+    // contiguous chunk per lane, exclusive prefix of chunk sums across the warp
+    const int j0 = lane * chunk;
+    const int j1 = min(j0 + chunk, Dk);
+    double cs = 0.0;
+    for (int j = j0; j < j1; ++j) cs += lbuf[j + (j >> 4)];
+    double incl = cs;
+#pragma unroll
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+      const double t = __shfl_up_sync(FULL, incl, o2);
+      if (lane >= o2) incl += t;
+    }
+    double pre = incl - cs;  // sum of l[0:j0]
+    for (int j = j0; j < j1; ++j) {
+      const double l = lbuf[j + (j >> 4)];
+      if (j >= 1) {
+        const double i = (double)j;
+        const int oj = j - 1;
+        obuf[oj + (oj >> 4)] = sqrt(i / (i + 1.0)) * (pre / i - l);
+      }
+      pre += l;
+    }
+    __syncwarp();
+    double *o = out + r * (int64_t)(Dk - 1);
+    for (int j = lane; j < Dk - 1; j += 32) __stcs(o + j, obuf[j + (j >> 4)]);
+    __syncwarp();
+  }
+}
+
+__global__ void reduce_partials_kernel(const double *__restrict__ partials, int n_parts, int D,
+                                       double *__restrict__ colsum) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  double s = 0.0;
+  for (int p = 0; p < n_parts; ++p) s += partials[(int64_t)p * D + j];
+  colsum[j] += s;
+}
+
+int norm_grid(int64_t n_rows) {
+  int64_t g = (int64_t)am::num_sms() * 4;
+  const int64_t need = (n_rows + NWARPS - 1) / NWARPS;
+  if (g > need) g = need;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace
+
+extern "C" int64_t am_normalize_work_bytes(int D) {
+  return (int64_t)am::num_sms() * 4 * D * (int64_t)sizeof(double);
+}
+
+extern "C" int am_normalize(const int32_t *d_counts, int64_t n_rows_out, int D,
+                            const int64_t *d_row_index, const int32_t *d_col_index, int D_keep,
+                            int method, double *d_out, double *d_colsum, void *d_work,
+                            void *stream) {
+  if (D < 1 || D > MAXD || D_keep < 1 || D_keep > D) return am::fail(AM_EINVAL, "am_normalize: bad D");
+  if (method < 0 || method > 2) return am::fail(AM_EINVAL, "am_normalize: bad method");
+  if (n_rows_out == 0) return AM_OK;
+  if (!d_counts || !d_out || n_rows_out < 0) return am::fail(AM_EINVAL, "am_normalize: null pointer");
+  if (d_colsum && !d_work) return am::fail(AM_EINVAL, "am_normalize: d_colsum needs d_work");
+  if (method == AM_NORM_ILR && (d_colsum || D_keep < 2))
+    return am::fail(AM_EINVAL, "am_normalize: ilr does not produce column sums / needs D>=2");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = norm_grid(n_rows_out);
+  if (method == AM_NORM_ILR) {
+    const int pitch = D_keep + D_keep / 16 + 2;
+    const size_t smem = (size_t)(LOGT + NWARPS * 2 * pitch) * sizeof(double);
+    if (smem > 48 * 1024)
+      AM_CUDA(cudaFuncSetAttribute(ilr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 227 * 1024) return am::fail(AM_EINVAL, "am_normalize: ilr row too wide for shared memory");
+    ilr_kernel<<<grid, NWARPS * 32, smem, st>>>(d_counts, n_rows_out, D, d_row_index, d_col_index,
+                                                D_keep, d_out);
+    AM_LAUNCHED("ilr_kernel");
+    return AM_OK;
+  }
+  double *partials = d_colsum ? (double *)d_work : nullptr;
+  const size_t smem = (size_t)(LOGT + (partials ? NWARPS * D_keep : 0)) * sizeof(double);
+  if (smem > 227 * 1024) return am::fail(AM_EINVAL, "am_normalize: row too wide for fused column sums");
+  if (method == AM_NORM_AM_CLR) {
+    if (smem > 48 * 1024)
+      AM_CUDA(cudaFuncSetAttribute(normalize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    normalize_kernel<0><<<grid, NWARPS * 32, smem, st>>>(d_counts, n_rows_out, D, d_row_index,
+                                                         d_col_index, D_keep, d_out, partials);
+  } else {
+    if (smem > 48 * 1024)
+      AM_CUDA(cudaFuncSetAttribute(normalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    normalize_kernel<1><<<grid, NWARPS * 32, smem, st>>>(d_counts, n_rows_out, D, d_row_index,
+                                                         d_col_index, D_keep, d_out, partials);
+  }
+  AM_LAUNCHED("normalize_kernel");
+  if (partials) {
+    reduce_partials_kernel<<<(D_keep + 127) / 128, 128, 0, st>>>(partials, grid, D_keep, d_colsum);
+    AM_LAUNCHED("reduce_partials_kernel");
+  }
+  return AM_OK;
+}

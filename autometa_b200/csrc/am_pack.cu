@@ -1,0 +1,161 @@
+// Device packer: ASCII contig bytes already in HBM -> 2-bit codes + exception
+// structure (layout documented in include/autometa_b200.h).  The k-mer kernels
+// count upper-case A/C/G/T only (autometa/common/kmers.py:197-204: a window counts
+// iff the k-mer string or its reverse complement is a key of the ACGT dictionary),
+// so every other byte becomes code 0 + an exception bit.
+// One thread per 64-base group; bytes are converted four at a time with byte-SIMD
+// compares and multiply-gathers.
+#include "am_common.cuh"
+#include "am_scan.cuh"
+
+namespace {
+
+__device__ __forceinline__ int find_contig(const int64_t *__restrict__ starts, int64_t n, int64_t pos) {
+  // last i with starts[i] <= pos
+  int64_t lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) >> 1;
+    if (__ldg(starts + mid) <= pos) lo = mid; else hi = mid - 1;
+  }
+  return (int)lo;
+}
+
+// convert 4 ASCII bytes: returns 8 bits of codes (byte i -> bits 2i..2i+1) and 4 invalid bits
+__device__ __forceinline__ void conv4(uint32_t w, uint32_t &code8, uint32_t &bad4) {
+  const uint32_t ok = __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x43434343u) |
+                      __vcmpeq4(w, 0x47474747u) | __vcmpeq4(w, 0x54545454u);
+  // (b >> 1) & 3: A->0 C->1 T->2 G->3; swap the two bits -> A0 T1 C2 G3
+  const uint32_t x = (w >> 1) & 0x03030303u;
+  uint32_t y = ((x & 0x01010101u) << 1) | ((x >> 1) & 0x01010101u);
+  y &= ok;  // invalid bytes are stored as code 0
+  code8 = (y * 0x01041040u) >> 24;
+  bad4 = (((~ok) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu;
+}
+
+__device__ __forceinline__ void pack_group(const uint8_t *__restrict__ seq, int64_t src, int nbases,
+                                           uint32_t (&codes)[4], uint64_t &bad) {
+  // read 17 aligned words covering [src, src+64)
+  const uint32_t *base = reinterpret_cast<const uint32_t *>(seq + (src & ~(int64_t)3));
+  const int sh = (int)(src & 3) * 8;
+  uint32_t prev = __ldg(base);
+  bad = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t c32 = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int wi = q * 4 + r;
+      const uint32_t next = __ldg(base + wi + 1);
+      const uint32_t w = __funnelshift_r(prev, next, sh);
+      prev = next;
+      uint32_t c8, b4;
+      conv4(w, c8, b4);
+      c32 |= c8 << (8 * r);
+      bad |= (uint64_t)b4 << (4 * wi);
+    }
+    codes[q] = c32;
+  }
+  if (nbases < 64) {
+    // bytes past the contig end belong to the next record: clear them
+    const uint64_t keep = nbases <= 0 ? 0ull : ((1ull << nbases) - 1ull);
+    bad &= keep;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int nb = nbases - 16 * q;
+      const uint32_t m = nb >= 16 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (2 * nb)) - 1u));
+      codes[q] &= m;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pack_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ offsets,
+            const int64_t *__restrict__ starts, int64_t n_contigs, int64_t n_groups,
+            uint4 *__restrict__ codes4, uint32_t *__restrict__ bitmap, uint32_t *__restrict__ pop) {
+  // n_groups is padded by the launcher to a multiple of 32 so every warp writes one bitmap word
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t c[4] = {0, 0, 0, 0};
+  uint64_t bad = 0;
+  if (g < n_groups && n_contigs > 0) {
+    const int64_t pos = g * AM_GROUP_BASES;
+    const int i = find_contig(starts, n_contigs, pos);
+    const int64_t off = __ldg(offsets + i);
+    const int64_t L = __ldg(offsets + i + 1) - off;
+    const int64_t local = pos - __ldg(starts + i);
+    if (local < L) {
+      const int64_t rem = L - local;
+      pack_group(seq, off + local, rem > 64 ? 64 : (int)rem, c, bad);
+    }
+  }
+  if (g < n_groups) codes4[g] = make_uint4(c[0], c[1], c[2], c[3]);
+  const uint32_t ball = __ballot_sync(0xffffffffu, bad != 0);
+  if ((threadIdx.x & 31) == 0) {
+    const int64_t w = g >> 5;
+    bitmap[w] = ball;
+    pop[w] = __popc(ball);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pack_mask_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ offsets,
+                 const int64_t *__restrict__ starts, int64_t n_contigs, int64_t n_groups,
+                 const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ rank,
+                 int64_t n_words, uint64_t *__restrict__ exc_mask, int64_t cap,
+                 int64_t *__restrict__ n_exc) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g == 0) n_exc[0] = (int64_t)rank[n_words - 1];
+  if (g >= n_groups) return;
+  const uint32_t bw = __ldg(bitmap + (g >> 5));
+  if (!((bw >> (g & 31)) & 1u)) return;
+  const int64_t r = (int64_t)__ldg(rank + (g >> 5)) + __popc(bw & ((1u << (g & 31)) - 1u));
+  if (r >= cap) return;
+  const int64_t pos = g * AM_GROUP_BASES;
+  const int i = find_contig(starts, n_contigs, pos);
+  const int64_t off = __ldg(offsets + i);
+  const int64_t L = __ldg(offsets + i + 1) - off;
+  const int64_t local = pos - __ldg(starts + i);
+  uint32_t c[4];
+  uint64_t bad = 0;
+  const int64_t rem = L - local;
+  pack_group(seq, off + local, rem > 64 ? 64 : (int)rem, c, bad);
+  exc_mask[r] = bad;
+}
+
+}  // namespace
+
+extern "C" int am_pack_device(const uint8_t *d_seq, const int64_t *d_offsets, const int64_t *d_starts,
+                              int64_t n_contigs, int64_t total_packed_bases, uint32_t *d_codes,
+                              uint32_t *d_exc_bitmap, uint32_t *d_exc_rank, uint64_t *d_exc_mask,
+                              int64_t exc_capacity, int64_t *d_n_exc, void *d_work, void *stream) {
+  if (n_contigs < 0 || total_packed_bases < 0 || total_packed_bases % AM_GROUP_BASES)
+    return am::fail(AM_EINVAL, "am_pack_device: bad sizes");
+  if (!d_seq || !d_offsets || !d_starts || !d_codes || !d_exc_bitmap || !d_exc_rank || !d_n_exc || !d_work)
+    return am::fail(AM_EINVAL, "am_pack_device: null pointer");
+  if (((uintptr_t)d_seq & 3) || ((uintptr_t)d_codes & 15))
+    return am::fail(AM_EINVAL, "am_pack_device: d_seq must be 4-byte and d_codes 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_groups = total_packed_bases / AM_GROUP_BASES;
+  const int64_t n_words = am_pack_bitmap_words(total_packed_bases);
+  if (n_words > 0x7fffffff) return am::fail(AM_EINVAL, "am_pack_device: assembly too large for one call");
+  // d_work: n_words uint32 popcounts
+  uint32_t *pop = (uint32_t *)d_work;
+  AM_CUDA(cudaMemsetAsync(d_exc_bitmap, 0, (size_t)n_words * 4, st));
+  AM_CUDA(cudaMemsetAsync(pop, 0, (size_t)n_words * 4, st));
+  const int64_t threads = (n_groups + 31) / 32 * 32;
+  const unsigned blocks = (unsigned)((threads + 255) / 256);
+  if (blocks) {
+    pack_kernel<<<blocks, 256, 0, st>>>(d_seq, d_offsets, d_starts, n_contigs, n_groups,
+                                        reinterpret_cast<uint4 *>(d_codes), d_exc_bitmap, pop);
+    AM_LAUNCHED("pack_kernel");
+  }
+  // rank[w] = flagged groups before bitmap word w; rank needs n_words + 1 slots
+  am::exclusive_scan_kernel<<<1, 1024, 0, st>>>(pop, d_exc_rank, (int)(n_words - 1));
+  AM_LAUNCHED("exclusive_scan_kernel");
+  if (blocks) {
+    pack_mask_kernel<<<blocks, 256, 0, st>>>(d_seq, d_offsets, d_starts, n_contigs, n_groups,
+                                             d_exc_bitmap, d_exc_rank, n_words, d_exc_mask,
+                                             exc_capacity, d_n_exc);
+    AM_LAUNCHED("pack_mask_kernel");
+  }
+  return AM_OK;
+}

@@ -1,0 +1,302 @@
+// Kernel 3 (fp64 baseline path) — column sums, centred Gram, projection.
+//
+// Restates sklearn 1.9 PCA(svd_solver="covariance_eigh") as called from
+// autometa/common/kmers.py:605: mean (_pca.py:560), covariance via the Gram
+// matrix (_pca.py:604-610) and the transform X @ Vt.T - mean @ Vt.T
+// (sklearn/decomposition/_base.py:151-159).  The Gram here is the fp64 CUDA-core
+// version: exact-enough reference for the tensor-core (tcgen05) Gram and the
+// fallback for shapes the tensor path does not cover.  All reductions are
+// deterministic (fixed split order), so multi-GPU results do not depend on timing.
+#include "am_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- column sums
+constexpr int CS_ROWS = 8;  // row lanes per CTA (blockDim = (128, CS_ROWS))
+
+__global__ void colsum_partial_kernel(const double *__restrict__ X, int64_t n, int D,
+                                      double *__restrict__ partials) {
+  // grid.x = column blocks of 128, grid.y = row splits
+  __shared__ double red[CS_ROWS][128];
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  double s = 0.0;
+  if (c < D)
+    for (int64_t r = (int64_t)blockIdx.y * CS_ROWS + threadIdx.y; r < n; r += (int64_t)gridDim.y * CS_ROWS)
+      s += __ldg(X + r * D + c);
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < D) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < CS_ROWS; ++i) t += red[i][threadIdx.x];
+    partials[(int64_t)blockIdx.y * D + c] = t;
+  }
+}
+
+__global__ void colsum_reduce_kernel(const double *__restrict__ partials, int n_parts, int D,
+                                     double *__restrict__ colsum) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  double s = 0.0;
+  for (int p = 0; p < n_parts; ++p) s += partials[(int64_t)p * D + j];
+  colsum[j] += s;
+}
+
+int colsum_splits(int64_t n) {
+  int64_t s = (int64_t)am::num_sms() * 2;
+  const int64_t need = (n + CS_ROWS - 1) / CS_ROWS;
+  if (s > need) s = need;
+  return (int)(s < 1 ? 1 : s);
+}
+
+// ---------------------------------------------------------------- Gram (fp64)
+constexpr int GT = 128;  // output tile edge
+constexpr int GK = 16;   // rows of X per pipeline stage
+
+__global__ void __launch_bounds__(256, 1)
+gram_kernel(const double *__restrict__ X, int64_t n, int D, const double *__restrict__ mu,
+            double *__restrict__ partials, int64_t rows_per_split, int T) {
+  extern __shared__ double sm[];
+  double(*As)[GK][GT] = reinterpret_cast<double(*)[GK][GT]>(sm);
+  double(*Bs)[GK][GT] = reinterpret_cast<double(*)[GK][GT]>(sm + 2 * GK * GT);
+  const int ntiles = T * (T + 1) / 2;
+  const int tile = blockIdx.x % ntiles;
+  const int split = blockIdx.x / ntiles;
+  int ti = 0, rem = tile;
+  while (rem >= T - ti) { rem -= T - ti; ++ti; }
+  const int tj = ti + rem;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int64_t row_begin = (int64_t)split * rows_per_split;
+  const int64_t row_end = min(n, row_begin + rows_per_split);
+  // loader mapping: element q = tid + 256*h -> (kr = q / 128, c = q % 128); c is fixed per thread
+  const int lc = tid & 127;
+  const int lk0 = tid >> 7;  // 0 or 1; kr = lk0 + 2*h
+  const int colA = ti * GT + lc, colB = tj * GT + lc;
+  const bool okA = colA < D, okB = colB < D;
+  const double muA = okA ? __ldg(mu + colA) : 0.0;
+  const double muB = okB ? __ldg(mu + colB) : 0.0;
+
+  double acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+
+  double ra[8], rb[8];
+  auto load_regs = [&](int64_t r0) {
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const int64_t r = r0 + lk0 + 2 * h;
+      const bool okr = r < row_end;
+      ra[h] = (okr && okA) ? __ldg(X + r * D + colA) - muA : 0.0;
+      rb[h] = (okr && okB) ? __ldg(X + r * D + colB) - muB : 0.0;
+    }
+  };
+  auto store_regs = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      As[buf][lk0 + 2 * h][lc] = ra[h];
+      Bs[buf][lk0 + 2 * h][lc] = rb[h];
+    }
+  };
+
+  if (row_begin < row_end) {
+    load_regs(row_begin);
+    store_regs(0);
+    __syncthreads();
+    int buf = 0;
+    for (int64_t r0 = row_begin; r0 < row_end; r0 += GK) {
+      const bool more = r0 + GK < row_end;
+      if (more) load_regs(r0 + GK);
+#pragma unroll
+      for (int k = 0; k < GK; ++k) {
+        double a[8], b[8];
+        const double2 *ap = reinterpret_cast<const double2 *>(&As[buf][k][ty * 8]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const double2 v = ap[i];
+          a[2 * i] = v.x;
+          a[2 * i + 1] = v.y;
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const double2 v = *reinterpret_cast<const double2 *>(&Bs[buf][k][m * 32 + tx * 2]);
+          b[2 * m] = v.x;
+          b[2 * m + 1] = v.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      }
+      if (more) store_regs(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  double *P = partials + ((int64_t)split * ntiles + tile) * (GT * GT);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+      *reinterpret_cast<double2 *>(P + (ty * 8 + i) * GT + m * 32 + tx * 2) =
+          make_double2(acc[i][2 * m], acc[i][2 * m + 1]);
+}
+
+__global__ void gram_reduce_kernel(const double *__restrict__ partials, int n_splits, int T, int D,
+                                   double *__restrict__ G) {
+  const int ntiles = T * (T + 1) / 2;
+  const int tile = blockIdx.x;
+  int ti = 0, rem = tile;
+  while (rem >= T - ti) { rem -= T - ti; ++ti; }
+  const int tj = ti + rem;
+  for (int e = threadIdx.x; e < GT * GT; e += blockDim.x) {
+    const int r = e / GT, c = e % GT;
+    const int gi = ti * GT + r, gj = tj * GT + c;
+    if (gi >= D || gj >= D) continue;
+    double s = 0.0;
+    for (int sp = 0; sp < n_splits; ++sp) s += partials[((int64_t)sp * ntiles + tile) * (GT * GT) + e];
+    G[(int64_t)gi * D + gj] += s;
+    if (ti != tj) G[(int64_t)gj * D + gi] += s;
+  }
+}
+
+void gram_shape(int D, int64_t n, int *T, int *S, int64_t *rows_per_split) {
+  *T = (D + GT - 1) / GT;
+  const int ntiles = *T * (*T + 1) / 2;
+  int s = am::num_sms() / ntiles;
+  if (s < 1) s = 1;
+  int64_t rps = (n + s - 1) / s;
+  rps = (rps + GK - 1) / GK * GK;
+  if (rps < GK) rps = GK;
+  *rows_per_split = rps;
+  *S = s;
+}
+
+// ---------------------------------------------------------------- projection
+constexpr int PM = 128;  // rows per CTA
+constexpr int PN = 64;   // components per CTA pass
+constexpr int PK = 16;
+constexpr int PA_PITCH = PM + 2;
+constexpr int PB_PITCH = PN + 2;
+
+__global__ void __launch_bounds__(256)
+project_kernel(const double *__restrict__ X, int64_t n, int D, const double *__restrict__ mu,
+               const double *__restrict__ comps, int P, double *__restrict__ scores) {
+  __shared__ double As[PK][PA_PITCH];
+  __shared__ double Bs[PK][PB_PITCH];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads; thread tile 8 rows x 4 comps
+  const int64_t row0 = (int64_t)blockIdx.x * PM;
+  const int p0 = blockIdx.y * PN;
+  double acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  // loaders: A chunk 128 rows x 16 cols: q = tid + 256*h (h<8): r = q / 16, kk = q % 16
+  //          B chunk 64 comps x 16 cols: q = tid + 256*h (h<4): p = q / 16, kk = q % 16
+  const int lkk = tid & 15;
+  for (int k0 = 0; k0 < D; k0 += PK) {
+    const int col = k0 + lkk;
+    const bool okc = col < D;
+    const double m = okc ? __ldg(mu + col) : 0.0;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const int r = (tid >> 4) + 16 * h;
+      const int64_t gr = row0 + r;
+      As[lkk][r] = (okc && gr < n) ? __ldg(X + gr * D + col) - m : 0.0;
+    }
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int p = (tid >> 4) + 16 * h;
+      const int gp = p0 + p;
+      Bs[lkk][p] = (okc && gp < P) ? __ldg(comps + (int64_t)gp * D + col) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PK; ++k) {
+      double a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[k][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t gr = row0 + ty * 8 + i;
+    if (gr >= n) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gp = p0 + tx + 16 * j;
+      if (gp < P) scores[gr * P + gp] = acc[i][j];
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int64_t am_colsum_work_bytes(int D) {
+  return (int64_t)am::num_sms() * 2 * D * (int64_t)sizeof(double);
+}
+
+extern "C" int am_colsum(const double *d_X, int64_t n_rows, int D, double *d_colsum, void *d_work,
+                         void *stream) {
+  if (D < 1 || n_rows < 0) return am::fail(AM_EINVAL, "am_colsum: bad shape");
+  if (n_rows == 0) return AM_OK;
+  if (!d_X || !d_colsum || !d_work) return am::fail(AM_EINVAL, "am_colsum: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = colsum_splits(n_rows);
+  dim3 grid((D + 127) / 128, S), block(128, CS_ROWS);
+  colsum_partial_kernel<<<grid, block, 0, st>>>(d_X, n_rows, D, (double *)d_work);
+  AM_LAUNCHED("colsum_partial_kernel");
+  colsum_reduce_kernel<<<(D + 127) / 128, 128, 0, st>>>((const double *)d_work, S, D, d_colsum);
+  AM_LAUNCHED("colsum_reduce_kernel");
+  return AM_OK;
+}
+
+extern "C" int64_t am_gram_work_bytes(int D) {
+  const int T = (D + GT - 1) / GT;
+  const int ntiles = T * (T + 1) / 2;
+  int s = am::num_sms() / ntiles;
+  if (s < 1) s = 1;
+  return (int64_t)s * ntiles * GT * GT * (int64_t)sizeof(double);
+}
+
+extern "C" int am_gram(const double *d_X, int64_t n_rows, int D, const double *d_mu, double *d_G,
+                       void *d_work, void *stream) {
+  if (D < 1 || n_rows < 0) return am::fail(AM_EINVAL, "am_gram: bad shape");
+  if (n_rows == 0) return AM_OK;
+  if (!d_X || !d_mu || !d_G || !d_work) return am::fail(AM_EINVAL, "am_gram: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int T, S;
+  int64_t rps;
+  gram_shape(D, n_rows, &T, &S, &rps);
+  const int ntiles = T * (T + 1) / 2;
+  const size_t smem = (size_t)4 * GK * GT * sizeof(double);
+  AM_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gram_kernel<<<ntiles * S, 256, smem, st>>>(d_X, n_rows, D, d_mu, (double *)d_work, rps, T);
+  AM_LAUNCHED("gram_kernel");
+  gram_reduce_kernel<<<ntiles, 256, 0, st>>>((const double *)d_work, S, T, D, d_G);
+  AM_LAUNCHED("gram_reduce_kernel");
+  return AM_OK;
+}
+
+extern "C" int am_project(const double *d_X, int64_t n_rows, int D, const double *d_mu,
+                          const double *d_comps, int P, double *d_scores, void *stream) {
+  if (D < 1 || P < 1 || n_rows < 0) return am::fail(AM_EINVAL, "am_project: bad shape");
+  if (n_rows == 0) return AM_OK;
+  if (!d_X || !d_mu || !d_comps || !d_scores) return am::fail(AM_EINVAL, "am_project: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((n_rows + PM - 1) / PM), (P + PN - 1) / PN);
+  project_kernel<<<grid, 256, 0, st>>>(d_X, n_rows, D, d_mu, d_comps, P, d_scores);
+  AM_LAUNCHED("project_kernel");
+  return AM_OK;
+}

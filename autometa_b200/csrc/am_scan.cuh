@@ -1,0 +1,58 @@
+// Single-CTA exclusive scan shared by the packer and the DBSCAN step.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace am {
+
+// single-CTA exclusive scan (n up to a few million): out[i] = sum_{j<i} in[j]; out[n] = total
+static __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const unsigned *__restrict__ in,
+                                                              unsigned *__restrict__ out, int n) {
+  __shared__ unsigned warp_tot[32];
+  __shared__ unsigned carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024 * 4) {
+    unsigned v[4];
+    unsigned s = 0;
+    const int i0 = base + tid * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = (i0 + k < n) ? in[i0 + k] : 0u;
+      s += v[k];
+    }
+    unsigned incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = warp_tot[lane];
+      unsigned wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    const unsigned carry = carry_s;
+    unsigned run = carry + warp_tot[warp] + (incl - s);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < n) out[i0 + k] = run;
+      run += v[k];
+    }
+    __syncthreads();
+    if (tid == 1023) carry_s = run;
+    __syncthreads();
+  }
+  if (tid == 0) out[n] = carry_s;
+}
+
+
+}  // namespace am

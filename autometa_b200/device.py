@@ -1,0 +1,242 @@
+"""Tensor-level wrappers over the C ABI: every function takes/returns torch CUDA
+tensors, launches on torch's current stream and never synchronises unless it
+has to read a scalar back.  These are what the reference-shaped functions in
+``common/kmers.py`` and ``binning/recursive_dbscan.py`` (and ``bench.py``) call.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .assembly import PackedAssembly, count_plan
+
+_num_columns_cache: Dict[int, int] = {}
+
+
+def num_columns(k: int) -> int:
+    if k not in _num_columns_cache:
+        n = L.lib.am_kmer_num_columns(int(k))
+        if n < 0:
+            L.check(n)
+        _num_columns_cache[k] = n
+    return _num_columns_cache[k]
+
+
+def column_names(k: int):
+    n = num_columns(k)
+    buf = np.zeros(n * (k + 1), dtype=np.uint8)
+    L.check(L.lib.am_kmer_column_names(k, L.np_ptr(buf)))
+    raw = buf.tobytes()
+    return [raw[i * (k + 1) : i * (k + 1) + k].decode() for i in range(n)]
+
+
+def column_lut(k: int) -> np.ndarray:
+    lut = np.zeros(4 ** k, dtype=np.int32)
+    L.check(L.lib.am_kmer_column_lut(k, L.np_ptr(lut)))
+    return lut
+
+
+class CountPlan:
+    """Device copy of the count work list for one (assembly, k)."""
+
+    def __init__(self, packed: PackedAssembly, k: int, max_item_bases: int = 32768):
+        import torch
+
+        items, multi = count_plan(packed.lengths, k, max_item_bases)
+        dev = packed.device
+        self.n_items = len(items)
+        self.n_multi = len(multi)
+        self.items = torch.from_numpy(items if len(items) else np.zeros((1, 4), np.int32)).to(dev)
+        self.multi = torch.from_numpy(multi if len(multi) else np.zeros(1, np.int32)).to(dev)
+        self.work = torch.zeros(64, dtype=torch.int32, device=dev)
+
+
+def get_count_plan(packed: PackedAssembly, k: int) -> CountPlan:
+    if k not in packed._plans:
+        packed._plans[k] = CountPlan(packed, k)
+    return packed._plans[k]
+
+
+def count_packed(packed: PackedAssembly, k: int = 5, counts=None, col_present=None, row_sum=None):
+    """Kernel 1. Returns (counts[int32 N x ncols], col_present[int32 ncols], row_sum[int32 N])."""
+    import torch
+
+    dev = packed.device
+    ncols = num_columns(k)
+    n = packed.n_contigs
+    plan = get_count_plan(packed, k)
+    with torch.cuda.device(dev):
+        if counts is None:
+            counts = torch.empty((n, ncols), dtype=torch.int32, device=dev)
+        if col_present is None:
+            col_present = torch.zeros(ncols, dtype=torch.int32, device=dev)
+        else:
+            col_present.zero_()
+        if row_sum is None:
+            row_sum = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        L.check(
+            L.lib.am_count_kmers(
+                L.t_ptr(packed.codes), L.t_ptr(packed.exc_bitmap), L.t_ptr(packed.exc_rank),
+                L.t_ptr(packed.exc_mask), L.t_ptr(packed.starts), L.t_ptr(plan.items), plan.n_items,
+                L.t_ptr(plan.multi), plan.n_multi, n, k, L.t_ptr(counts), L.t_ptr(col_present),
+                L.t_ptr(row_sum), L.t_ptr(plan.work), L.stream_ptr(dev),
+            )
+        )
+    return counts, col_present, row_sum[:n]
+
+
+_work_cache: Dict[Tuple[str, int, int], "torch.Tensor"] = {}
+
+
+def _work(dev, nbytes: int, tag: str):
+    import torch
+
+    key = (tag, dev.index, 0)
+    t = _work_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        _work_cache[key] = t
+    return t
+
+
+def normalize_counts(counts, method: str = "am_clr", row_index=None, col_index=None, out=None,
+                     colsum=None):
+    """Kernel 2. ``counts`` int32 [N x D] on device; optional gathers fuse am_clr's
+    row/column drops.  Returns float64 [N_out x D_out]."""
+    import torch
+
+    dev = counts.device
+    if method not in L.NORM_METHODS:
+        raise ValueError(f"Normalize Method not available! {method}. choices: ilr, clr, am_clr")
+    m = L.NORM_METHODS[method]
+    n_in, D = counts.shape
+    n_out = n_in if row_index is None else int(row_index.numel())
+    Dk = D if col_index is None else int(col_index.numel())
+    Dout = Dk - 1 if method == "ilr" else Dk
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((n_out, Dout), dtype=torch.float64, device=dev)
+        work = None
+        if colsum is not None:
+            work = _work(dev, L.lib.am_normalize_work_bytes(D), "norm")
+        L.check(
+            L.lib.am_normalize(
+                L.t_ptr(counts), n_out, D, L.t_ptr(row_index), L.t_ptr(col_index), Dk, m,
+                L.t_ptr(out), L.t_ptr(colsum), L.t_ptr(work), L.stream_ptr(dev),
+            )
+        )
+    return out
+
+
+def colsum(X, out=None):
+    import torch
+
+    dev = X.device
+    n, D = X.shape
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.zeros(D, dtype=torch.float64, device=dev)
+        work = _work(dev, L.lib.am_colsum_work_bytes(D), "colsum")
+        L.check(L.lib.am_colsum(L.t_ptr(X), n, D, L.t_ptr(out), L.t_ptr(work), L.stream_ptr(dev)))
+    return out
+
+
+def gram_centered(X, mu, out=None):
+    """G += (X - mu)^T (X - mu) (fp64).  ``out`` must be zeroed by the caller when given."""
+    import torch
+
+    dev = X.device
+    n, D = X.shape
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.zeros((D, D), dtype=torch.float64, device=dev)
+        work = _work(dev, L.lib.am_gram_work_bytes(D), "gram")
+        L.check(L.lib.am_gram(L.t_ptr(X), n, D, L.t_ptr(mu), L.t_ptr(out), L.t_ptr(work), L.stream_ptr(dev)))
+    return out
+
+
+def eigh_desc(A, max_sweeps: int = 30, tol: float = 0.0):
+    """All eigenpairs of symmetric A, descending; rows of the returned matrix are
+    eigenvectors with sklearn's svd_flip(u_based_decision=False) sign."""
+    import torch
+
+    dev = A.device
+    D = A.shape[0]
+    with torch.cuda.device(dev):
+        evals = torch.empty(D, dtype=torch.float64, device=dev)
+        evecs = torch.empty((D, D), dtype=torch.float64, device=dev)
+        work = _work(dev, L.lib.am_eigh_work_bytes(D), "eigh")
+        L.check(
+            L.lib.am_eigh(L.t_ptr(A), D, L.t_ptr(evals), L.t_ptr(evecs), L.t_ptr(work), max_sweeps,
+                          float(tol), L.stream_ptr(dev))
+        )
+    return evals, evecs
+
+
+def project(X, mu, comps, out=None):
+    import torch
+
+    dev = X.device
+    n, D = X.shape
+    P = comps.shape[0]
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((n, P), dtype=torch.float64, device=dev)
+        L.check(
+            L.lib.am_project(L.t_ptr(X), n, D, L.t_ptr(mu), L.t_ptr(comps), P, L.t_ptr(out), L.stream_ptr(dev))
+        )
+    return out
+
+
+class EpsSweep:
+    """Incremental DBSCAN(min_samples=1) over increasing eps on one point set."""
+
+    def __init__(self, X):
+        import torch
+
+        assert X.dtype == torch.float64 and X.dim() == 2 and X.is_contiguous()
+        self.X = X
+        self.dev = X.device
+        self.n, self.F = X.shape
+        with torch.cuda.device(self.dev):
+            self.parent = torch.empty(max(self.n, 1), dtype=torch.int32, device=self.dev)
+            L.check(L.lib.am_iota_i32(L.t_ptr(self.parent), self.n, L.stream_ptr(self.dev)))
+            self.work = torch.empty(max(256, L.lib.am_dbscan_work_bytes(self.n)), dtype=torch.uint8, device=self.dev)
+            self.labels = torch.empty(max(self.n, 1), dtype=torch.int64, device=self.dev)
+            self.n_clusters = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            if self.n:
+                self.h_min = np.ascontiguousarray(X.min(dim=0).values.cpu().numpy(), dtype=np.float64)
+                self.h_max = np.ascontiguousarray(X.max(dim=0).values.cpu().numpy(), dtype=np.float64)
+            else:
+                self.h_min = np.zeros(self.F)
+                self.h_max = np.zeros(self.F)
+        self.last_eps = 0.0
+
+    def reset(self):
+        import torch
+
+        with torch.cuda.device(self.dev):
+            L.check(L.lib.am_iota_i32(L.t_ptr(self.parent), self.n, L.stream_ptr(self.dev)))
+        self.last_eps = 0.0
+
+    def step(self, eps: float):
+        """Labels (int64 device tensor, valid until the next step) at ``eps``.
+        eps may not decrease without ``reset()``."""
+        import torch
+
+        if eps < self.last_eps:
+            self.reset()
+        self.last_eps = eps
+        with torch.cuda.device(self.dev):
+            st = L.stream_ptr(self.dev)
+            L.check(
+                L.lib.am_eps_union(L.t_ptr(self.X), self.n, self.F, float(eps), L.np_ptr(self.h_min),
+                                   L.np_ptr(self.h_max), L.t_ptr(self.parent), L.t_ptr(self.work), st)
+            )
+            L.check(
+                L.lib.am_labels_from_parent(L.t_ptr(self.parent), self.n, L.t_ptr(self.labels),
+                                            L.t_ptr(self.n_clusters), L.t_ptr(self.work), st)
+            )
+        return self.labels[: self.n]

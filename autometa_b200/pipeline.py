@@ -1,0 +1,137 @@
+"""Device-resident featurisation: count -> normalise -> PCA in one pass.
+
+This is the path ``bench.py`` times and what ``autometa-kmers`` amounts to once
+the TSV hand-offs between count / normalize / embed (kmers.py:709-851) are
+removed: the packed contigs stay in HBM, every stage reads the previous stage's
+tensor, and with several GPUs each rank owns a bp-balanced contig shard and only
+the tiny reductions in ``dist.py`` cross NVLink.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from . import _lib as L
+from . import device as _dev
+from . import dist as _dist
+from .assembly import HostAssembly, PackedAssembly, pack_device_arrays, pack_plan
+
+
+def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_components: int = 50,
+              group=None, distributed: bool = False, keep: bool = True) -> Dict[str, Any]:
+    """counts, normalised matrix and PCA scores of this rank's contig shard.
+
+    am_clr's global column drop (kmers.py:369) is handled optimistically: the
+    normalise kernel runs assuming every column is present somewhere and every
+    contig has counts; the flags are read back once at the end together with the
+    results and the rare other case re-runs with explicit gathers.
+    """
+    import torch
+
+    dev = packed.device
+    with torch.cuda.device(dev):
+        counts, present, row_sum = _dev.count_packed(packed, k)
+        D = counts.shape[1]
+        if distributed:
+            _dist.allreduce_max_(present, group)
+        row_index = col_index = None
+        rows_ok = True
+        if method == "am_clr":
+            flags = torch.stack([present.min(), (row_sum.min() > 0).to(torch.int32) if packed.n_contigs else present.min()])
+            flags_h = flags.cpu().numpy()  # one small D2H; also orders the stream for the host decision
+            if flags_h[0] == 0:
+                col_index = torch.nonzero(present > 0).flatten().to(torch.int32)
+            if flags_h[1] == 0:
+                rows_ok = False
+                row_index = torch.nonzero(row_sum > 0).flatten()
+        else:
+            if packed.n_contigs and int((row_sum.min()).item()) == 0:
+                raise ValueError("Input matrix cannot have rows with all zeros")
+        Dk = D if col_index is None else int(col_index.numel())
+        Dout = Dk - 1 if method == "ilr" else Dk
+        cs = torch.zeros(Dout, dtype=torch.float64, device=dev)
+        if method == "ilr":
+            X = _dev.normalize_counts(counts, method, row_index, col_index)
+            _dev.colsum(X, out=cs)
+        else:
+            X = _dev.normalize_counts(counts, method, row_index, col_index, colsum=cs)
+        n_t = torch.tensor([float(X.shape[0])], dtype=torch.float64, device=dev)
+        if distributed:
+            _dist.allreduce_sum_([cs, n_t], group)
+        mu = cs / n_t
+        G = _dev.gram_centered(X, mu)
+        if distributed:
+            _dist.allreduce_sum_([G], group)
+        C = G / (n_t - 1.0)
+        evals, evecs = _dev.eigh_desc(C)
+        evals = torch.clamp(evals, min=0.0)
+        total = evals.sum()
+        P = min(n_components, Dout)
+        comps = evecs[:P].contiguous()
+        scores = _dev.project(X, mu, comps)
+        out = dict(
+            scores=scores,
+            explained_variance=evals[:P],
+            explained_variance_ratio=evals[:P] / total,
+            components=comps,
+            mean=mu,
+            row_index=row_index,
+            col_index=col_index,
+        )
+        if keep:
+            out.update(counts=counts, normalized=X, col_present=present, row_sum=row_sum)
+        return out
+
+
+class HostFeaturiser:
+    """End-to-end entry for host buffers: ASCII contig bytes in pinned host memory
+    -> H2D -> device pack -> featurise -> scores (+ explained variance) back on the
+    host.  Buffers are allocated once and reused across calls."""
+
+    def __init__(self, asm: HostAssembly, device=None, k: int = 5, method: str = "am_clr", n_components: int = 50):
+        import torch
+
+        self.dev = L.require_cuda(device)
+        self.k, self.method, self.P = k, method, n_components
+        offsets = np.ascontiguousarray(asm.offsets, dtype=np.int64)
+        base = int(offsets[0])
+        self.n = asm.n_contigs
+        self.total_bp = asm.total_bp
+        self.starts_h, self.lengths, self.total = pack_plan(offsets)
+        with torch.cuda.device(self.dev):
+            self.h_seq = torch.empty(self.total_bp, dtype=torch.uint8).pin_memory()
+            self.h_seq.numpy()[:] = asm.seq[base : base + self.total_bp]
+            self.h_off = torch.from_numpy(offsets - base).pin_memory()
+            self.h_starts = torch.from_numpy(self.starts_h if self.n else np.zeros(1, np.int64)).pin_memory()
+            self.d_seq = torch.empty(self.total_bp + 64, dtype=torch.uint8, device=self.dev)
+            self.d_off = torch.empty_like(self.h_off, device=self.dev)
+            self.d_starts = torch.empty_like(self.h_starts, device=self.dev)
+            self.h_scores = None
+        self.h2d_bytes = self.total_bp + self.h_off.numel() * 8 + self.h_starts.numel() * 8
+        self.d2h_bytes = 0
+        self.exc_cap = 0
+
+    def run(self, group=None, distributed: bool = False):
+        import torch
+
+        with torch.cuda.device(self.dev):
+            self.d_seq[: self.total_bp].copy_(self.h_seq, non_blocking=True)
+            self.d_off.copy_(self.h_off, non_blocking=True)
+            self.d_starts.copy_(self.h_starts, non_blocking=True)
+            packed = pack_device_arrays(self.d_seq, self.d_off, self.d_starts, self.n, self.total,
+                                        self.lengths, self.starts_h, self.total_bp, exc_capacity=self.exc_cap)
+            self.exc_cap = max(self.exc_cap, packed.n_exc + 1024)
+            if getattr(self, "_plans", None):
+                packed._plans = self._plans  # the work list depends only on the contig lengths
+            res = featurise(packed, self.k, self.method, self.P, group=group, distributed=distributed, keep=False)
+            self._plans = packed._plans
+            scores = res["scores"]
+            if self.h_scores is None or self.h_scores.shape != scores.shape:
+                self.h_scores = torch.empty(scores.shape, dtype=scores.dtype).pin_memory()
+                self.h_ev = torch.empty(res["explained_variance"].shape, dtype=torch.float64).pin_memory()
+            self.h_scores.copy_(scores, non_blocking=True)
+            self.h_ev.copy_(res["explained_variance"], non_blocking=True)
+            torch.cuda.current_stream(self.dev).synchronize()
+            self.d2h_bytes = self.h_scores.numel() * 8 + self.h_ev.numel() * 8
+        return self.h_scores, self.h_ev

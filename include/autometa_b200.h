@@ -1,0 +1,220 @@
+/*
+ * autometa_b200.h — C ABI of libautometa_b200.so
+ *
+ * B200 (sm_100a) kernels for the one data-parallel hot path of KwanLab/Autometa:
+ *   autometa.common.kmers.count / normalize / embed (PCA stage) and the DBSCAN
+ *   eps-neighbourhood sweep inside autometa.binning.recursive_dbscan.
+ *
+ * The reference is pure Python and has NO FFI for this path: the
+ * boundary a maintainer binds is this header, called from the Python functions
+ * that keep the reference's signatures (autometa_b200/common/kmers.py and
+ * autometa_b200/binning/recursive_dbscan.py).  Each entry point below cites the
+ * reference lines it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.
+ *   - every function returns 0 on success, a negative AM_E* code on failure;
+ *     am_last_error() returns a thread-local message for the last failure.
+ *   - "d_" pointers are device pointers on the CUDA device that is current for
+ *     the calling thread; "h_" pointers are host pointers.  All buffers are
+ *     allocated and freed by the caller (as torch tensors in the Python host).
+ *   - device functions are asynchronous on `stream` (a cudaStream_t passed as
+ *     void*); they never synchronise and never allocate.
+ *   - there is no CPU fallback: device entry points fail with AM_ECUDA when no
+ *     sm_100 device/context is usable.
+ */
+#ifndef AUTOMETA_B200_H
+#define AUTOMETA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AM_OK 0
+#define AM_EINVAL (-1)   /* bad argument                                   */
+#define AM_ECUDA (-2)    /* CUDA runtime / launch error                    */
+#define AM_ECAPACITY (-3) /* caller-provided buffer too small (see docs)   */
+#define AM_EFORMAT (-4)  /* malformed input (e.g. FASTA)                   */
+
+#define AM_NORM_AM_CLR 0
+#define AM_NORM_CLR 1
+#define AM_NORM_ILR 2
+
+/* bases per packed group: one 16-byte vector load = one lane's segment */
+#define AM_GROUP_BASES 64
+/* windows per work-list tile (32 lanes x 64 bases) */
+#define AM_TILE_BASES 2048
+
+int am_version(void);
+const char *am_last_error(void);
+/* number of CUDA kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t am_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * k-mer column table — replaces init_kmers / _revcomp
+ * (autometa/common/kmers.py:38-53, 56-89).  Encoding A=0,T=1,C=2,G=3 (the
+ * reference's enumeration order, kmers.py:75); column = rank of min(code, rc).
+ * ------------------------------------------------------------------------- */
+int am_kmer_num_columns(int k);                 /* 512 for k=5; <0 on bad k (1..7) */
+int am_kmer_column_lut(int k, int32_t *h_lut);  /* h_lut[4^k]: MSB-first code -> column */
+/* h_names: ncols * (k+1) bytes, NUL-terminated strings in column order */
+int am_kmer_column_names(int k, char *h_names);
+
+/* ---------------------------------------------------------------------------
+ * FASTA ingest (host) — replaces Bio.SeqIO.parse as used at kmers.py:143-148,
+ * 234-235: id = first whitespace-delimited token of the header line; sequence
+ * = the record's lines concatenated with whitespace removed, case preserved.
+ *
+ * am_fasta_index: one pass over an in-memory FASTA buffer.
+ *   h_seq_out   [>= len bytes]  sequence bytes of all records, concatenated
+ *   h_offsets   [cap+1] int64   record i occupies h_seq_out[off[i], off[i+1])
+ *   h_id_begin/h_id_end [cap]   byte span of record i's id inside h_buf
+ *   *n_records  number of records found (if > cap returns AM_ECAPACITY with
+ *               *n_records set to the required capacity)
+ * ------------------------------------------------------------------------- */
+int am_fasta_index(const uint8_t *h_buf, int64_t len, uint8_t *h_seq_out,
+                   int64_t *h_offsets, int64_t *h_id_begin, int64_t *h_id_end,
+                   int64_t cap, int64_t *n_records);
+
+/* ---------------------------------------------------------------------------
+ * 2-bit packing.  Layout in HBM ("packed assembly"):
+ *   codes      uint32 words, 16 bases per word, base b at bits [2(b%16), +2),
+ *              A=0 T=1 C=2 G=3; any other byte (N, IUPAC, lower case — the
+ *              reference counts upper-case ACGT only, kmers.py:197-204) is
+ *              stored as 0 and recorded as an exception.
+ *   starts[i]  first packed base of contig i; a multiple of 64 so that every
+ *              contig begins on a 16-byte boundary.  am_pack_plan fills it and
+ *              returns the total number of packed bases (multiple of 64, incl.
+ *              one trailing pad group that kernels may over-read).
+ *   exc_bitmap one bit per 64-base group: group holds >= 1 invalid base
+ *   exc_rank   per 32 groups: number of flagged groups before this bitmap word
+ *   exc_mask   one uint64 per flagged group (bit j = base j invalid), in group order
+ * ------------------------------------------------------------------------- */
+int am_pack_plan(const int64_t *h_offsets, int64_t n_contigs, int64_t *h_starts,
+                 int32_t *h_lengths, int64_t *total_packed_bases);
+/* sizes (in elements) of the arrays for a packed assembly of `total_packed_bases` */
+int64_t am_pack_code_words(int64_t total_packed_bases);   /* uint32 count */
+int64_t am_pack_bitmap_words(int64_t total_packed_bases); /* uint32 count (bitmap and rank) */
+/* host packer; exc_capacity = room in h_exc_mask; *n_exc = flagged groups found
+ * (AM_ECAPACITY if it does not fit: call again with a larger buffer). */
+int am_pack_host(const uint8_t *h_seq, const int64_t *h_offsets, int64_t n_contigs,
+                 const int64_t *h_starts, int64_t total_packed_bases,
+                 uint32_t *h_codes, uint32_t *h_exc_bitmap, uint32_t *h_exc_rank,
+                 uint64_t *h_exc_mask, int64_t exc_capacity, int64_t *n_exc,
+                 int n_threads);
+/* device packer: ASCII bytes already in HBM -> the same layout.  d_seq must be
+ * 4-byte aligned and readable up to 4 bytes past the last base; d_exc_mask holds
+ * exc_capacity entries; d_n_exc receives the number of flagged groups (if it
+ * exceeds exc_capacity the surplus masks were dropped: call again with a larger
+ * buffer).  d_work: am_pack_bitmap_words(total) uint32 of scratch. */
+int am_pack_device(const uint8_t *d_seq, const int64_t *d_offsets,
+                   const int64_t *d_starts, int64_t n_contigs,
+                   int64_t total_packed_bases, uint32_t *d_codes,
+                   uint32_t *d_exc_bitmap, uint32_t *d_exc_rank,
+                   uint64_t *d_exc_mask, int64_t exc_capacity, int64_t *d_n_exc,
+                   void *d_work, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Work list for the count kernel: contigs are cut into items of at most
+ * `max_item_bases` windows (a multiple of AM_TILE_BASES) so that a multi-Mbp
+ * contig is spread over many warps.  Item = {contig, first window, n windows,
+ * flags}; flags bit0 = contig has several items (accumulate with atomics into a
+ * pre-zeroed row).  h_multi_rows lists those contigs.
+ * ------------------------------------------------------------------------- */
+int am_count_plan(const int32_t *h_lengths, int64_t n_contigs, int k,
+                  int32_t max_item_bases, int32_t *h_items /*4 x cap*/,
+                  int64_t item_cap, int64_t *n_items, int32_t *h_multi_rows,
+                  int64_t multi_cap, int64_t *n_multi);
+
+/* ---------------------------------------------------------------------------
+ * Kernel 1 — canonical k-mer count.  Replaces record_counter / seq_counter /
+ * mp_counter (kmers.py:122-265): for contig i of length L the first L-k windows
+ * are counted (kmers.py:186,193 — the last k-mer is dropped), a window counts
+ * iff all k bases are upper-case ACGT, canonical column per am_kmer_column_lut.
+ *   d_counts      [n_contigs x ncols] int32, row-major, fully overwritten
+ *   d_col_present [ncols] int32, set to 1 for columns with any count (must be
+ *                 zeroed by the caller; feeds am_clr's column drop, kmers.py:369)
+ *   d_row_sum     [n_contigs] int32 total counted windows per contig (may be NULL)
+ *   d_work        >= 16 bytes of device scratch (work-queue counter)
+ * ------------------------------------------------------------------------- */
+int am_count_kmers(const uint32_t *d_codes, const uint32_t *d_exc_bitmap,
+                   const uint32_t *d_exc_rank, const uint64_t *d_exc_mask,
+                   const int64_t *d_starts, const int32_t *d_items, int64_t n_items,
+                   const int32_t *d_multi_rows, int64_t n_multi, int64_t n_contigs,
+                   int k, int32_t *d_counts, int32_t *d_col_present,
+                   int32_t *d_row_sum, void *d_work, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Kernel 2 — row-wise log-ratio normalisation.  Replaces autometa_clr
+ * (kmers.py:333-373) and the skbio multiplicative_replacement + clr / ilr calls
+ * (kmers.py:418-421).
+ *   d_counts   [n_rows_in x D] int32 (NA == 0)
+ *   d_row_index[n_rows_out] int64 source row of each output row, or NULL = identity
+ *   d_col_index[D_keep] int32 source column of each retained column, or NULL = all
+ *   d_out      [n_rows_out x D_out] float64; D_out = D_keep (am_clr, clr) or D_keep-1 (ilr)
+ *   d_colsum   [D_out] float64 or NULL: column sums of the output are ADDED here
+ *              (caller zeroes) — the PCA mean comes for free.  Deterministic:
+ *              per-CTA partials in d_work (am_normalize_work_bytes(D) bytes) are
+ *              reduced in a fixed order.  Not available for ilr (use am_colsum).
+ * am_clr: out = log1p(x) - mean_j log1p(x)   (== log(((x+1)/S)/gmean((x+1)/S)))
+ * clr/ilr: p = x/S; zeros -> 1/D^2, others * (1 - z/D^2); log; centre; (ilr: Helmert basis)
+ * ------------------------------------------------------------------------- */
+int64_t am_normalize_work_bytes(int D);
+int am_normalize(const int32_t *d_counts, int64_t n_rows_out, int D,
+                 const int64_t *d_row_index, const int32_t *d_col_index, int D_keep,
+                 int method, double *d_out, double *d_colsum, void *d_work, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Kernel 3 — PCA (sklearn 1.9 PCA, svd_solver="covariance_eigh", the branch
+ * kmers.py:605 takes for N >= 10*D; sklearn/decomposition/_pca.py:560,604-646).
+ *   am_colsum      colsum[D] += sum_i X[i,:]                       (_pca.py:560)
+ *   am_gram        G[D x D] += (X - mu)^T (X - mu) over this rank's rows
+ *                  (centred before the product instead of _pca.py:604-610's
+ *                  X^T X - n mu mu^T: same matrix, no cancellation)
+ *   am_eigh        all eigenpairs of the symmetric D x D matrix, descending
+ *                  (_pca.py:611-624); d_evecs row j = eigenvector j with sklearn's
+ *                  svd_flip(u_based_decision=False) sign (largest-|.| entry > 0)
+ *   am_project     scores[N x P] = (X - mu) @ comps[P x D]^T        (_base.py:151-159)
+ * d_work for am_gram / am_eigh: see am_gram_work_bytes / am_eigh_work_bytes.
+ * ------------------------------------------------------------------------- */
+int64_t am_colsum_work_bytes(int D);
+int am_colsum(const double *d_X, int64_t n_rows, int D, double *d_colsum, void *d_work,
+              void *stream);
+int64_t am_gram_work_bytes(int D);
+int am_gram(const double *d_X, int64_t n_rows, int D, const double *d_mu,
+            double *d_G, void *d_work, void *stream);
+int64_t am_eigh_work_bytes(int D);
+int am_eigh(const double *d_A, int D, double *d_evals, double *d_evecs,
+            void *d_work, int max_sweeps, double tol, void *stream);
+int am_project(const double *d_X, int64_t n_rows, int D, const double *d_mu,
+               const double *d_comps, int P, double *d_scores, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Kernel 4 — DBSCAN(min_samples=1) eps step.  Replaces
+ * DBSCAN(eps, min_samples=1).fit(X).labels_ at recursive_dbscan.py:109: every
+ * point is a core point, so labels = connected components of the graph
+ * {(i,j): sum_d (X[i,d]-X[j,d])^2 <= eps*eps} (fp64, column order, inclusive —
+ * sklearn/neighbors/_binary_tree.pxi.tp:1952-1957), numbered by ascending
+ * minimum member row (sklearn/cluster/_dbscan_inner.pyx visiting order).
+ *   am_eps_union          unions all pairs within eps into the forest d_parent
+ *                         (int32[N], caller initialises to identity once and
+ *                         keeps it across increasing eps: the sweep is
+ *                         incremental — components only merge)
+ *   am_labels_from_parent compress + relabel; d_n_clusters int32[1]
+ * d_work: am_dbscan_work_bytes(N) bytes of device scratch.
+ * ------------------------------------------------------------------------- */
+int64_t am_dbscan_work_bytes(int64_t n_points);
+int am_eps_union(const double *d_X, int64_t n_points, int F, double eps,
+                 const double *h_min /*F*/, const double *h_max /*F*/,
+                 int32_t *d_parent, void *d_work, void *stream);
+int am_labels_from_parent(int32_t *d_parent, int64_t n_points, int64_t *d_labels,
+                          int32_t *d_n_clusters, void *d_work, void *stream);
+int am_iota_i32(int32_t *d_v, int64_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUTOMETA_B200_H */
