@@ -19,7 +19,7 @@ from .assembly import HostAssembly, PackedAssembly, pack_device_arrays, pack_pla
 
 
 def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_components: int = 50,
-              group=None, distributed: bool = False, keep: bool = True) -> Dict[str, Any]:
+              group=None, distributed: bool = False, keep: bool = True, marks=None) -> Dict[str, Any]:
     """counts, normalised matrix and PCA scores of this rank's contig shard.
 
     am_clr's global column drop (kmers.py:369) is handled optimistically: the
@@ -30,8 +30,11 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
     import torch
 
     dev = packed.device
+    mark = marks if marks is not None else (lambda name: None)
     with torch.cuda.device(dev):
+        mark("start")
         counts, present, row_sum = _dev.count_packed(packed, k)
+        mark("count")
         D = counts.shape[1]
         if distributed:
             _dist.allreduce_max_(present, group)
@@ -56,6 +59,7 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
             _dev.colsum(X, out=cs)
         else:
             X = _dev.normalize_counts(counts, method, row_index, col_index, colsum=cs)
+        mark("normalise")
         n_t = torch.tensor([float(X.shape[0])], dtype=torch.float64, device=dev)
         if distributed:
             _dist.allreduce_sum_([cs, n_t], group)
@@ -64,12 +68,15 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
         if distributed:
             _dist.allreduce_sum_([G], group)
         C = G / (n_t - 1.0)
+        mark("gram")
         evals, evecs = _dev.eigh_desc(C)
+        mark("eigh")
         evals = torch.clamp(evals, min=0.0)
         total = evals.sum()
         P = min(n_components, Dout)
         comps = evecs[:P].contiguous()
         scores = _dev.project(X, mu, comps)
+        mark("project")
         out = dict(
             scores=scores,
             explained_variance=evals[:P],
@@ -105,8 +112,8 @@ class HostFeaturiser:
             self.h_off = torch.from_numpy(offsets - base).pin_memory()
             self.h_starts = torch.from_numpy(self.starts_h if self.n else np.zeros(1, np.int64)).pin_memory()
             self.d_seq = torch.empty(self.total_bp + 64, dtype=torch.uint8, device=self.dev)
-            self.d_off = torch.empty_like(self.h_off, device=self.dev)
-            self.d_starts = torch.empty_like(self.h_starts, device=self.dev)
+            self.d_off = torch.empty(self.h_off.shape, dtype=torch.int64, device=self.dev)
+            self.d_starts = torch.empty(self.h_starts.shape, dtype=torch.int64, device=self.dev)
             self.h_scores = None
         self.h2d_bytes = self.total_bp + self.h_off.numel() * 8 + self.h_starts.numel() * 8
         self.d2h_bytes = 0

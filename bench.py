@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — featurise throughput (5-mer count + am_clr + PCA(50)) on synthetic assemblies.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # CPU port of the reference path
+
+A step = one pass of the hot path (count -> am_clr -> PCA fit + scores) over the rank's
+synthetic contig shard.  N=1 workload: BASELINE.json configs[1] (200k contigs / 1 Gbp).
+N>1: one process per GPU (torchrun); every rank holds its own 200k-contig / 1 Gbp shard of
+an N Gbp assembly (weak scaling); the only cross-GPU traffic is the column-presence OR, the
+column sums + row count and the 512x512 Gram all-reduce (NCCL).  `--scaling strong` instead
+shards ONE 1 Gbp assembly by bp across the ranks (BASELINE.json configs[2]).
+
+`value`: whole-job Gbp/s with the 2-bit-packed contigs already in HBM, CUDA events, max over
+ranks.  `e2e`: the same metric from pinned HOST ASCII bytes through H2D, the device packer,
+the pipeline and the D2H copy of the scores.  Inputs/outputs per step (0.25 GB codes, 0.41 GB
+counts, 0.82 GB normalised) exceed the 126 MB L2, so no explicit L2 flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "featurise throughput (5-mer count + am_clr + PCA50)"
+UNIT = "Gbp/s"
+N_CONTIGS = 200_000
+TOTAL_BP = 1_000_000_000
+SEED = 20261019 + 2
+K = 5
+NCOMP = 50
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def cpu_port_step(asm, threads):
+    """One pass of the CPU port (oracle) over `asm`: C count + C am_clr + sklearn PCA(50)."""
+    from sklearn.decomposition import PCA
+
+    from oracle import oracle_c
+
+    counts = oracle_c.count(asm.seq, asm.offsets, K, threads)
+    keep = counts.sum(axis=1) > 0
+    X = oracle_c.am_clr(counts if keep.all() else counts[keep], threads)
+    p = PCA(n_components=NCOMP, random_state=np.random.RandomState(42))
+    scores = p.fit_transform(X)
+    return scores, p.explained_variance_
+
+
+def cpu_baseline(asm_full, threads, sample_bp=50_000_000):
+    """Oracle port timed on a bounded sample (first contigs totalling ~sample_bp)."""
+    n = int(np.searchsorted(asm_full.offsets, asm_full.offsets[0] + sample_bp))
+    n = max(10 * 512 + 1, min(n, asm_full.n_contigs))
+    sub = asm_full.slice(0, n)
+    cpu_port_step(sub.slice(0, min(n, 6000)), threads)  # warm the BLAS/thread pools
+    t0 = time.perf_counter()
+    cpu_port_step(sub, threads)
+    dt = time.perf_counter() - t0
+    return {
+        "value": sub.total_bp / dt / 1e9,
+        "unit": UNIT,
+        "cores": threads,
+        "kind": "port",
+        "sample": f"first {n} contigs / {sub.total_bp / 1e6:.1f} Mbp of the workload: C port of the count + am_clr "
+                  f"loops on {threads} threads + sklearn PCA(50) (covariance_eigh), one pass, {dt:.2f} s",
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the Python reference cannot
+    travel to the GPU box) on the host cores, same metric/config, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from autometa_b200 import synth
+
+    threads = os.cpu_count() or 1
+    sample_contigs, sample_bp = 40_000, 200_000_000
+    asm = synth.make_assembly(sample_contigs, sample_bp, seed=SEED)
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_step(asm.slice(0, 6000), threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_step(asm, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = asm.total_bp / dt / 1e9
+    sample = (f"{sample_contigs} contigs / {sample_bp / 1e6:.0f} Mbp per step (bounded sample of the 200k-contig / "
+              f"1 Gbp workload): C port of the reference count + am_clr loops on {threads} threads + sklearn PCA(50)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32 counts / f64 features", "data": "synthetic",
+        "config": {"workload": "C2: 5-mer count + am_clr + PCA(50), 200k contigs / 1 Gbp synthetic assembly",
+                   "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+STAGE_BYTES = None
+
+
+def stage_accounting(n_contigs, total_bp, D=512, P=NCOMP):
+    """Algorithmic bytes / flops per launch, for this rank's shard."""
+    return {
+        "count": {"bytes": total_bp / 4 + 8 * (n_contigs + 1) + 4 * D * n_contigs, "bound": "hbm"},
+        "normalise": {"bytes": 4 * D * n_contigs + 8 * D * n_contigs, "bound": "hbm"},
+        "gram": {"bytes": 8 * D * n_contigs, "flops": 2.0 * n_contigs * D * D, "bound": "hbm"},
+        "eigh": {"bytes": 2 * 8 * D * D, "bound": "hbm"},
+        "project": {"bytes": 8 * D * n_contigs + 8 * P * n_contigs, "flops": 2.0 * n_contigs * D * P, "bound": "hbm"},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--contigs", type=int, default=N_CONTIGS)
+    ap.add_argument("--bp", type=int, default=TOTAL_BP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from autometa_b200 import _lib as L
+    from autometa_b200 import assembly, dist as DD, pipeline, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic shard for this rank
+    if args.scaling == "weak" or not distributed:
+        asm = synth.make_assembly(args.contigs, args.bp, seed=SEED + 1000 * rank)
+    else:
+        full = synth.make_assembly(args.contigs, args.bp, seed=SEED)
+        lo, hi = DD.shard_ranges(full.lengths, world)[rank]
+        asm = full.slice(lo, hi)
+    packed = assembly.pack_to_device(asm, device=dev, on_device=True)
+    shard_bp, shard_n = asm.total_bp, asm.n_contigs
+    job_bp = torch.tensor([float(shard_bp)], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(job_bp)
+    job_bp = float(job_bp.item())
+
+    stages = ["count", "normalise", "gram", "eigh", "project"]
+
+    def run_step(marks=None):
+        return pipeline.featurise(packed, K, "am_clr", NCOMP, distributed=distributed, keep=False, marks=marks)
+
+    for _ in range(args.warmup):
+        run_step()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev_start = torch.cuda.Event(enable_timing=True)
+    ev_end = torch.cuda.Event(enable_timing=True)
+    step_marks = []
+    launches0 = L.launch_count()
+    ev_start.record()
+    for _ in range(args.steps):
+        marks = []
+        run_step(lambda name: marks.append((name, _rec(torch))))
+        step_marks.append(marks)
+    ev_end.record()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = L.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev_start.elapsed_time(ev_end)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = job_bp / (ms_per_step * 1e-3) / 1e9
+
+    # per-stage durations from the events recorded inside the timed region
+    stage_ms = {s: 0.0 for s in stages}
+    for marks in step_marks:
+        d = dict(marks)
+        order = ["start"] + stages
+        for a, b in zip(order[:-1], order[1:]):
+            stage_ms[b] += d[a].elapsed_time(d[b])
+    stage_ms = {s: v / args.steps for s, v in stage_ms.items()}
+
+    # ---- end to end from host buffers
+    e2e = None
+    if not args.no_e2e:
+        hf = pipeline.HostFeaturiser(asm, device=dev, k=K, method="am_clr", n_components=NCOMP)
+        for _ in range(2):
+            hf.run(distributed=distributed)
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            hf.run(distributed=distributed)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e_ms = float(dt.item()) / e_steps * 1e3
+        e2e = {"value": job_bp / (e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(hf.h2d_bytes), "d2h_bytes_per_step": int(hf.d2h_bytes),
+               "path": "pinned host ASCII -> H2D -> am_pack_device -> count -> am_clr -> PCA -> D2H scores"}
+
+    if rank == 0:
+        hbm, bf16, how = measured_peaks()
+        acct = stage_accounting(shard_n, shard_bp)
+        stage_report = {}
+        for s in stages:
+            gbs = acct[s]["bytes"] / (stage_ms[s] * 1e-3) / 1e9 if stage_ms[s] > 0 else None
+            stage_report[s] = {"ms": round(stage_ms[s], 4), "algorithmic_GB": round(acct[s]["bytes"] / 1e9, 4),
+                               "achieved_GBps": None if gbs is None else round(gbs, 1),
+                               "frac_of_hbm_peak": None if gbs is None else round(gbs / hbm, 4)}
+            if "flops" in acct[s] and stage_ms[s] > 0:
+                stage_report[s]["achieved_TFLOPs"] = round(acct[s]["flops"] / (stage_ms[s] * 1e-3) / 1e12, 2)
+        dom = max(stages, key=lambda s: stage_ms[s])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(dom)
+            except Exception:
+                traffic = None
+        roofline = {
+            "kernel": dom, "bound": acct[dom]["bound"],
+            "achieved": stage_report[dom]["achieved_GBps"], "peak": hbm, "unit": "GB/s",
+            "frac": stage_report[dom]["frac_of_hbm_peak"], "traffic": traffic,
+            "peak_source": f"{how} (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "fallback 6.65 TB/s",
+            "composite": {
+                "algorithmic_GB": round(sum(a["bytes"] for a in acct.values()) / 1e9, 3),
+                "achieved_GBps": round(sum(a["bytes"] for a in acct.values()) / (ms_per_step * 1e-3) / 1e9, 1),
+                "frac": round(sum(a["bytes"] for a in acct.values()) / (ms_per_step * 1e-3) / 1e9 / hbm, 4),
+            },
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline(asm, os.cpu_count() or 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "int32 counts / f64 features",
+            "data": "synthetic",
+            "config": {
+                "workload": f"C2: 5-mer count + am_clr + PCA(50), {shard_n} contigs / {shard_bp / 1e9:.3f} Gbp per GPU "
+                            f"({job_bp / 1e9:.3f} Gbp job), seeded synthetic assembly",
+                "k": K, "norm": "am_clr", "pca_dimensions": NCOMP,
+                "parallelism": f"contigs sharded by bp over {world} GPU(s); NCCL all-reduce of column presence, "
+                               "column sums and the 512x512 Gram only",
+                "l2": "inputs larger than L2 (0.25 GB codes, 0.41 GB counts, 0.82 GB features per step); no flush",
+            },
+            "roofline": roofline, "stages": stage_report, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def _rec(torch):
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+if __name__ == "__main__":
+    main()

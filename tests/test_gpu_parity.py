@@ -1,0 +1,393 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI and the
+reference-shaped Python functions, against the oracle, the reference's golden
+outputs and size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8d):
+  counts            bit-exact
+  normalised        max|d| <= 1e-12 * max|row|   (fp64)
+  PCA               explained variance within 1e-6 relative; components equal up to the
+                    sklearn sign rule (|cos| >= 1 - 1e-9); scores within 1e-8 * max|score|
+  DBSCAN            label vectors identical (min_samples=1: no border points exist)
+"""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return torch
+
+
+# ----------------------------------------------------------------------------- count
+def test_count_api_matches_reference_golden(torch_cuda, golden_kmers, small_fna, tmp_path):
+    from autometa_b200.common import kmers
+
+    out = tmp_path / "kmers.tsv"
+    df = kmers.count(small_fna, size=5, out=str(out), force=True, cpus=2)
+    assert df.index.name == "contig"
+    assert df.index.tolist() == golden_kmers["count_ids"].tolist()
+    assert df.columns.tolist() == golden_kmers["count_columns"].tolist()
+    got = df.fillna(0).to_numpy().astype(np.int64)
+    ref = golden_kmers["count_k5"].astype(np.int64)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(df.isna().to_numpy(), ref == 0)  # zero counts are NA (kmers.py:205)
+    # TSV round trip = what kmers.load gives the reference's next stage
+    back = kmers.load(str(out))
+    assert np.array_equal(np.nan_to_num(back.to_numpy(dtype=float)), ref)
+    assert np.array_equal(np.isnan(back.to_numpy(dtype=float)), ref == 0)
+    # out exists and not force -> read back (kmers.py:310-314)
+    again = kmers.count("nonexistent.fna", size=5, out=str(out), force=False)
+    assert again.shape == df.shape
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 6, 7])
+def test_count_other_k(torch_cuda, golden_kmers, small_fna, k):
+    from autometa_b200 import assembly as A, device as D
+
+    h = A.read_fasta(small_fna)
+    packed = A.pack_to_device(h, device="cuda:0")
+    counts, present, row_sum = D.count_packed(packed, k)
+    got = counts.cpu().numpy()
+    _, seqs = O.read_fasta(small_fna)
+    ref, ok = O.count_sequences(seqs, k)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(row_sum.cpu().numpy(), ref.sum(axis=1))
+    assert np.array_equal(present.cpu().numpy() > 0, ref.sum(axis=0) > 0)
+    if f"count_k{k}" in golden_kmers:
+        ids = golden_kmers["count_ids"].tolist()
+        last = {c: i for i, c in enumerate(h.ids)}
+        assert np.array_equal(got[[last[c] for c in ids]], golden_kmers[f"count_k{k}"])
+
+
+def test_device_packer_equals_host_packer(torch_cuda, small_fna):
+    from autometa_b200 import assembly as A, synth
+
+    for h in (A.read_fasta(small_fna), synth.make_assembly(300, 300 * 3400, seed=2, tiny=True)):
+        starts, lengths, total, codes, bitmap, rank, masks = A.pack_host_arrays(h, 2)
+        p = A.pack_to_device(h, device="cuda:0", on_device=True)
+        assert p.total_packed_bases == total and p.n_exc == len(masks)
+        assert np.array_equal(p.codes.cpu().numpy().view(np.uint32), codes)
+        assert np.array_equal(p.exc_bitmap.cpu().numpy().view(np.uint32), bitmap)
+        assert np.array_equal(p.exc_rank.cpu().numpy().view(np.uint32), rank)
+        assert np.array_equal(p.exc_mask.cpu().numpy().view(np.uint64)[: p.n_exc], masks)
+
+
+def test_count_synthetic_vs_oracle_and_sharding_invariance(torch_cuda):
+    from autometa_b200 import assembly as A, device as D, dist as DD, synth
+
+    asm = synth.make_assembly(1500, 1500 * 4000, seed=20261019, tiny=True)
+    ref, ok = O.count_sequences(synth.sequences(asm), 5)
+    for on_device in (False, True):
+        packed = A.pack_to_device(asm, device="cuda:0", on_device=on_device)
+        counts, present, row_sum = D.count_packed(packed, 5)
+        assert np.array_equal(counts.cpu().numpy(), ref)
+    # sharding by bp never changes a row (the multi-GPU path counts shards independently)
+    parts = []
+    for lo, hi in DD.shard_ranges(asm.lengths, 3):
+        p = A.pack_to_device(asm.slice(lo, hi), device="cuda:0", on_device=True)
+        parts.append(D.count_packed(p, 5)[0].cpu().numpy())
+    assert np.array_equal(np.concatenate(parts), ref)
+
+
+def test_count_empty_and_degenerate(torch_cuda):
+    from autometa_b200 import assembly as A, device as D
+
+    h = A.from_sequences(["e", "t", "x"], [b"", b"ACGTA", b"ACGTAC"])
+    packed = A.pack_to_device(h, device="cuda:0", on_device=True)
+    counts, present, row_sum = D.count_packed(packed, 5)
+    c = counts.cpu().numpy()
+    assert c[:2].sum() == 0 and c[2].sum() == 1
+    h0 = A.from_sequences([], [])
+    p0 = A.pack_to_device(h0, device="cuda:0")
+    c0, _, _ = D.count_packed(p0, 5)
+    assert c0.shape == (0, 512)
+
+
+def _valid_window_counts(asm, k):
+    """rows sums expected from the raw bytes, vectorised (independent of the oracle's histogramming)."""
+    seq = asm.seq[: asm.total_bp]
+    good = (seq == 65) | (seq == 67) | (seq == 71) | (seq == 84)
+    bad_prefix = np.concatenate([[0], np.cumsum(~good, dtype=np.int64)])
+    out = np.zeros(asm.n_contigs, dtype=np.int64)
+    off = asm.offsets
+    for i in range(asm.n_contigs):
+        a, b = int(off[i]), int(off[i + 1])
+        nwin = b - a - k
+        if nwin <= 0:
+            continue
+        starts = np.arange(a, a + nwin)
+        out[i] = np.count_nonzero(bad_prefix[starts + k] - bad_prefix[starts] == 0)
+    return out
+
+
+def test_count_full_size_properties(torch_cuda):
+    """C2 (200k contigs / 1 Gbp): row sums equal the number of all-ACGT windows among the
+    first L-k (checked exactly on a contig sample and in aggregate), linearity across shards."""
+    import torch
+
+    from autometa_b200 import assembly as A, device as D, synth
+
+    asm = synth.make_assembly(200_000, 1_000_000_000, seed=20261019 + 2)
+    packed = A.pack_to_device(asm, device="cuda:0", on_device=True)
+    counts, present, row_sum = D.count_packed(packed, 5)
+    rs = row_sum.cpu().numpy().astype(np.int64)
+    assert np.array_equal(counts.sum(dim=1, dtype=torch.int64).cpu().numpy(), rs)
+    assert int(present.min().item()) == 1
+    lens = asm.lengths
+    assert np.all(rs <= lens - 5) and rs.sum() > 0.99 * (lens - 5).sum()
+    sample = np.random.default_rng(0).choice(asm.n_contigs, size=300, replace=False)
+    sub = A.HostAssembly([asm.ids[i] for i in sample], asm.seq, asm.offsets)  # reuse bytes
+    exp = np.zeros(len(sample), dtype=np.int64)
+    for j, i in enumerate(sample):
+        one = A.HostAssembly([asm.ids[i]], asm.seq[int(asm.offsets[i]) : int(asm.offsets[i + 1])],
+                             np.array([0, lens[i]], dtype=np.int64))
+        exp[j] = _valid_window_counts(one, 5)[0]
+    assert np.array_equal(rs[sample], exp)
+    # oracle on a slice of whole contigs
+    seqs = [asm.seq[int(asm.offsets[i]) : int(asm.offsets[i + 1])].tobytes() for i in sample[:60]]
+    ref, _ = O.count_sequences(seqs, 5)
+    assert np.array_equal(counts[torch.from_numpy(sample[:60]).cuda()].cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------------- normalise
+def _golden_count_frame(golden_kmers, k=5):
+    X = golden_kmers[f"count_k{k}"].astype(np.float64)
+    X[X == 0] = np.nan
+    names, _ = O.kmer_columns(k)
+    return pd.DataFrame(X, index=pd.Index(golden_kmers["count_ids"].tolist(), name="contig"), columns=names)
+
+
+def test_normalize_am_clr_matches_reference_golden(torch_cuda, golden_kmers, tmp_path):
+    from autometa_b200.common import kmers
+
+    df = _golden_count_frame(golden_kmers)
+    out = tmp_path / "norm.tsv"
+    norm = kmers.normalize(df, method="am_clr", out=str(out), force=True)
+    ref = golden_kmers["am_clr_values"]
+    assert norm.index.tolist() == golden_kmers["am_clr_index"].tolist()
+    assert norm.columns.tolist() == golden_kmers["am_clr_columns"].tolist()
+    assert norm.index.name == "contig"
+    got = norm.to_numpy()
+    assert np.max(np.abs(got - ref) / np.max(np.abs(ref), axis=1, keepdims=True)) <= 1e-12
+    assert out.exists()
+    # dropped columns (k=6 sub-table where many 6-mers never occur)
+    d6 = _golden_count_frame(golden_kmers, 6).iloc[5:12]
+    n6 = kmers.normalize(d6, method="am_clr")
+    assert n6.columns.tolist() == golden_kmers["am_clr6_columns"].tolist()
+    assert n6.index.tolist() == golden_kmers["am_clr6_rows"].tolist()
+    r6 = golden_kmers["am_clr6_values"]
+    assert np.max(np.abs(n6.to_numpy() - r6) / np.max(np.abs(r6), axis=1, keepdims=True)) <= 1e-12
+
+
+@pytest.mark.parametrize("method", ["clr", "ilr"])
+def test_normalize_clr_ilr_match_reference_call_site(torch_cuda, golden_kmers, method):
+    from autometa_b200.common import kmers
+
+    df = _golden_count_frame(golden_kmers).loc[golden_kmers["clr_rows"].tolist()]
+    norm = kmers.normalize(df, method=method)
+    ref = golden_kmers[f"{method}_values"]
+    assert norm.shape == ref.shape
+    assert list(norm.columns) == list(range(ref.shape[1]))  # integer labels (kmers.py:422)
+    assert np.max(np.abs(norm.to_numpy() - ref) / np.max(np.abs(ref), axis=1, keepdims=True)) <= 1e-12
+    with pytest.raises(ValueError):  # skbio closure(): all-zero row
+        kmers.normalize(_golden_count_frame(golden_kmers), method=method)
+
+
+def test_normalize_synthetic_all_methods(torch_cuda):
+    import torch
+
+    from autometa_b200 import device as D
+
+    rng = np.random.default_rng(5)
+    counts = rng.poisson(9.0, size=(3000, 512)).astype(np.int32)
+    counts[rng.random(counts.shape) < 0.05] = 0
+    counts[7, :40] = rng.integers(2049, 90000, size=40)  # beyond the log table
+    d = torch.from_numpy(counts).cuda()
+    cs = torch.zeros(512, dtype=torch.float64, device="cuda")
+    got = D.normalize_counts(d, "am_clr", colsum=cs).cpu().numpy()
+    ref, _, _ = O.am_clr(O.counts_to_float_frame(counts.astype(np.int64)))
+    assert np.max(np.abs(got - ref) / np.max(np.abs(ref), axis=1, keepdims=True)) <= 1e-12
+    np.testing.assert_allclose(cs.cpu().numpy(), ref.sum(axis=0), rtol=0, atol=1e-9)
+    for method, fn in (("clr", O.clr), ("ilr", O.ilr)):
+        got = D.normalize_counts(d, method).cpu().numpy()
+        ref = fn(counts.astype(np.float64))
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref) / np.max(np.abs(ref), axis=1, keepdims=True)) <= 1e-12
+    # gathers
+    ridx = torch.tensor([5, 1, 2999, 7], dtype=torch.int64, device="cuda")
+    cidx = torch.arange(0, 512, 3, dtype=torch.int32, device="cuda")
+    got = D.normalize_counts(d, "am_clr", ridx, cidx).cpu().numpy()
+    sub = counts[[5, 1, 2999, 7]][:, ::3].astype(np.float64)
+    ref = np.log1p(sub) - np.log1p(sub).mean(axis=1, keepdims=True)
+    assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+# ------------------------------------------------------------------------------- PCA
+def _check_pca(res, ref, score_tol=1e-8):
+    ev, rev = res["explained_variance"], ref["explained_variance"]
+    assert np.max(np.abs(ev - rev) / rev) <= 1e-6
+    rr = ref["explained_variance_ratio"]
+    assert np.max(np.abs(res["explained_variance_ratio"] - rr) / rr) <= 1e-6
+    cos = np.sum(res["components"] * ref["components"], axis=1)
+    assert np.all(cos >= 1 - 1e-9), cos.min()
+    assert np.max(np.abs(res["scores"] - ref["scores"])) <= score_tol * np.max(np.abs(ref["scores"]))
+
+
+def test_pca_matches_sklearn_golden(torch_cuda, golden_pca):
+    from autometa_b200.common import kmers
+
+    P = golden_pca["scores"].shape[1]
+    res = kmers.pca(golden_pca["X"], n_components=P)
+    _check_pca(res, golden_pca)
+    assert np.allclose(res["scores"][:, :3], golden_pca["embed_first3"], rtol=0,
+                       atol=1e-8 * np.abs(golden_pca["scores"]).max())
+    with pytest.raises(ValueError):
+        kmers.pca(golden_pca["X"][:5], n_components=10)
+
+
+def test_pca_on_kmer_features_vs_oracle(torch_cuda):
+    """512-column am_clr features of a synthetic assembly (N >= 10*D: sklearn's covariance_eigh branch)."""
+    from sklearn.decomposition import PCA
+
+    from autometa_b200 import assembly as A, pipeline, synth
+
+    asm = synth.make_assembly(6000, 6000 * 3600, seed=77, tiny=True)
+    packed = A.pack_to_device(asm, device="cuda:0", on_device=True)
+    res = pipeline.featurise(packed, 5, "am_clr", 50)
+    X = res["normalized"].cpu().numpy()
+    assert X.shape == (6000, 512)  # the three tiny contigs are dropped by am_clr
+    ref_counts, _ = O.count_sequences(synth.sequences(asm), 5)
+    assert np.array_equal(res["counts"].cpu().numpy(), ref_counts)
+    refX, _, _ = O.am_clr(O.counts_to_float_frame(ref_counts))
+    assert np.max(np.abs(X - refX) / np.max(np.abs(refX), axis=1, keepdims=True)) <= 1e-12
+    p = PCA(n_components=50, random_state=np.random.RandomState(42))
+    sc = p.fit_transform(refX)
+    assert p._fit_svd_solver == "covariance_eigh"
+    ref = dict(explained_variance=p.explained_variance_, explained_variance_ratio=p.explained_variance_ratio_,
+               components=p.components_, scores=sc)
+    got = {k: res[k].cpu().numpy() for k in ref}
+    _check_pca(got, ref)
+
+
+def test_eigh_against_numpy(torch_cuda):
+    import torch
+
+    from autometa_b200 import device as D
+
+    rng = np.random.default_rng(1)
+    for n in (2, 5, 64, 511, 512):
+        A_ = rng.normal(size=(n, n + 3))
+        S = A_ @ A_.T / n
+        w, V = D.eigh_desc(torch.from_numpy(S).cuda())
+        w = w.cpu().numpy()
+        V = V.cpu().numpy()
+        wr = np.linalg.eigvalsh(S)[::-1]
+        assert np.max(np.abs(w - wr)) <= 1e-12 * wr[0]
+        assert np.max(np.abs(V @ V.T - np.eye(n))) < 1e-12
+        assert np.max(np.abs(S @ V.T - V.T * w)) <= 1e-11 * wr[0]
+        idx = np.argmax(np.abs(V), axis=1)
+        assert np.all(V[np.arange(n), idx] > 0)  # svd_flip(u_based_decision=False)
+
+
+# ---------------------------------------------------------------------------- DBSCAN
+def _sweep_table():
+    from autometa_b200 import synth
+
+    return synth.make_sweep_input(n_points=3000, n_clusters=12, n_markers=40, seed=11)
+
+
+def test_run_dbscan_matches_reference_golden(torch_cuda, golden_dbscan):
+    from autometa_b200.binning import recursive_dbscan as R
+    from autometa_b200.common.exceptions import TableFormatError
+
+    table, _ = _sweep_table()
+    for i, eps in enumerate(golden_dbscan["eps_list"]):
+        df = table.copy()
+        df["purity"] = 1.0  # must be dropped in place (recursive_dbscan.py:95)
+        out = R.run_dbscan(df, eps=float(eps))
+        assert "purity" not in df.columns and "purity" not in out.columns
+        assert out["cluster"].dtype == np.int64
+        assert np.array_equal(out["cluster"].to_numpy(), golden_dbscan[f"labels_{i}"]), eps
+        assert out.index.equals(table.index)
+    one = R.run_dbscan(table.iloc[:1].copy(), eps=0.3)
+    assert one["cluster"].isna().all()
+    bad = table.copy()
+    bad.iloc[3, 0] = np.nan
+    with pytest.raises(TableFormatError):
+        R.run_dbscan(bad, eps=0.3)
+
+
+def test_recursive_dbscan_matches_reference_golden(torch_cuda, golden_dbscan):
+    from autometa_b200.binning import recursive_dbscan as R
+
+    table, markers = _sweep_table()
+    clustered, unclustered = R.recursive_dbscan(table.copy(), markers, 20.0, 90.0, 25.0, 5.0)
+    assert clustered.columns.tolist() == golden_dbscan["clustered_columns"].tolist()
+    assert clustered.index.tolist() == golden_dbscan["clustered_index"].tolist()
+    assert np.array_equal(clustered["cluster"].to_numpy(), golden_dbscan["clustered_cluster"])
+    for m in ["completeness", "purity", "coverage_stddev", "gc_content_stddev"]:
+        np.testing.assert_allclose(clustered[m].to_numpy(dtype=float), golden_dbscan[f"clustered_{m}"],
+                                   rtol=1e-12, atol=1e-12)
+    assert unclustered.index.tolist() == golden_dbscan["unclustered_index"].tolist()
+    assert np.array_equal(unclustered["cluster"].to_numpy(), golden_dbscan["unclustered_cluster"])
+
+
+def test_sweep_incremental_equals_fresh_and_oracle(torch_cuda):
+    import torch
+
+    from autometa_b200 import device as D, synth
+
+    table, _ = synth.make_sweep_input(20000, 60, 10, seed=5)
+    X = np.ascontiguousarray(table[["x_1", "x_2", "coverage"]].to_numpy())
+    Xd = torch.from_numpy(X).cuda()
+    sweep = D.EpsSweep(Xd)
+    prev_n = None
+    for eps in O.eps_schedule(48)[::6] + [14.6, 40.0, 400.0]:
+        inc = sweep.step(eps).cpu().numpy()
+        fresh = D.EpsSweep(Xd).step(eps).cpu().numpy()
+        assert np.array_equal(inc, fresh)
+        n = int(sweep.n_clusters.item())
+        assert n == inc.max() + 1
+        # labels are numbered by first occurrence (sklearn's visiting order)
+        first = np.unique(inc, return_index=True)[1]
+        assert np.all(np.diff(first) > 0)
+        if prev_n is not None:
+            assert n <= prev_n
+        prev_n = n
+        if eps <= 3.5:
+            assert np.array_equal(inc, O.dbscan_labels(X, eps)), eps
+    assert prev_n == 1
+
+
+def test_sweep_full_size_c4(torch_cuda):
+    """C4: 200k points, reference eps grid; identical to sklearn at a few eps (sklearn is what
+    recursive_dbscan.py:109 executes) and monotone merging everywhere."""
+    import torch
+    from sklearn.cluster import DBSCAN
+
+    from autometa_b200 import device as D, synth
+
+    table, _ = synth.make_sweep_input()
+    X = np.ascontiguousarray(table[["x_1", "x_2", "coverage"]].to_numpy())
+    sweep = D.EpsSweep(torch.from_numpy(X).cuda())
+    grid = O.eps_schedule(48)
+    check = {0: None, 5: None, 17: None, 47: None}
+    prev = None
+    for i, eps in enumerate(grid):
+        lab = sweep.step(eps)
+        n = int(sweep.n_clusters.item())
+        if prev is not None:
+            assert n <= prev
+        prev = n
+        if i in check:
+            ref = DBSCAN(eps=eps, min_samples=1, n_jobs=-1).fit(X).labels_
+            assert np.array_equal(lab.cpu().numpy(), ref.astype(np.int64)), eps

@@ -1,0 +1,228 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, host
+logic (FASTA index, packers, work list, metrics, sharding) matches the oracle and
+the reference's golden outputs.  No CUDA compute calls here."""
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import oracle_np as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from autometa_b200 import _lib as L
+
+    hdr = open(os.path.join(ROOT, "include", "autometa_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(am_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(L.lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(L.EXPORTS)
+    assert L.lib.am_version() >= 100
+
+
+def test_column_table_matches_oracle():
+    from autometa_b200 import device as D
+
+    for k in range(1, 8):
+        names, lut = O.kmer_columns(k)
+        assert D.num_columns(k) == len(names)
+        assert D.column_names(k) == names
+        assert np.array_equal(D.column_lut(k), lut)
+
+
+def test_init_kmers_api(golden_kmers):
+    from autometa_b200.common import kmers
+
+    d = kmers.init_kmers(5)
+    assert list(d) == golden_kmers["count_columns"].tolist()
+    assert list(d.values()) == list(range(512))
+    with pytest.raises(TypeError):
+        kmers.init_kmers(5.5)
+    assert kmers._revcomp("AACGT") == "ACGTT"
+
+
+def test_fasta_index_matches_oracle(small_fna, tmp_path):
+    from autometa_b200 import assembly as A
+
+    ids, seqs = O.read_fasta(small_fna)
+    h = A.read_fasta(small_fna)
+    assert h.ids == ids
+    assert [bytes(h.seq[h.offsets[i] : h.offsets[i + 1]]) for i in range(h.n_contigs)] == seqs
+    # gz, CRLF, blank lines, header-only record, no trailing newline
+    import gzip
+
+    raw = b">a x y\r\nAC GT\r\n\r\nNN\r\n>b\n>c\tq\nacgt"
+    p = tmp_path / "t.fa.gz"
+    with gzip.open(p, "wb") as fh:
+        fh.write(raw)
+    h = A.read_fasta(str(p))
+    assert h.ids == ["a", "b", "c"]
+    assert [bytes(h.seq[h.offsets[i] : h.offsets[i + 1]]) for i in range(3)] == [b"ACGTNN", b"", b"acgt"]
+    assert O.read_fasta(str(p))[1] == [b"ACGTNN", b"", b"acgt"]
+    with pytest.raises(FileNotFoundError):
+        A.read_fasta(str(tmp_path / "missing.fa"))
+
+
+def _py_pack(seqs):
+    enc = {65: 0, 84: 1, 67: 2, 71: 3}
+    starts, pos = [], 0
+    for s in seqs:
+        starts.append(pos)
+        pos += (len(s) + 63) // 64 * 64
+    total = pos + 128
+    codes = np.zeros(total // 16, dtype=np.uint32)
+    masks = {}
+    for st, s in zip(starts, seqs):
+        for j, ch in enumerate(s):
+            b = st + j
+            if ch in enc:
+                codes[b >> 4] |= np.uint32(enc[ch] << (2 * (b & 15)))
+            else:
+                masks[b >> 6] = masks.get(b >> 6, 0) | (1 << (b & 63))
+    return np.array(starts), total, codes, masks
+
+
+def test_pack_host_matches_python_restatement(small_fna):
+    from autometa_b200 import assembly as A
+
+    h = A.read_fasta(small_fna)
+    _, seqs = O.read_fasta(small_fna)
+    for threads in (1, 3):
+        starts, lengths, total, codes, bitmap, rank, masks = A.pack_host_arrays(h, threads)
+        pstarts, ptotal, pcodes, pmasks = _py_pack(seqs)
+        assert np.array_equal(starts, pstarts) and total == ptotal
+        assert np.array_equal(lengths, [len(s) for s in seqs])
+        assert np.array_equal(codes, pcodes)
+        groups = sorted(pmasks)
+        flagged = [g for g in range(total // 64) if (bitmap[g >> 5] >> (g & 31)) & 1]
+        assert flagged == groups
+        assert [int(m) for m in masks] == [pmasks[g] for g in groups]
+        for g in groups:
+            r = int(rank[g >> 5]) + bin(int(bitmap[g >> 5]) & ((1 << (g & 31)) - 1)).count("1")
+            assert int(masks[r]) == pmasks[g]
+
+
+def test_count_plan():
+    from autometa_b200 import assembly as A
+
+    lengths = np.array([3, 5, 6, 2048 + 5, 40000, 100000, 7], dtype=np.int32)
+    items, multi = A.count_plan(lengths, 5, 32768)
+    assert multi.tolist() == [4, 5]
+    per = {}
+    for c, w0, nw, fl in items.tolist():
+        assert w0 % 2048 == 0 and 0 <= nw <= 32768
+        assert fl == (1 if c in (4, 5) else 0)
+        per.setdefault(c, []).append((w0, nw))
+    for c, L in enumerate(lengths.tolist()):
+        spans = sorted(per[c])
+        assert sum(n for _, n in spans) == max(L - 5, 0)
+        pos = 0
+        for w0, n in spans:
+            assert w0 == pos
+            pos += n
+
+
+def _sweep_table():
+    from autometa_b200 import synth
+
+    return synth.make_sweep_input(n_points=3000, n_clusters=12, n_markers=40, seed=11)
+
+
+def test_add_metrics_matches_reference_golden(golden_dbscan):
+    from autometa_b200.binning import utilities as U
+
+    table, markers = _sweep_table()
+    df = table.copy()
+    df["cluster"] = golden_dbscan["labels_2"]  # eps = 1.2
+    cdf, mdf = U.add_metrics(df, markers)
+    assert mdf.index.name == "cluster"
+    assert np.array_equal(mdf.index.to_numpy(), golden_dbscan["metrics_cluster_index"])
+    assert list(mdf.columns) == U.METRICS
+    for name in U.METRICS:
+        np.testing.assert_allclose(mdf[name].to_numpy(dtype=float), golden_dbscan[f"metrics_{name}"],
+                                   rtol=1e-12, atol=1e-12, equal_nan=True)
+        np.testing.assert_allclose(cdf[name].to_numpy(dtype=float), golden_dbscan[f"contig_{name}"],
+                                   rtol=1e-12, atol=1e-12, equal_nan=True)
+    assert list(cdf.columns) == ["x_1", "x_2", "coverage", "gc_content", "cluster"] + U.METRICS
+    f = U.apply_binning_metrics_filter(mdf, 20.0, 90.0, 25.0, 5.0)
+    ok = U.passing_mask({k: mdf[k].to_numpy(dtype=float) for k in U.METRICS}, 20.0, 90.0, 25.0, 5.0)
+    assert np.array_equal(f.index.to_numpy(), mdf.index.to_numpy()[ok])
+    with pytest.raises(KeyError):
+        U.apply_binning_metrics_filter(table)
+    # no 'cluster' column -> NA metrics (utilities.py:163-171)
+    c2, m2 = U.add_metrics(table.copy(), markers)
+    assert c2[U.METRICS].isna().all().all()
+
+
+def test_api_errors_before_any_gpu_work(tmp_path):
+    from autometa_b200.common import kmers
+    from autometa_b200.common.exceptions import TableFormatError
+
+    with pytest.raises(TypeError):
+        kmers.count("whatever.fna", size=5.5)
+    df = pd.DataFrame({"AAA": [1, 2]}, index=pd.Index(["a", "b"], name="contig"))
+    with pytest.raises(ValueError):
+        kmers.normalize(df, method="am_clrs")
+    with pytest.raises(TypeError):
+        kmers.embed(kmers=12345)
+    with pytest.raises(FileNotFoundError):
+        kmers.embed(kmers=pd.DataFrame())
+    with pytest.raises(ValueError):
+        kmers.embed(kmers=df, method="nope")
+    with pytest.raises(FileNotFoundError):
+        kmers.load(str(tmp_path / "none.tsv"))
+    bad = tmp_path / "bad.tsv"
+    bad.write_text("a\tb\n1\t2\n")
+    with pytest.raises(TableFormatError):
+        kmers.load(str(bad))
+    # cached outputs are returned without recomputation (kmers.py:310-314, 406-412)
+    cache = tmp_path / "counts.tsv"
+    df.to_csv(cache, sep="\t")
+    got = kmers.count("does-not-matter.fna", size=5, out=str(cache), force=False)
+    assert got.index.name == "contig" and got.shape == (2, 1)
+    got = kmers.normalize(df, out=str(cache), force=False)
+    assert got.shape == (2, 1)
+
+
+def test_no_cpu_fallback(monkeypatch):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from autometa_b200.common import kmers
+
+    df = pd.DataFrame({"AAA": [1, 2], "AAT": [3, 4]}, index=pd.Index(["a", "b"], name="contig"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        kmers.normalize(df, method="am_clr")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        kmers.pca(np.random.rand(20, 4), n_components=2)
+
+
+def test_synth_is_seeded():
+    from autometa_b200 import synth
+
+    a = synth.make_assembly(50, 50 * 3600, seed=9, tiny=True)
+    b = synth.make_assembly(50, 50 * 3600, seed=9, tiny=True)
+    assert a.ids == b.ids and np.array_equal(a.offsets, b.offsets)
+    assert np.array_equal(a.seq[: a.total_bp], b.seq[: b.total_bp])
+    assert a.total_bp == 50 * 3600 + 15 and a.lengths[-3:].tolist() == [4, 5, 6]
+    assert a.lengths[:-3].min() >= 3000
+
+
+def test_shard_ranges_balance_and_cover():
+    from autometa_b200 import dist as DD, synth
+
+    rng = np.random.default_rng(0)
+    lens = synth.contig_lengths(5000, 5000 * 5000, rng)
+    for w in (1, 2, 4, 8):
+        r = DD.shard_ranges(lens, w)
+        assert r[0][0] == 0 and r[-1][1] == len(lens)
+        assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+        bp = np.array([lens[a:b].sum() for a, b in r])
+        assert bp.max() - bp.min() <= 2 * lens.max()

@@ -133,3 +133,24 @@ def test_cluster_metrics_match_reference(golden_dbscan):
 def test_eps_schedule_known_answers():
     s = O.eps_schedule(12)
     assert s[5] == 0.7999999999999999 and s[8] == 1.0999999999999999 and s[11] == 1.4000000000000001
+
+
+def test_c_port_matches_numpy_oracle_and_golden(golden_kmers, small_fna):
+    from autometa_b200 import synth
+    from oracle import oracle_c
+
+    ids, seqs = O.read_fasta(small_fna)
+    offsets = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.int64)
+    seq = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    for k in (3, 5, 6):
+        ref, _ = O.count_sequences(seqs, k)
+        for threads in (1, 3):
+            assert np.array_equal(oracle_c.count(seq, offsets, k, threads), ref)
+    asm = synth.make_assembly(80, 80 * 3500, seed=4, tiny=True)
+    ref, ok = O.count_sequences(synth.sequences(asm), 5)
+    got = oracle_c.count(asm.seq, asm.offsets, 5, 4)
+    assert np.array_equal(got, ref)
+    keep = ref.sum(axis=1) > 0
+    a = oracle_c.am_clr(got[keep], 2)
+    b, _, _ = O.am_clr(O.counts_to_float_frame(ref))
+    assert np.max(np.abs(a - b)) <= 1e-13 * np.max(np.abs(b))
