@@ -144,7 +144,7 @@ static void init_b2c() {
 int am_pack_host(const uint8_t *seq, const int64_t *offsets, int64_t n, const int64_t *starts,
                  int64_t total, uint32_t *codes, uint32_t *bitmap, uint32_t *rank,
                  uint64_t *exc_mask, int64_t exc_capacity, int64_t *n_exc, int n_threads) {
-  if (!seq || !offsets || !starts || !codes || !bitmap || !rank || !n_exc)
+  if (!seq || !offsets || n < 0 || (n > 0 && !starts) || !codes || !bitmap || !rank || !n_exc)
     return am::fail(AM_EINVAL, "am_pack_host: bad args");
   init_b2c();
   const int64_t n_groups = total / AM_GROUP_BASES;
@@ -217,7 +217,7 @@ int am_pack_host(const uint8_t *seq, const int64_t *offsets, int64_t n, const in
 int am_count_plan(const int32_t *lengths, int64_t n, int k, int32_t max_item_bases,
                   int32_t *items, int64_t item_cap, int64_t *n_items, int32_t *multi_rows,
                   int64_t multi_cap, int64_t *n_multi) {
-  if (!lengths || !n_items || !n_multi || k < 1 || k > 7 || max_item_bases < AM_TILE_BASES ||
+  if (n < 0 || (n > 0 && !lengths) || !n_items || !n_multi || k < 1 || k > 7 || max_item_bases < AM_TILE_BASES ||
       max_item_bases % AM_TILE_BASES)
     return am::fail(AM_EINVAL, "am_count_plan: bad args");
   if (n > 0x7fffffff) return am::fail(AM_EINVAL, "am_count_plan: too many contigs");

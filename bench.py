@@ -74,9 +74,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None, t_load=None):
+        """Median SM clock over the samples taken inside [t0, t1] (the timed region); when the
+        region is shorter than the sampling period, over the samples since `t_load` (first warm-up)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -87,7 +89,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        window = "timed region"
+        rows = [ln for (ts, ln) in self.lines if t0 is None or (t0 - 0.02 <= ts <= t1 + 0.12)]
+        if len(rows) < 3 and t_load is not None:
+            rows = [ln for (ts, ln) in self.lines if ts >= t_load]
+            window = "warm-up + timed region (timed region shorter than 3 samples)"
+        for ln in rows:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -103,6 +110,7 @@ class ClockSampler:
             "sm_mhz": float(np.median(sm)) if sm else None,
             "sm_max_mhz": float(max(mx)) if mx else None,
             "samples": len(sm),
+            "window": window,
             "reasons": sorted(reasons),
         }
 
@@ -238,6 +246,13 @@ def main():
     def run_step(marks=None):
         return pipeline.featurise(packed, K, "am_clr", NCOMP, distributed=distributed, keep=False, marks=marks)
 
+    # clocks are sampled from the first warm-up step to the end of the timed region (nvidia-smi needs
+    # ~0.3 s to start and samples every 100 ms, so a short timed region alone could fall between samples)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)
+    t_load = time.time()
     for _ in range(args.warmup):
         run_step()
     torch.cuda.synchronize()
@@ -245,13 +260,11 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev_start = torch.cuda.Event(enable_timing=True)
     ev_end = torch.cuda.Event(enable_timing=True)
     step_marks = []
     launches0 = L.launch_count()
+    t_timed0 = time.time()
     ev_start.record()
     for _ in range(args.steps):
         marks = []
@@ -263,7 +276,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     launches = L.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_timed0, time.time(), t_load) if rank == 0 else None
     ms_total = ev_start.elapsed_time(ev_end)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if distributed:

@@ -264,7 +264,9 @@ def test_pca_on_kmer_features_vs_oracle(torch_cuda):
     packed = A.pack_to_device(asm, device="cuda:0", on_device=True)
     res = pipeline.featurise(packed, 5, "am_clr", 50)
     X = res["normalized"].cpu().numpy()
-    assert X.shape == (6000, 512)  # the three tiny contigs are dropped by am_clr
+    # am_clr drops the tiny contigs of length 4 and 5 (no window: all-NA rows, kmers.py:187-192,369);
+    # the length-6 one has exactly one window (L-k = 1) and stays
+    assert X.shape == (6001, 512)
     ref_counts, _ = O.count_sequences(synth.sequences(asm), 5)
     assert np.array_equal(res["counts"].cpu().numpy(), ref_counts)
     refX, _, _ = O.am_clr(O.counts_to_float_frame(ref_counts))
