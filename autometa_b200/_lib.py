@@ -62,6 +62,8 @@ _SIGS = {
     "am_gram": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
     "am_eigh_work_bytes": (_i64, [_i32]),
     "am_eigh": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _f64, _p]),
+    "am_eigh_topk_work_bytes": (_i64, [_i32, _i32]),
+    "am_eigh_topk": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p]),
     "am_project": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _p, _p]),
     "am_dbscan_work_bytes": (_i64, [_i64]),
     "am_eps_union": (C.c_int, [_p, _i64, _i32, _f64, _p, _p, _p, _p, _p]),

@@ -250,17 +250,17 @@ def pca_device(Xd, n_components: int, group=None) -> Dict[str, Any]:
 
         dist.all_reduce(G, group=group if group is not True else None)
     C = G / (n - 1.0)
-    evals, evecs = _dev.eigh_desc(C)
+    # only the leading n_components pairs are solved; total variance = trace (sum of all eigenvalues)
+    evals, comps, total = _dev.eigh_topk(C, n_components)
     evals = torch.clamp(evals, min=0.0)  # _pca.py:630
-    total = evals.sum()
-    comps = evecs[:n_components].contiguous()
+    total = total.reshape(())
     scores = _dev.project(Xd, mu, comps)
     return dict(
         scores=scores,
         mean=mu,
         components=comps,
-        explained_variance=evals[:n_components].clone(),
-        explained_variance_ratio=evals[:n_components] / total,
+        explained_variance=evals.clone(),
+        explained_variance_ratio=evals / total,
         total_variance=total,
         covariance=C,
     )

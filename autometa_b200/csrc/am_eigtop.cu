@@ -1,0 +1,586 @@
+// Top-P eigenpairs of the symmetric D x D covariance (D = 512 for k = 5) — sm_100a.
+//
+// Replaces scipy.linalg.eigh inside sklearn PCA._fit_full(covariance_eigh)
+// (sklearn/decomposition/_pca.py:611-624) for the P = pca_dimensions leading pairs that
+// kmers.embed keeps (autometa/common/kmers.py:601-605), with svd_flip(u_based_decision=False)
+// (sklearn/utils/extmath.py:973-981) applied to the rows.  Same route as LAPACK's dsyevx:
+//
+//   1. tridiag_cluster_kernel  Householder tridiagonalisation Q^T A Q = T.  ONE thread-block
+//      cluster of 16 CTAs holds the whole matrix in distributed shared memory (row i lives in CTA
+//      i mod 16), so the 510 dependent steps never touch L2/HBM: per step every CTA does a fused
+//      "apply previous rank-2 update + mat-vec with the new reflector" pass over its rows, the
+//      p = tau*A*v slices are all-gathered with DSMEM stores, and ONE cluster barrier closes the
+//      step; the O(D) reflector algebra is replicated in every CTA (bit-identical by construction).
+//   2. bisect_kernel           P leading eigenvalues of T by multisection on the Sturm count
+//      (one CTA per eigenvalue, 512 shifts per round).
+//   3. invit_kernel            eigenvectors of T by inverse iteration (LU with partial pivoting).
+//   4. cholqr_kernel           re-orthonormalisation (CholeskyQR2) — only matters for clusters.
+//   5. backtransform_kernel    z = Q y (reflectors applied in reverse), sign rule, output.
+#include <cooperative_groups.h>
+
+#include "am_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int TC = 16;        // CTAs in the cluster
+constexpr int TT = 512;       // threads per CTA
+constexpr int TW = TT / 32;   // warps per CTA
+constexpr int MAXRPW = 3;     // local rows per warp (RL <= 48)
+constexpr int SMEM_N_MAX = 576;
+constexpr int PMAX = 128;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// all threads get the same, order-deterministic total; `red` holds >= 32 doubles
+template <int NW>
+__device__ __forceinline__ double block_sum(double v, double *red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = (threadIdx.x & 31) < NW ? red[threadIdx.x & 31] : 0.0;
+  s = warp_sum(s);
+  __syncthreads();
+  return s;
+}
+
+struct TriOut {
+  double *V;     // [n][np] reflectors (v_k in row k; zeros up to k, 1 at k+1)
+  double *tau;   // [n]
+  double *d;     // [n]
+  double *e;     // [n]  (e[i] couples i and i+1)
+};
+
+// ------------------------------------------------------------------ 1. tridiagonalisation
+__global__ void __cluster_dims__(TC, 1, 1) __launch_bounds__(TT, 1)
+tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriOut out) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int c = (int)cluster.block_rank();
+  extern __shared__ double sm[];
+  double *rows = sm;                          // RL x np
+  double *vb = rows + (size_t)RL * np;        // 2 x np
+  double *wb = vb + 2 * np;                   // 2 x np
+  double *x = wb + 2 * np;                    // np
+  double *gP = x + np;                        // 2 x np  (all-gathered p slices)
+  double *gA = gP + 2 * np;                   // 2 x np  (all-gathered next-column slices)
+  double *red = gA + 2 * np;                  // 32
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // load own rows (symmetrised), zero the vectors
+  for (int lr = 0; lr < RL; ++lr) {
+    const int i = c + TC * lr;
+    for (int j = tid; j < np; j += TT) {
+      double a = 0.0;
+      if (i < n && j < n) a = 0.5 * (__ldg(A + (size_t)i * n + j) + __ldg(A + (size_t)j * n + i));
+      rows[(size_t)lr * np + j] = a;
+    }
+  }
+  for (int j = tid; j < 2 * np; j += TT) { vb[j] = 0.0; wb[j] = 0.0; gP[j] = 0.0; gA[j] = 0.0; }
+  for (int j = tid; j < np; j += TT) x[j] = 0.0;
+  __syncthreads();
+  cluster.sync();  // every CTA's buffers exist and are zeroed before any remote store
+
+  // prologue: all-gather column 0 into gA[1]
+  for (int lr = warp; lr < RL; lr += TW) {
+    const int i = c + TC * lr;
+    if (i < n && lane < TC) {
+      double *dst = cluster.map_shared_rank(gA + np + i, lane);
+      *dst = rows[(size_t)lr * np + 0];
+    }
+  }
+  cluster.sync();
+  double sig_part = 0.0;
+  for (int i = tid; i < np; i += TT) {
+    const double xv = (i >= 1 && i < n) ? gA[np + i] : 0.0;
+    x[i] = xv;
+    if (i >= 2) sig_part += xv * xv;
+  }
+  double sigma = block_sum<TW>(sig_part, red);
+
+  for (int k = 0; k <= n - 3; ++k) {
+    double *vcur = vb + (k & 1) * np, *wcur = wb + (k & 1) * np;
+    const double *vprev = vb + ((k + 1) & 1) * np, *wprev = wb + ((k + 1) & 1) * np;
+    // ---- A. reflector from x (replicated in every CTA)
+    const double alpha = x[k + 1];
+    double beta, tau, scale;
+    if (!(sigma > 1e-290)) {
+      beta = alpha; tau = 0.0; scale = 0.0;
+    } else {
+      beta = -copysign(sqrt(alpha * alpha + sigma), alpha);
+      tau = (beta - alpha) / beta;
+      scale = 1.0 / (alpha - beta);
+    }
+    __syncthreads();  // all reads of x[k+1] / previous vcur slot done before overwriting
+    for (int i = tid; i < np; i += TT)
+      vcur[i] = (i == k + 1) ? 1.0 : ((i > k + 1 && i < n) ? x[i] * scale : 0.0);
+    if (c == 0 && tid == 0) { out.e[k] = beta; out.tau[k] = tau; }
+    __syncthreads();
+    if (c == (k % TC))
+      for (int i = tid; i < np; i += TT) out.V[(size_t)k * np + i] = vcur[i];
+
+    // ---- B. fused pass over own rows >= k: apply pending update (k-1), p = tau * A v_k
+    {
+      int lrs[MAXRPW];
+      double vpi[MAXRPW], wpi[MAXRPW], acc[MAXRPW];
+      int nr = 0;
+#pragma unroll
+      for (int r = 0; r < MAXRPW; ++r) {
+        const int lr = warp + TW * r;
+        const int i = c + TC * lr;
+        lrs[r] = -1; vpi[r] = 0.0; wpi[r] = 0.0; acc[r] = 0.0;
+        if (lr < RL && i < n && i >= k) { lrs[r] = lr; vpi[r] = vprev[i]; wpi[r] = wprev[i]; nr = r + 1; }
+      }
+      if (nr > 0) {
+        for (int j = (k & ~31) + lane; j < np; j += 32) {
+          const double vpj = vprev[j], wpj = wprev[j], vcj = vcur[j];
+#pragma unroll
+          for (int r = 0; r < MAXRPW; ++r) {
+            if (lrs[r] >= 0) {
+              double *ap = rows + (size_t)lrs[r] * np + j;
+              double a = *ap;
+              a = fma(-vpi[r], wpj, a);
+              a = fma(-wpi[r], vpj, a);
+              *ap = a;
+              acc[r] = fma(a, vcj, acc[r]);
+            }
+          }
+        }
+        __syncwarp();
+        const int buf = k & 1;
+#pragma unroll
+        for (int r = 0; r < MAXRPW; ++r) {
+          if (lrs[r] >= 0) {
+            const int i = c + TC * lrs[r];
+            const double p = tau * warp_sum(acc[r]);
+            const double a1 = rows[(size_t)lrs[r] * np + (k + 1)];  // post-update A[i][k+1]
+            if (i >= k + 1) {
+              if (lane < TC) *cluster.map_shared_rank(gP + buf * np + i, lane) = p;
+              else *cluster.map_shared_rank(gA + buf * np + i, lane - TC) = a1;
+            }
+          }
+        }
+      }
+    }
+    cluster.sync();
+
+    // ---- C. w_k, next column x_{k+1} (replicated)
+    const double *P = gP + (k & 1) * np, *AC = gA + (k & 1) * np;
+    double part = 0.0;
+    for (int j = tid; j < np; j += TT)
+      if (j >= k + 1 && j < n) part = fma(P[j], vcur[j], part);
+    const double gamma = block_sum<TW>(part, red);
+    const double Kc = 0.5 * tau * gamma;
+    for (int j = tid; j < np; j += TT) wcur[j] = (j >= k + 1 && j < n) ? fma(-Kc, vcur[j], P[j]) : 0.0;
+    __syncthreads();
+    const double wk1 = wcur[k + 1];
+    sig_part = 0.0;
+    for (int i = tid; i < np; i += TT) {
+      double xv = 0.0;
+      if (i >= k + 2 && i < n) xv = AC[i] - vcur[i] * wk1 - wcur[i];
+      x[i] = xv;
+      if (i >= k + 3) sig_part += xv * xv;
+    }
+    sigma = block_sum<TW>(sig_part, red);
+  }
+
+  // epilogue: pending update (n-3) on rows/cols >= n-2, then d and the last e
+  {
+    const int k = n - 2;
+    const double *vprev = vb + ((k + 1) & 1) * np, *wprev = wb + ((k + 1) & 1) * np;
+    for (int lr = warp; lr < RL; lr += TW) {
+      const int i = c + TC * lr;
+      if (i < n && i >= k) {
+        const double vi = vprev[i], wi = wprev[i];
+        for (int j = (k & ~31) + lane; j < np; j += 32) {
+          double *ap = rows + (size_t)lr * np + j;
+          double a = *ap;
+          a = fma(-vi, wprev[j], a);
+          a = fma(-wi, vprev[j], a);
+          *ap = a;
+        }
+      }
+    }
+    __syncthreads();
+    for (int lr = tid; lr < RL; lr += TT) {
+      const int i = c + TC * lr;
+      if (i < n) {
+        out.d[i] = rows[(size_t)lr * np + i];
+        if (i == n - 1) { out.e[n - 2] = rows[(size_t)lr * np + (n - 2)]; out.e[n - 1] = 0.0; out.tau[n - 2] = 0.0; out.tau[n - 1] = 0.0; }
+      }
+    }
+  }
+  cluster.sync();  // no CTA exits while a peer may still address its shared memory
+}
+
+// ------------------------------------------------------------------ 2. bisection
+constexpr int BT = 512;  // shifts per round
+
+__device__ __forceinline__ int sturm_count(const double *d, const double *e2, int n, double x, double pivmin) {
+  // number of eigenvalues of T that are < x (LAPACK dlaebz recurrence)
+  int cnt = 0;
+  double q = d[0] - x;
+  if (fabs(q) < pivmin) q = -pivmin;
+  cnt += q < 0.0;
+  for (int i = 1; i < n; ++i) {
+    q = (d[i] - x) - e2[i - 1] / q;
+    if (fabs(q) < pivmin) q = -pivmin;
+    cnt += q < 0.0;
+  }
+  return cnt;
+}
+
+__global__ void __launch_bounds__(BT)
+bisect_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int n, int P,
+              double *__restrict__ lam, double *__restrict__ trace) {
+  extern __shared__ double sm[];
+  double *d = sm, *e2 = sm + n, *red = sm + 2 * n;  // red: 64
+  __shared__ int first_warp[BT / 32];
+  __shared__ double s_lo, s_hi;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int jtop = blockIdx.x;  // jtop-th largest
+  double gl = 1e300, gu = -1e300, emax = 0.0, tr = 0.0;
+  for (int i = tid; i < n; i += BT) {
+    const double di = dg[i], el = i > 0 ? fabs(eg[i - 1]) : 0.0, er = i < n - 1 ? fabs(eg[i]) : 0.0;
+    d[i] = di;
+    e2[i] = i < n - 1 ? eg[i] * eg[i] : 0.0;
+    gl = fmin(gl, di - el - er);
+    gu = fmax(gu, di + el + er);
+    emax = fmax(emax, er * er);
+    tr += di;
+  }
+  // block min / max / sum
+  for (int o = 16; o > 0; o >>= 1) {
+    gl = fmin(gl, __shfl_xor_sync(FULL, gl, o));
+    gu = fmax(gu, __shfl_xor_sync(FULL, gu, o));
+    emax = fmax(emax, __shfl_xor_sync(FULL, emax, o));
+  }
+  if (lane == 0) { red[warp] = gl; red[16 + warp] = gu; red[32 + warp] = emax; }
+  __syncthreads();
+  gl = red[0]; gu = red[16]; emax = red[32];
+  for (int w = 1; w < BT / 32; ++w) { gl = fmin(gl, red[w]); gu = fmax(gu, red[16 + w]); emax = fmax(emax, red[32 + w]); }
+  __syncthreads();
+  tr = block_sum<BT / 32>(tr, red);
+  if (blockIdx.x == 0 && tid == 0 && trace) *trace = tr;
+  const double tnorm = fmax(fabs(gl), fabs(gu));
+  const double pivmin = 2.2250738585072014e-308 * fmax(1.0, emax);
+  const double ulp = 2.220446049250313e-16;
+  double lo = gl - 2.0 * tnorm * ulp * n - 2.0 * pivmin;
+  double hi = gu + 2.0 * tnorm * ulp * n + 2.0 * pivmin;
+  const int target = n - jtop;  // want smallest x with count(x) >= target  (lambda index n-1-jtop ascending)
+  for (int round = 0; round < 12; ++round) {
+    const double width = hi - lo;
+    if (!(width > 2.0 * ulp * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin)) break;
+    const double xt = lo + width * ((double)(tid + 1) / (double)(BT + 1));
+    const int cnt = sturm_count(d, e2, n, xt, pivmin);
+    const unsigned ball = __ballot_sync(FULL, cnt >= target);
+    if (lane == 0) first_warp[warp] = ball ? (warp * 32 + __ffs(ball) - 1) : -1;
+    __syncthreads();
+    if (tid == 0) {
+      int first = -1;
+      for (int w = 0; w < BT / 32; ++w)
+        if (first_warp[w] >= 0) { first = first_warp[w]; break; }
+      // points are lo + width*(t+1)/(BT+1)
+      double nlo, nhi;
+      if (first < 0) { nlo = lo + width * ((double)BT / (double)(BT + 1)); nhi = hi; }
+      else { nhi = lo + width * ((double)(first + 1) / (double)(BT + 1)); nlo = first == 0 ? lo : lo + width * ((double)first / (double)(BT + 1)); }
+      s_lo = nlo; s_hi = nhi;
+    }
+    __syncthreads();
+    lo = s_lo; hi = s_hi;
+    __syncthreads();
+  }
+  if (tid == 0) lam[jtop] = 0.5 * (lo + hi);
+}
+
+// ------------------------------------------------------------------ 3. inverse iteration
+__global__ void __launch_bounds__(32)
+invit_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int n, int np, int P,
+             const double *__restrict__ lam, double *__restrict__ Y) {
+  extern __shared__ double sm[];
+  double *dd = sm, *dl = sm + np, *du = sm + 2 * np, *du2 = sm + 3 * np, *rdd = sm + 4 * np, *b = sm + 5 * np;
+  int *piv = (int *)(sm + 6 * np);
+  const int lane = threadIdx.x;
+  const int j = blockIdx.x;
+  // shift: separate numerically coincident eigenvalues like dstein does
+  double tnorm = 0.0;
+  for (int i = lane; i < n; i += 32) tnorm = fmax(tnorm, fabs(dg[i]) + (i < n - 1 ? fabs(eg[i]) : 0.0) + (i > 0 ? fabs(eg[i - 1]) : 0.0));
+  for (int o = 16; o > 0; o >>= 1) tnorm = fmax(tnorm, __shfl_xor_sync(FULL, tnorm, o));
+  const double ulp = 2.220446049250313e-16;
+  double shift = lam[j];
+  {
+    // count how many earlier (larger) eigenvalues sit within 10 ulp*|T| of this one
+    int close = 0;
+    for (int q = j - 1; q >= 0; --q) {
+      if (fabs(lam[q] - lam[j]) <= 10.0 * ulp * tnorm) ++close; else break;
+    }
+    shift -= (double)close * 10.0 * ulp * tnorm;
+  }
+  const double tinyp = fmax(ulp * tnorm * 0.25, 1e-300);
+  for (int i = lane; i < n; i += 32) {
+    dd[i] = dg[i] - shift;
+    du[i] = i < n - 1 ? eg[i] : 0.0;
+    dl[i] = i < n - 1 ? eg[i] : 0.0;
+    du2[i] = 0.0;
+    // deterministic pseudo-random start in [-1, 1)
+    unsigned h = (unsigned)i * 2654435761u ^ ((unsigned)j + 1u) * 40503u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    b[i] = (double)(h >> 8) * (1.0 / 8388608.0) - 1.0;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    // LU with partial pivoting of the tridiagonal (LAPACK dgttrf)
+    for (int i = 0; i < n - 1; ++i) {
+      if (fabs(dd[i]) >= fabs(dl[i])) {
+        piv[i] = 0;
+        if (fabs(dd[i]) < tinyp) dd[i] = copysign(tinyp, dd[i]);
+        const double fact = dl[i] / dd[i];
+        dl[i] = fact;
+        dd[i + 1] -= fact * du[i];
+        du2[i] = 0.0;
+      } else {
+        piv[i] = 1;
+        const double fact = dd[i] / dl[i];
+        dd[i] = dl[i];
+        dl[i] = fact;
+        const double temp = du[i];
+        du[i] = dd[i + 1];
+        dd[i + 1] = temp - fact * dd[i + 1];
+        if (i < n - 2) { du2[i] = du[i + 1]; du[i + 1] = -fact * du[i + 1]; }
+      }
+    }
+    if (fabs(dd[n - 1]) < tinyp) dd[n - 1] = copysign(tinyp, dd[n - 1]);
+  }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) rdd[i] = 1.0 / dd[i];
+  __syncwarp();
+  for (int it = 0; it < 3; ++it) {
+    if (lane == 0) {
+      for (int i = 0; i < n - 1; ++i) {
+        if (!piv[i]) {
+          b[i + 1] -= dl[i] * b[i];
+        } else {
+          const double temp = b[i];
+          b[i] = b[i + 1];
+          b[i + 1] = temp - dl[i] * b[i];
+        }
+      }
+      b[n - 1] *= rdd[n - 1];
+      if (n > 1) b[n - 2] = (b[n - 2] - du[n - 2] * b[n - 1]) * rdd[n - 2];
+      for (int i = n - 3; i >= 0; --i) b[i] = (b[i] - du[i] * b[i + 1] - du2[i] * b[i + 2]) * rdd[i];
+    }
+    __syncwarp();
+    double mx = 0.0;
+    for (int i = lane; i < n; i += 32) mx = fmax(mx, fabs(b[i]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+    const double inv = mx > 0.0 ? 1.0 / mx : 1.0;
+    for (int i = lane; i < n; i += 32) b[i] *= inv;
+    __syncwarp();
+  }
+  double ss = 0.0;
+  for (int i = lane; i < n; i += 32) ss += b[i] * b[i];
+  ss = warp_sum(ss);
+  const double inv = 1.0 / sqrt(ss);
+  for (int i = lane; i < np; i += 32) Y[(size_t)j * np + i] = i < n ? b[i] * inv : 0.0;
+}
+
+// ------------------------------------------------------------------ 4. CholeskyQR2 on the P rows of Y
+constexpr int CT = 1024;
+__global__ void __launch_bounds__(CT)
+cholqr_kernel(double *__restrict__ Y, int n, int np, int P) {
+  extern __shared__ double sm[];
+  double *G = sm;  // P x P (row-major), becomes L (lower)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int npairs = P * (P + 1) / 2;
+    for (int pr = warp; pr < npairs; pr += CT / 32) {
+      // pr -> (a >= b)
+      int a = (int)((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
+      while (a * (a + 1) / 2 > pr) --a;
+      while ((a + 1) * (a + 2) / 2 <= pr) ++a;
+      const int bb = pr - a * (a + 1) / 2;
+      double s = 0.0;
+      for (int i = lane; i < n; i += 32) s = fma(Y[(size_t)a * np + i], Y[(size_t)bb * np + i], s);
+      s = warp_sum(s);
+      if (lane == 0) { G[a * P + bb] = s; G[bb * P + a] = s; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int cidx = 0; cidx < P; ++cidx) {
+        double dsum = G[cidx * P + cidx];
+        for (int m = 0; m < cidx; ++m) dsum -= G[cidx * P + m] * G[cidx * P + m];
+        const double lcc = sqrt(fmax(dsum, 1e-300));
+        __syncwarp();
+        for (int a = cidx + 1 + lane; a < P; a += 32) {
+          double s = G[a * P + cidx];
+          for (int m = 0; m < cidx; ++m) s -= G[a * P + m] * G[cidx * P + m];
+          G[a * P + cidx] = s / lcc;
+        }
+        if (lane == 0) G[cidx * P + cidx] = lcc;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // rows: q_a = (y_a - sum_{b<a} L[a][b] q_b) / L[a][a], independently per element i
+    for (int i = tid; i < n; i += CT) {
+      double q[PMAX];
+      for (int a = 0; a < P; ++a) {
+        double s = Y[(size_t)a * np + i];
+        for (int bq = 0; bq < a; ++bq) s = fma(-G[a * P + bq], q[bq], s);
+        q[a] = s / G[a * P + a];
+      }
+      for (int a = 0; a < P; ++a) Y[(size_t)a * np + i] = q[a];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ 5. back-transformation + sign + output
+constexpr int KT = 128;
+__global__ void __launch_bounds__(KT)
+backtransform_kernel(const double *__restrict__ V, const double *__restrict__ tau, int n, int np,
+                     const double *__restrict__ Y, const double *__restrict__ lam,
+                     double *__restrict__ evals, double *__restrict__ evecs) {
+  extern __shared__ double sm[];
+  double *z = sm;             // np
+  double *red = sm + np;      // 32
+  __shared__ double s_best[KT / 32];
+  __shared__ int s_idx[KT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = blockIdx.x;
+  for (int i = tid; i < np; i += KT) z[i] = Y[(size_t)j * np + i];
+  __syncthreads();
+  for (int k = n - 3; k >= 0; --k) {
+    const double *vk = V + (size_t)k * np;
+    const double tk = __ldg(tau + k);
+    double part = 0.0;
+    for (int i = (k & ~(KT - 1)) + tid; i < n; i += KT) part = fma(__ldg(vk + i), z[i], part);  // v_k is 0 up to k
+    const double s = tk * block_sum<KT / 32>(part, red);
+    for (int i = (k & ~(KT - 1)) + tid; i < n; i += KT) z[i] = fma(-s, __ldg(vk + i), z[i]);
+    // the block_sum of the next step synchronises before any z is read by another thread
+  }
+  __syncthreads();
+  // sklearn svd_flip(u_based_decision=False): largest-|.| entry (first occurrence) made positive
+  double best = -1.0;
+  int bidx = 0;
+  for (int i = tid; i < n; i += KT) {
+    const double a = fabs(z[i]);
+    if (a > best) { best = a; bidx = i; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(FULL, best, o);
+    const int oi = __shfl_xor_sync(FULL, bidx, o);
+    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+  }
+  if (lane == 0) { s_best[warp] = best; s_idx[warp] = bidx; }
+  __syncthreads();
+  best = s_best[0]; bidx = s_idx[0];
+  for (int w = 1; w < KT / 32; ++w)
+    if (s_best[w] > best || (s_best[w] == best && s_idx[w] < bidx)) { best = s_best[w]; bidx = s_idx[w]; }
+  const double sgn = z[bidx] < 0.0 ? -1.0 : 1.0;
+  for (int i = tid; i < n; i += KT) evecs[(size_t)j * n + i] = sgn * z[i];
+  if (tid == 0) evals[j] = lam[j];
+}
+
+inline int round_up32(int x) { return (x + 31) & ~31; }
+
+struct TopWork {
+  double *V, *tau, *d, *e, *lam, *Y;
+};
+
+int64_t carve_top(void *base, int n, int P, TopWork *w) {
+  const int np = round_up32(n);
+  int64_t off = 0;
+  char *p = (char *)base;
+  auto take = [&](int64_t bytes) {
+    char *q = p ? p + off : nullptr;
+    off += (bytes + 255) & ~(int64_t)255;
+    return (double *)q;
+  };
+  TopWork t;
+  t.V = take((int64_t)n * np * 8);
+  t.tau = take((int64_t)np * 8);
+  t.d = take((int64_t)np * 8);
+  t.e = take((int64_t)np * 8);
+  t.lam = take((int64_t)PMAX * 8);
+  t.Y = take((int64_t)P * np * 8);
+  if (w) *w = t;
+  return off;
+}
+
+}  // namespace
+
+extern "C" int64_t am_eigh_topk_work_bytes(int D, int P) {
+  if (D < 1 || P < 1) return 0;
+  return carve_top(nullptr, D, P, nullptr);
+}
+
+extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, double *d_evecs,
+                            double *d_trace, void *d_work, void *stream) {
+  if (D < 3 || D > SMEM_N_MAX) return am::fail(AM_EINVAL, "am_eigh_topk: D must be in 3..576 (use am_eigh otherwise)");
+  if (P < 1 || P > D || P > PMAX) return am::fail(AM_EINVAL, "am_eigh_topk: P must be in 1..min(D,128)");
+  if (!d_A || !d_evals || !d_evecs || !d_work) return am::fail(AM_EINVAL, "am_eigh_topk: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = D, np = round_up32(n);
+  const int RL = (n + TC - 1) / TC;
+  if (RL > MAXRPW * TW) return am::fail(AM_EINVAL, "am_eigh_topk: D too large for the cluster path");
+  TopWork w;
+  carve_top(d_work, n, P, &w);
+  TriOut out{w.V, w.tau, w.d, w.e};
+
+  // 1. tridiagonalisation (one cluster of 16 CTAs)
+  {
+    const size_t smem = ((size_t)RL * np + 9 * (size_t)np + 32) * sizeof(double);
+    if (smem > 227 * 1024) return am::fail(AM_EINVAL, "am_eigh_topk: matrix does not fit the cluster's shared memory");
+    AM_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AM_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(TC);
+    cfg.blockDim = dim3(TT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = TC;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AM_CUDA(cudaLaunchKernelEx(&cfg, tridiag_cluster_kernel, d_A, n, np, RL, out));
+    AM_LAUNCHED("tridiag_cluster_kernel");
+  }
+  // 2. bisection
+  {
+    const size_t smem = ((size_t)2 * n + 64) * sizeof(double);
+    bisect_kernel<<<P, BT, smem, st>>>(w.d, w.e, n, P, w.lam, d_trace);
+    AM_LAUNCHED("bisect_kernel");
+  }
+  // 3. inverse iteration
+  {
+    const size_t smem = ((size_t)7 * np) * sizeof(double);
+    if (smem > 48 * 1024)
+      AM_CUDA(cudaFuncSetAttribute(invit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    invit_kernel<<<P, 32, smem, st>>>(w.d, w.e, n, np, P, w.lam, w.Y);
+    AM_LAUNCHED("invit_kernel");
+  }
+  // 4. CholeskyQR2
+  if (P > 1) {
+    const size_t smem = (size_t)P * P * sizeof(double);
+    if (smem > 48 * 1024)
+      AM_CUDA(cudaFuncSetAttribute(cholqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cholqr_kernel<<<1, CT, smem, st>>>(w.Y, n, np, P);
+    AM_LAUNCHED("cholqr_kernel");
+  }
+  // 5. back-transformation
+  {
+    const size_t smem = ((size_t)np + 32) * sizeof(double);
+    backtransform_kernel<<<P, KT, smem, st>>>(w.V, w.tau, n, np, w.Y, w.lam, d_evals, d_evecs);
+    AM_LAUNCHED("backtransform_kernel");
+  }
+  return AM_OK;
+}

@@ -175,6 +175,34 @@ def eigh_desc(A, max_sweeps: int = 30, tol: float = 0.0):
     return evals, evecs
 
 
+TOPK_MAX_D = 576
+TOPK_MAX_P = 128
+
+
+def eigh_topk(A, P: int):
+    """Leading ``P`` eigenpairs of symmetric ``A`` (descending) and the trace.
+
+    Cluster/DSMEM tridiagonalisation path for 3 <= D <= 576 and P <= 128; other shapes
+    go through the full Jacobi solver (``eigh_desc``) and are cut to P."""
+    import torch
+
+    dev = A.device
+    D = A.shape[0]
+    if not (3 <= D <= TOPK_MAX_D and 1 <= P <= min(D, TOPK_MAX_P)):
+        evals, evecs = eigh_desc(A)
+        return evals[:P].contiguous(), evecs[:P].contiguous(), torch.clamp(evals, min=0.0).sum().reshape(1)
+    with torch.cuda.device(dev):
+        evals = torch.empty(P, dtype=torch.float64, device=dev)
+        evecs = torch.empty((P, D), dtype=torch.float64, device=dev)
+        trace = torch.empty(1, dtype=torch.float64, device=dev)
+        work = _work(dev, L.lib.am_eigh_topk_work_bytes(D, P), "eigtop")
+        L.check(
+            L.lib.am_eigh_topk(L.t_ptr(A), D, P, L.t_ptr(evals), L.t_ptr(evecs), L.t_ptr(trace),
+                               L.t_ptr(work), L.stream_ptr(dev))
+        )
+    return evals, evecs, trace
+
+
 def project(X, mu, comps, out=None):
     import torch
 

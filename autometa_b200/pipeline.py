@@ -69,18 +69,16 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
             _dist.allreduce_sum_([G], group)
         C = G / (n_t - 1.0)
         mark("gram")
-        evals, evecs = _dev.eigh_desc(C)
+        P = min(n_components, Dout)
+        evals, comps, total = _dev.eigh_topk(C, P)
         mark("eigh")
         evals = torch.clamp(evals, min=0.0)
-        total = evals.sum()
-        P = min(n_components, Dout)
-        comps = evecs[:P].contiguous()
         scores = _dev.project(X, mu, comps)
         mark("project")
         out = dict(
             scores=scores,
-            explained_variance=evals[:P],
-            explained_variance_ratio=evals[:P] / total,
+            explained_variance=evals,
+            explained_variance_ratio=evals / total,
             components=comps,
             mean=mu,
             row_index=row_index,

@@ -189,6 +189,15 @@ int am_gram(const double *d_X, int64_t n_rows, int D, const double *d_mu,
 int64_t am_eigh_work_bytes(int D);
 int am_eigh(const double *d_A, int D, double *d_evals, double *d_evecs,
             void *d_work, int max_sweeps, double tol, void *stream);
+/* Leading P eigenpairs only (what kmers.embed keeps: pca_dimensions = 50, kmers.py:601-605)
+ * by Householder tridiagonalisation inside one 16-CTA cluster (matrix resident in distributed
+ * shared memory), Sturm-count multisection, inverse iteration and back-transformation — the
+ * dsyevx route.  3 <= D <= 576, P <= min(D, 128).  d_evals[P] descending; d_evecs[P x D] rows
+ * with the svd_flip sign; d_trace[1] (may be NULL) = sum of ALL eigenvalues (= trace), the
+ * denominator of explained_variance_ratio_ (_pca.py:645-646). */
+int64_t am_eigh_topk_work_bytes(int D, int P);
+int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, double *d_evecs,
+                 double *d_trace, void *d_work, void *stream);
 int am_project(const double *d_X, int64_t n_rows, int D, const double *d_mu,
                const double *d_comps, int P, double *d_scores, void *stream);
 
