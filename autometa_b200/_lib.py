@@ -58,6 +58,10 @@ _SIGS = {
     "am_normalize": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _i32, _p, _p, _p, _p]),
     "am_colsum_work_bytes": (_i64, [_i32]),
     "am_colsum": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
+    "am_colstats_work_bytes": (_i64, [_i32]),
+    "am_colstats": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
+    "am_gram_i8_work_bytes": (_i64, [_i64, _i32, _i32]),
+    "am_gram_i8": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _p]),
     "am_gram_work_bytes": (_i64, [_i32]),
     "am_gram": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
     "am_eigh_work_bytes": (_i64, [_i32]),

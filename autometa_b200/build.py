@@ -19,6 +19,7 @@ SOURCES = [
     "am_count.cu",
     "am_normalize.cu",
     "am_pca.cu",
+    "am_gram_i8.cu",
     "am_eigh.cu",
     "am_eigtop.cu",
     "am_dbscan.cu",

@@ -55,6 +55,7 @@ struct TriOut {
   double *tau;   // [n]
   double *d;     // [n]
   double *e;     // [n]  (e[i] couples i and i+1)
+  long long *dbg;  // optional [8] phase cycle counters (CTA 0, thread 0); may be NULL
 };
 
 // ------------------------------------------------------------------ 1. tridiagonalisation
@@ -103,6 +104,8 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
   }
   double sigma = block_sum<TW>(sig_part, red);
 
+  long long tA = 0, tB = 0, tS = 0, tC = 0, t0 = clock64(), t1;
+#define AM_TICK(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
   for (int k = 0; k <= n - 3; ++k) {
     double *vcur = vb + (k & 1) * np, *wcur = wb + (k & 1) * np;
     const double *vprev = vb + ((k + 1) & 1) * np, *wprev = wb + ((k + 1) & 1) * np;
@@ -124,6 +127,7 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
     if (c == (k % TC))
       for (int i = tid; i < np; i += TT) out.V[(size_t)k * np + i] = vcur[i];
 
+    AM_TICK(tA);
     // ---- B. fused pass over own rows >= k: apply pending update (k-1), p = tau * A v_k
     {
       int lrs[MAXRPW];
@@ -167,7 +171,9 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
         }
       }
     }
+    AM_TICK(tB);
     cluster.sync();
+    AM_TICK(tS);
 
     // ---- C. w_k, next column x_{k+1} (replicated)
     const double *P = gP + (k & 1) * np, *AC = gA + (k & 1) * np;
@@ -187,7 +193,9 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
       if (i >= k + 3) sig_part += xv * xv;
     }
     sigma = block_sum<TW>(sig_part, red);
+    AM_TICK(tC);
   }
+  if (out.dbg && c == 0 && tid == 0) { out.dbg[0] = tA; out.dbg[1] = tB; out.dbg[2] = tS; out.dbg[3] = tC; }
 
   // epilogue: pending update (n-3) on rows/cols >= n-2, then d and the last e
   {
@@ -490,7 +498,7 @@ backtransform_kernel(const double *__restrict__ V, const double *__restrict__ ta
 inline int round_up32(int x) { return (x + 31) & ~31; }
 
 struct TopWork {
-  double *V, *tau, *d, *e, *lam, *Y;
+  double *V, *tau, *d, *e, *lam, *Y, *dbg;
 };
 
 int64_t carve_top(void *base, int n, int P, TopWork *w) {
@@ -509,6 +517,7 @@ int64_t carve_top(void *base, int n, int P, TopWork *w) {
   t.e = take((int64_t)np * 8);
   t.lam = take((int64_t)PMAX * 8);
   t.Y = take((int64_t)P * np * 8);
+  t.dbg = take(64);
   if (w) *w = t;
   return off;
 }
@@ -531,7 +540,7 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
   if (RL > MAXRPW * TW) return am::fail(AM_EINVAL, "am_eigh_topk: D too large for the cluster path");
   TopWork w;
   carve_top(d_work, n, P, &w);
-  TriOut out{w.V, w.tau, w.d, w.e};
+  TriOut out{w.V, w.tau, w.d, w.e, (long long *)w.dbg};
 
   // 1. tridiagonalisation (one cluster of 16 CTAs)
   {

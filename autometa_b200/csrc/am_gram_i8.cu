@@ -1,0 +1,431 @@
+// Kernel 3 (tensor-core path) — centred Gram G = (X - mu)^T (X - mu) on the 5th-gen tensor
+// cores (tcgen05.mma kind::i8, accumulators in TMEM, operands staged by TMA) — sm_100a.
+//
+// Replaces the BLAS product X.T @ X of sklearn PCA._fit_full(covariance_eigh)
+// (sklearn/decomposition/_pca.py:604-610), reached from autometa/common/kmers.py:605.
+//
+// fp64 accuracy from integer tensor cores (error-free "sliced" product):
+//   1. quantize_planes_kernel: every centred value is turned into a fixed-point integer
+//        q = round((x - mu_j) * 2^(8S-2-e_j)),   2^e_j > max_i |x_ij - mu_j|,
+//      written as S balanced base-256 digits a_0..a_{S-1} in [-128,127] ("planes" of int8,
+//      row-major like X, so K = contig rows and the operands are MN-major for the MMA).
+//   2. gram_i8_kernel: sum_r q_ri q_rj = sum_{s,t} 256^(2(S-1)-s-t) sum_r a_s[r,i] a_t[r,j];
+//      the digit products are exact in int32 and each weight d = s+t gets its own TMEM
+//      accumulator P_d (S accumulators of 128 x 64 int32).  Pairs with s+t >= S (relative weight
+//      <= 2^-8S) are dropped.  One persistent CTA per SM: warp 0 = TMA producer (planes -> smem,
+//      128B/64B swizzle), warp 1 = single-thread tcgen05.mma issuer, warps 2-5 = epilogue
+//      (tcgen05.ld -> fp64 combine sum_d 2^-8d P_d -> partial tile in the workspace).
+//   3. gram_i8_reduce_kernel: partial tiles are summed over row chunks in a FIXED order
+//      (deterministic), scaled by 2^(e_i+e_j-12) and mirrored into the symmetric G.
+// With S = 6 the quantisation step is 2^-46 of the column range; the integer arithmetic adds no
+// rounding at all, so G is at least as accurate as an fp64 BLAS Gram.
+#include <cuda.h>
+
+#include "am_common.cuh"
+
+namespace {
+
+constexpr int GI_M = 128;       // G rows per tile  (TMEM lanes)
+constexpr int GI_N = 64;        // G cols per tile  (TMEM columns per accumulator)
+constexpr int GI_K = 32;        // contig rows per stage = K of one kind::i8 MMA
+constexpr int GI_MAXS = 7;      // S * GI_N <= 512 TMEM columns
+constexpr int GI_THREADS = 192;
+constexpr int GI_A_BYTES = GI_M * GI_K;  // 4096 per plane per stage
+constexpr int GI_B_BYTES = GI_N * GI_K;  // 2048 per plane per stage
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, MN-major operand, one swizzle atom wide (SM100 format:
+// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64))
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+struct GramI8Params {
+  int S;              // digit planes
+  int n_rows;         // contig rows
+  int rows_per_chunk; // multiple of GI_K
+  int n_chunks;
+  int TI;             // ceil(D / 128)
+  int TJ;             // ceil(D / 64)
+  int n_tiles;        // upper-triangular tiles: sum_I (TJ - 2I)
+  int stages;
+};
+
+__device__ __forceinline__ void decode_tile(int tile, int TJ, int &I, int &Jb) {
+  I = 0;
+  int rem = tile;
+  while (rem >= TJ - 2 * I) { rem -= TJ - 2 * I; ++I; }
+  Jb = 2 * I + rem;
+}
+
+// ------------------------------------------------------------------ 2. the tensor-core Gram
+__global__ void __launch_bounds__(GI_THREADS, 1)
+gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               GramI8Params p, double *__restrict__ part) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B-swizzled tiles
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int S = p.S, NS = p.stages;
+  const uint32_t stage_bytes = (uint32_t)S * (GI_A_BYTES + GI_B_BYTES);
+  const uint32_t bars = base + (uint32_t)NS * stage_bytes;  // full[NS], empty[NS], acc_full, acc_empty
+  const uint32_t bar_full = bars, bar_empty = bars + 8u * NS, bar_accf = bars + 16u * NS, bar_acce = bar_accf + 8u;
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.n_chunks * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, 1); }
+    mbar_init(bar_accf, 1);
+    mbar_init(bar_acce, 4);  // one arrive per epilogue warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int chunk = item / p.n_tiles, tile = item % p.n_tiles;
+        int I, Jb;
+        decode_tile(tile, p.TJ, I, Jb);
+        const int row0 = chunk * p.rows_per_chunk;
+        const int row1 = min(p.n_rows, row0 + p.rows_per_chunk);
+        for (int r = row0; r < row1; r += GI_K) {
+          mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+          const uint32_t fb = bar_full + 8u * stage;
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+          const uint32_t sb = sa + (uint32_t)S * GI_A_BYTES;
+          for (int s = 0; s < S; ++s) {
+            tma_load_3d(sa + (uint32_t)s * GI_A_BYTES, &tmA, I * GI_M, r, s, fb);
+            tma_load_3d(sb + (uint32_t)s * GI_B_BYTES, &tmB, Jb * GI_N, r, s, fb);
+          }
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D=S32, A=B=signed int8, both MN-major, N=64, M=128
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(GI_N >> 3) << 17) | ((uint32_t)(GI_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int chunk = item / p.n_tiles;
+        const int row0 = chunk * p.rows_per_chunk;
+        const int row1 = min(p.n_rows, row0 + p.rows_per_chunk);
+        mbar_wait(bar_acce, acc_phase ^ 1u);  // epilogue has drained the accumulators
+        tc_fence_after();
+        bool first = true;
+        for (int r = row0; r < row1; r += GI_K) {
+          mbar_wait(bar_full + 8u * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+          const uint32_t sb = sa + (uint32_t)S * GI_A_BYTES;
+          for (int d = 0; d < S; ++d) {
+            for (int s = 0; s <= d; ++s) {
+              const int t = d - s;
+              // A: 128 cols x 32 rows, 128B swizzle (atom = 128 B x 8 rows -> SBO 1024)
+              const uint64_t da = make_desc(sa + (uint32_t)s * GI_A_BYTES, GI_K * 128, 1024, 2);
+              // B: 64 cols x 32 rows, 64B swizzle (atom = 64 B x 8 rows -> SBO 512)
+              const uint64_t db = make_desc(sb + (uint32_t)t * GI_B_BYTES, GI_K * 64, 512, 4);
+              umma_i8(tmem + (uint32_t)d * GI_N, da, db, idesc, (first && s == 0) ? 0u : 1u);
+            }
+          }
+          first = false;
+          umma_commit(bar_empty + 8u * stage);  // frees the smem stage when the MMAs have read it
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(bar_accf);  // accumulators complete
+        acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> fp64 partial tile =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      mbar_wait(bar_accf, acc_phase);
+      tc_fence_after();
+      double *out = part + ((size_t)item * GI_M + (size_t)(q * 32 + lane)) * GI_N;
+      for (int c = 0; c < GI_N / 16; ++c) {
+        double g[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) g[j] = 0.0;
+        double wd = 1.0;
+        for (int d = 0; d < S; ++d) {
+          uint32_t v[16];
+          const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * GI_N + c * 16);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              : "r"(ta));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g[j] = fma((double)(int32_t)v[j], wd, g[j]);
+          wd *= 1.0 / 256.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2 *>(out + c * 16 + j) = make_double2(g[j], g[j + 1]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce);
+      acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ 1. quantisation into digit planes
+__global__ void prep_scales_kernel(const double *__restrict__ mu, const double *__restrict__ colmaxabs, int D,
+                                   int S, int *__restrict__ e, double *__restrict__ sc) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  const double bound = colmaxabs[j] + fabs(mu[j]);
+  int ej = 0;
+  if (bound > 0.0 && isfinite(bound)) ej = ilogb(bound) + 1;  // 2^ej > bound >= max|x - mu|
+  e[j] = ej;
+  sc[j] = ldexp(1.0, 8 * S - 2 - ej);
+}
+
+__global__ void __launch_bounds__(256)
+quantize_planes_kernel(const double *__restrict__ X, int64_t n, int D, int Dp, const double *__restrict__ mu,
+                       const double *__restrict__ sc, int S, int8_t *__restrict__ planes) {
+  // one thread = 8 consecutive columns of one row
+  const int groups = Dp / 8;
+  const int64_t total = n * groups;
+  const double lim = ldexp(1.0, 8 * S - 2);
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = w / groups;
+    const int c0 = (int)(w % groups) * 8;
+    long long q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      double v = 0.0;
+      if (c < D) v = (__ldcs(X + r * D + c) - __ldg(mu + c)) * __ldg(sc + c);
+      v = fmin(fmax(v, -lim), lim);
+      q[j] = __double2ll_rn(v);
+    }
+    for (int s = S - 1; s >= 0; --s) {
+      unsigned long long packed = 0ull;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int a = (int)((q[j] + 128) & 255) - 128;  // balanced digit in [-128, 127]
+        q[j] = (q[j] - a) >> 8;
+        packed |= (unsigned long long)(unsigned)(a & 255) << (8 * j);
+      }
+      *reinterpret_cast<unsigned long long *>(planes + ((size_t)s * n + r) * Dp + c0) = packed;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ 3. fixed-order reduction + scaling + mirror
+__global__ void __launch_bounds__(256)
+gram_i8_reduce_kernel(const double *__restrict__ part, GramI8Params p, int D, const int *__restrict__ e,
+                      double *__restrict__ G) {
+  const int tile = blockIdx.x;
+  int I, Jb;
+  decode_tile(tile, p.TJ, I, Jb);
+  for (int el = threadIdx.x; el < GI_M * GI_N; el += blockDim.x) {
+    const int i = I * GI_M + el / GI_N, j = Jb * GI_N + el % GI_N;
+    if (i >= D || j >= D || j < i) continue;
+    double s = 0.0;
+    for (int ch = 0; ch < p.n_chunks; ++ch) s += part[((size_t)ch * p.n_tiles + tile) * (GI_M * GI_N) + el];
+    const double g = ldexp(s, e[i] + e[j] - 12);
+    G[(size_t)i * D + j] += g;
+    if (j != i) G[(size_t)j * D + i] += g;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+struct I8Work {
+  int8_t *planes;
+  double *part;
+  int *e;
+  double *sc;
+};
+
+inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+void gram_i8_shape(int64_t n_rows, int D, int S, GramI8Params *p) {
+  p->S = S;
+  p->n_rows = (int)n_rows;
+  p->TI = (D + GI_M - 1) / GI_M;
+  p->TJ = (D + GI_N - 1) / GI_N;
+  int nt = 0;
+  for (int I = 0; I < p->TI; ++I) nt += std::max(0, p->TJ - 2 * I);
+  p->n_tiles = nt;
+  const int sms = am::num_sms();
+  // row chunks: enough work items for ~5 waves of persistent CTAs, chunk <= 16384 rows (int32
+  // headroom: S pairs x rows x 2^14 < 2^31), >= 512 rows
+  int64_t want_items = (int64_t)sms * 5;
+  int64_t chunks = std::max<int64_t>(1, want_items / nt);
+  int64_t rpc = (n_rows + chunks - 1) / chunks;
+  rpc = std::max<int64_t>(rpc, 512);
+  rpc = std::min<int64_t>(rpc, 16384);
+  rpc = (rpc + GI_K - 1) / GI_K * GI_K;
+  p->rows_per_chunk = (int)rpc;
+  p->n_chunks = (int)((n_rows + rpc - 1) / rpc);
+  const int stage_bytes = S * (GI_A_BYTES + GI_B_BYTES);
+  p->stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+}
+
+int64_t carve_i8(void *base, int64_t n_rows, int D, int S, I8Work *w) {
+  GramI8Params p;
+  gram_i8_shape(n_rows, D, S, &p);
+  const int Dp = (D + 15) & ~15;
+  int64_t off = 0;
+  char *b = (char *)base;
+  auto take = [&](int64_t bytes) {
+    char *q = b ? b + off : nullptr;
+    off += align256(bytes);
+    return q;
+  };
+  I8Work t;
+  t.planes = (int8_t *)take((int64_t)S * n_rows * Dp + 1024);
+  t.part = (double *)take((int64_t)p.n_chunks * p.n_tiles * GI_M * GI_N * 8);
+  t.e = (int *)take((int64_t)D * 4);
+  t.sc = (double *)take((int64_t)D * 8);
+  if (w) *w = t;
+  return off;
+}
+
+}  // namespace
+
+extern "C" int64_t am_gram_i8_work_bytes(int64_t n_rows, int D, int S) {
+  if (n_rows < 1 || D < 1 || S < 2 || S > GI_MAXS) return 0;
+  return carve_i8(nullptr, n_rows, D, S, nullptr);
+}
+
+extern "C" int am_gram_i8(const double *d_X, int64_t n_rows, int D, const double *d_mu,
+                          const double *d_colmaxabs, int S, double *d_G, void *d_work, void *stream) {
+  if (D < 1 || n_rows < 0 || n_rows > 0x7fffffff) return am::fail(AM_EINVAL, "am_gram_i8: bad shape");
+  if (S < 2 || S > GI_MAXS) return am::fail(AM_EINVAL, "am_gram_i8: S (digit planes) must be in 2..7");
+  if (n_rows == 0) return AM_OK;
+  if (!d_X || !d_mu || !d_colmaxabs || !d_G || !d_work) return am::fail(AM_EINVAL, "am_gram_i8: null pointer");
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return am::fail(AM_ECUDA, "am_gram_i8: cuTensorMapEncodeTiled entry point unavailable");
+  cudaStream_t st = (cudaStream_t)stream;
+  GramI8Params p;
+  gram_i8_shape(n_rows, D, S, &p);
+  I8Work w;
+  carve_i8(d_work, n_rows, D, S, &w);
+  const int Dp = (D + 15) & ~15;
+
+  prep_scales_kernel<<<(D + 127) / 128, 128, 0, st>>>(d_mu, d_colmaxabs, D, S, w.e, w.sc);
+  AM_LAUNCHED("prep_scales_kernel");
+  {
+    const int64_t total = n_rows * (Dp / 8);
+    const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)am::num_sms() * 16);
+    quantize_planes_kernel<<<grid, 256, 0, st>>>(d_X, n_rows, D, Dp, d_mu, w.sc, S, w.planes);
+    AM_LAUNCHED("quantize_planes_kernel");
+  }
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)n_rows, (cuuint64_t)S};
+    cuuint64_t gstr[2] = {(cuuint64_t)Dp, (cuuint64_t)Dp * (cuuint64_t)n_rows};
+    cuuint32_t estr[3] = {1, 1, 1};
+    cuuint32_t boxA[3] = {GI_M, GI_K, 1};
+    cuuint32_t boxB[3] = {GI_N, GI_K, 1};
+    CUresult r1 = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, w.planes, gdim, gstr, boxA, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, w.planes, gdim, gstr, boxB, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return am::fail(AM_ECUDA, "am_gram_i8: cuTensorMapEncodeTiled failed");
+  }
+  {
+    const size_t smem = (size_t)p.stages * S * (GI_A_BYTES + GI_B_BYTES) + 16 * (size_t)p.stages + 64 + 1024;
+    AM_CUDA(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_items = p.n_chunks * p.n_tiles;
+    const int grid = std::min(n_items, am::num_sms());
+    gram_i8_kernel<<<grid, GI_THREADS, smem, st>>>(tmA, tmB, p, w.part);
+    AM_LAUNCHED("gram_i8_kernel");
+  }
+  gram_i8_reduce_kernel<<<p.n_tiles, 256, 0, st>>>(w.part, p, D, w.e, d_G);
+  AM_LAUNCHED("gram_i8_reduce_kernel");
+  return AM_OK;
+}

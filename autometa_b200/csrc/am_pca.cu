@@ -42,6 +42,43 @@ __global__ void colsum_reduce_kernel(const double *__restrict__ partials, int n_
   colsum[j] += s;
 }
 
+// column sums AND column max-abs in one pass (the max-abs sizes the fixed-point scale of the
+// tensor-core Gram, am_gram_i8.cu)
+__global__ void colstats_partial_kernel(const double *__restrict__ X, int64_t n, int D,
+                                        double *__restrict__ psum, double *__restrict__ pmax) {
+  __shared__ double red[CS_ROWS][128];
+  __shared__ double redm[CS_ROWS][128];
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  double s = 0.0, m = 0.0;
+  if (c < D)
+    for (int64_t r = (int64_t)blockIdx.y * CS_ROWS + threadIdx.y; r < n; r += (int64_t)gridDim.y * CS_ROWS) {
+      const double v = __ldg(X + r * D + c);
+      s += v;
+      m = fmax(m, fabs(v));
+    }
+  red[threadIdx.y][threadIdx.x] = s;
+  redm[threadIdx.y][threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < D) {
+    double t = 0.0, tm = 0.0;
+#pragma unroll
+    for (int i = 0; i < CS_ROWS; ++i) { t += red[i][threadIdx.x]; tm = fmax(tm, redm[i][threadIdx.x]); }
+    psum[(int64_t)blockIdx.y * D + c] = t;
+    pmax[(int64_t)blockIdx.y * D + c] = tm;
+  }
+}
+
+__global__ void colstats_reduce_kernel(const double *__restrict__ psum, const double *__restrict__ pmax,
+                                       int n_parts, int D, double *__restrict__ colsum,
+                                       double *__restrict__ colmax) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  double s = 0.0, m = 0.0;
+  for (int p = 0; p < n_parts; ++p) { s += psum[(int64_t)p * D + j]; m = fmax(m, pmax[(int64_t)p * D + j]); }
+  colsum[j] += s;
+  colmax[j] = fmax(colmax[j], m);
+}
+
 int colsum_splits(int64_t n) {
   int64_t s = (int64_t)am::num_sms() * 2;
   const int64_t need = (n + CS_ROWS - 1) / CS_ROWS;
@@ -259,6 +296,25 @@ extern "C" int am_colsum(const double *d_X, int64_t n_rows, int D, double *d_col
   AM_LAUNCHED("colsum_partial_kernel");
   colsum_reduce_kernel<<<(D + 127) / 128, 128, 0, st>>>((const double *)d_work, S, D, d_colsum);
   AM_LAUNCHED("colsum_reduce_kernel");
+  return AM_OK;
+}
+
+extern "C" int64_t am_colstats_work_bytes(int D) { return 2 * am_colsum_work_bytes(D); }
+
+extern "C" int am_colstats(const double *d_X, int64_t n_rows, int D, double *d_colsum,
+                           double *d_colmaxabs, void *d_work, void *stream) {
+  if (D < 1 || n_rows < 0) return am::fail(AM_EINVAL, "am_colstats: bad shape");
+  if (n_rows == 0) return AM_OK;
+  if (!d_X || !d_colsum || !d_colmaxabs || !d_work) return am::fail(AM_EINVAL, "am_colstats: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = colsum_splits(n_rows);
+  double *psum = (double *)d_work;
+  double *pmax = psum + (int64_t)am::num_sms() * 2 * D;
+  dim3 grid((D + 127) / 128, S), block(128, CS_ROWS);
+  colstats_partial_kernel<<<grid, block, 0, st>>>(d_X, n_rows, D, psum, pmax);
+  AM_LAUNCHED("colstats_partial_kernel");
+  colstats_reduce_kernel<<<(D + 127) / 128, 128, 0, st>>>(psum, pmax, S, D, d_colsum, d_colmaxabs);
+  AM_LAUNCHED("colstats_reduce_kernel");
   return AM_OK;
 }
 

@@ -157,6 +157,42 @@ def gram_centered(X, mu, out=None):
     return out
 
 
+def colstats(X, colsum_out=None, colmax_out=None):
+    """Column sums and column max|x| of ``X`` in one pass (both accumulate into the outputs)."""
+    import torch
+
+    dev = X.device
+    n, D = X.shape
+    with torch.cuda.device(dev):
+        if colsum_out is None:
+            colsum_out = torch.zeros(D, dtype=torch.float64, device=dev)
+        if colmax_out is None:
+            colmax_out = torch.zeros(D, dtype=torch.float64, device=dev)
+        work = _work(dev, L.lib.am_colstats_work_bytes(D), "colstats")
+        L.check(L.lib.am_colstats(L.t_ptr(X), n, D, L.t_ptr(colsum_out), L.t_ptr(colmax_out), L.t_ptr(work),
+                                  L.stream_ptr(dev)))
+    return colsum_out, colmax_out
+
+
+GRAM_SLICES = 6
+
+
+def gram_centered_i8(X, mu, colmaxabs, out=None, slices: int = GRAM_SLICES):
+    """G += (X - mu)^T (X - mu) on the tensor cores (tcgen05 kind::i8 over ``slices`` exact
+    base-256 digit planes; see csrc/am_gram_i8.cu).  ``colmaxabs[j] >= max_i |X[i, j]|``."""
+    import torch
+
+    dev = X.device
+    n, D = X.shape
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.zeros((D, D), dtype=torch.float64, device=dev)
+        work = _work(dev, L.lib.am_gram_i8_work_bytes(n, D, slices), "gram_i8")
+        L.check(L.lib.am_gram_i8(L.t_ptr(X), n, D, L.t_ptr(mu), L.t_ptr(colmaxabs), slices, L.t_ptr(out),
+                                 L.t_ptr(work), L.stream_ptr(dev)))
+    return out
+
+
 def eigh_desc(A, max_sweeps: int = 30, tol: float = 0.0):
     """All eigenpairs of symmetric A, descending; rows of the returned matrix are
     eigenvectors with sklearn's svd_flip(u_based_decision=False) sign."""

@@ -183,9 +183,23 @@ int am_normalize(const int32_t *d_counts, int64_t n_rows_out, int D,
 int64_t am_colsum_work_bytes(int D);
 int am_colsum(const double *d_X, int64_t n_rows, int D, double *d_colsum, void *d_work,
               void *stream);
+/* column sums and column max|x| in one pass: colsum[D] += , colmaxabs[D] = max(colmaxabs, .)
+ * (caller zeroes both); the max-abs sizes the fixed-point scale of am_gram_i8 */
+int64_t am_colstats_work_bytes(int D);
+int am_colstats(const double *d_X, int64_t n_rows, int D, double *d_colsum, double *d_colmaxabs,
+                void *d_work, void *stream);
 int64_t am_gram_work_bytes(int D);
 int am_gram(const double *d_X, int64_t n_rows, int D, const double *d_mu,
             double *d_G, void *d_work, void *stream);
+/* Tensor-core Gram (tcgen05.mma kind::i8, TMEM accumulators, TMA-staged operands): the same
+ * G[D x D] += (X - mu)^T (X - mu) as am_gram, computed exactly on S balanced base-256 digit
+ * planes of the fixed-point values round((x - mu_j) 2^(8S-2-e_j)), 2^e_j > colmaxabs_j + |mu_j|.
+ * S in 2..7 (6: quantisation step 2^-46 of the column range).  d_colmaxabs[D] >= max_i |X[i,j]|
+ * (from am_colstats or the normalise kernel).  d_work: am_gram_i8_work_bytes(n_rows, D, S)
+ * bytes (digit planes S*n_rows*D int8 + partial tiles). */
+int64_t am_gram_i8_work_bytes(int64_t n_rows, int D, int S);
+int am_gram_i8(const double *d_X, int64_t n_rows, int D, const double *d_mu,
+               const double *d_colmaxabs, int S, double *d_G, void *d_work, void *stream);
 int64_t am_eigh_work_bytes(int D);
 int am_eigh(const double *d_A, int D, double *d_evals, double *d_evecs,
             void *d_work, int max_sweeps, double tol, void *stream);
