@@ -55,7 +55,7 @@ _SIGS = {
     "am_count_plan": (C.c_int, [_p, _i64, _i32, _i32, _p, _i64, _p, _p, _i64, _p]),
     "am_count_kmers": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p]),
     "am_normalize_work_bytes": (_i64, [_i32]),
-    "am_normalize": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _i32, _p, _p, _p, _p]),
+    "am_normalize": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _i32, _p, _p, _p, _p, _p]),
     "am_colsum_work_bytes": (_i64, [_i32]),
     "am_colsum": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "am_colstats_work_bytes": (_i64, [_i32]),

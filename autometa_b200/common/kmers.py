@@ -235,7 +235,7 @@ def pca_device(Xd, n_components: int, group=None) -> Dict[str, Any]:
     import torch
 
     n_local, D = Xd.shape
-    cs = _dev.colsum(Xd)
+    cs, cm = _dev.colstats(Xd)
     n_t = torch.tensor([float(n_local)], dtype=torch.float64, device=Xd.device)
     if group is not None:
         import torch.distributed as dist
@@ -244,7 +244,7 @@ def pca_device(Xd, n_components: int, group=None) -> Dict[str, Any]:
         dist.all_reduce(n_t, group=group if group is not True else None)
     n = n_t  # stays on device: no host sync in the fit
     mu = cs / n
-    G = _dev.gram_centered(Xd, mu)
+    G = _dev.gram_centered_i8(Xd, mu, cm)  # tcgen05 int8 digit-plane product, exact integer accumulation
     if group is not None:
         import torch.distributed as dist
 

@@ -95,6 +95,9 @@ struct GramI8Params {
   int TJ;             // ceil(D / 64)
   int n_tiles;        // upper-triangular tiles: sum_I (TJ - 2I)
   int stages;
+  int n_acc;          // TMEM accumulators (distinct weights d = s + t)
+  int n_pairs;        // digit-plane pairs multiplied per K step
+  uint8_t ps[32], pt[32], pd[32], pfirst[32];  // pair i: planes (s, t) -> accumulator d; first pair of its d
 };
 
 __device__ __forceinline__ void decode_tile(int tile, int TJ, int &I, int &Jb) {
@@ -180,15 +183,12 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)stage * stage_bytes;
           const uint32_t sb = sa + (uint32_t)S * GI_A_BYTES;
-          for (int d = 0; d < S; ++d) {
-            for (int s = 0; s <= d; ++s) {
-              const int t = d - s;
-              // A: 128 cols x 32 rows, 128B swizzle (atom = 128 B x 8 rows -> SBO 1024)
-              const uint64_t da = make_desc(sa + (uint32_t)s * GI_A_BYTES, GI_K * 128, 1024, 2);
-              // B: 64 cols x 32 rows, 64B swizzle (atom = 64 B x 8 rows -> SBO 512)
-              const uint64_t db = make_desc(sb + (uint32_t)t * GI_B_BYTES, GI_K * 64, 512, 4);
-              umma_i8(tmem + (uint32_t)d * GI_N, da, db, idesc, (first && s == 0) ? 0u : 1u);
-            }
+          for (int i = 0; i < p.n_pairs; ++i) {
+            // A: 128 cols x 32 rows, 128B swizzle (atom = 128 B x 8 rows -> SBO 1024)
+            const uint64_t da = make_desc(sa + (uint32_t)p.ps[i] * GI_A_BYTES, GI_K * 128, 1024, 2);
+            // B: 64 cols x 32 rows, 64B swizzle (atom = 64 B x 8 rows -> SBO 512)
+            const uint64_t db = make_desc(sb + (uint32_t)p.pt[i] * GI_B_BYTES, GI_K * 64, 512, 4);
+            umma_i8(tmem + (uint32_t)p.pd[i] * GI_N, da, db, idesc, (first && p.pfirst[i]) ? 0u : 1u);
           }
           first = false;
           umma_commit(bar_empty + 8u * stage);  // frees the smem stage when the MMAs have read it
@@ -211,7 +211,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 16; ++j) g[j] = 0.0;
         double wd = 1.0;
-        for (int d = 0; d < S; ++d) {
+        for (int d = 0; d < p.n_acc; ++d) {
           uint32_t v[16];
           const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * GI_N + c * 16);
           asm volatile(
@@ -350,6 +350,21 @@ void gram_i8_shape(int64_t n_rows, int D, int S, GramI8Params *p) {
   p->n_chunks = (int)((n_rows + rpc - 1) / rpc);
   const int stage_bytes = S * (GI_A_BYTES + GI_B_BYTES);
   p->stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+  // pairs kept: s + t <= S-1, plus the square term (S/2, S/2) of weight S when S is even — the only
+  // dropped term with a systematic (non zero-mean) contribution, on the diagonal of G
+  int np = 0;
+  const int dmax = (S % 2 == 0 && S * 64 + 64 <= 512) ? S : S - 1;
+  for (int d = 0; d <= dmax; ++d)
+    for (int s = 0; s <= d; ++s) {
+      const int t = d - s;
+      if (s >= S || t >= S) continue;
+      if (d == S && s != t) continue;
+      p->ps[np] = (uint8_t)s; p->pt[np] = (uint8_t)t; p->pd[np] = (uint8_t)d;
+      p->pfirst[np] = (np == 0 || p->pd[np - 1] != d) ? 1 : 0;
+      ++np;
+    }
+  p->n_pairs = np;
+  p->n_acc = dmax + 1;
 }
 
 int64_t carve_i8(void *base, int64_t n_rows, int D, int S, I8Work *w) {

@@ -34,16 +34,19 @@ template <int METHOD>
 __global__ void __launch_bounds__(NWARPS * 32)
 normalize_kernel(const int32_t *__restrict__ counts, int64_t n_out, int D,
                  const int64_t *__restrict__ row_index, const int32_t *__restrict__ col_index,
-                 int Dk, double *__restrict__ out, double *__restrict__ partials) {
+                 int Dk, double *__restrict__ out, double *__restrict__ partials,
+                 double *__restrict__ pmax) {
   extern __shared__ double sm[];
   double *logt = sm;               // LOGT
   double *csum = sm + LOGT;        // NWARPS * Dk (only when partials != nullptr)
+  double *cmx = csum + NWARPS * Dk;  // NWARPS * Dk
   for (int i = threadIdx.x; i < LOGT; i += blockDim.x) logt[i] = log((double)(i + 1));
   if (partials)
-    for (int i = threadIdx.x; i < NWARPS * Dk; i += blockDim.x) csum[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * NWARPS * Dk; i += blockDim.x) csum[i] = 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *mysum = csum + warp * Dk;
+  double *mymax = cmx + warp * Dk;
   const int64_t wstride = (int64_t)gridDim.x * NWARPS;
   for (int64_t r = (int64_t)blockIdx.x * NWARPS + warp; r < n_out; r += wstride) {
     const int64_t src = row_index ? row_index[r] : r;
@@ -60,7 +63,7 @@ normalize_kernel(const int32_t *__restrict__ counts, int64_t n_out, int D,
         const int c = col_index ? col_index[j] : j;
         const double v = log_int(logt, __ldg(x + c) + 1) - mean;
         __stcs(o + j, v);
-        if (partials) mysum[j] += v;
+        if (partials) { mysum[j] += v; mymax[j] = fmax(mymax[j], fabs(v)); }
       }
     } else {
       // closure + multiplicative replacement (delta = 1/D^2 over the retained columns)
@@ -99,7 +102,7 @@ normalize_kernel(const int32_t *__restrict__ counts, int64_t n_out, int D,
         const int v = __ldg(x + c);
         const double l = (v == 0 ? lzero : (log_int(logt, v) + lscale)) - mean;
         __stcs(o + j, l);
-        if (partials) mysum[j] += l;
+        if (partials) { mysum[j] += l; mymax[j] = fmax(mymax[j], fabs(l)); }
       }
     }
   }
@@ -110,6 +113,109 @@ normalize_kernel(const int32_t *__restrict__ counts, int64_t n_out, int D,
 #pragma unroll
       for (int w = 0; w < NWARPS; ++w) s += csum[w * Dk + j];
       partials[(int64_t)blockIdx.x * Dk + j] = s;
+      double m = 0.0;
+#pragma unroll
+      for (int w = 0; w < NWARPS; ++w) m = fmax(m, cmx[w * Dk + j]);
+      pmax[(int64_t)blockIdx.x * Dk + j] = m;
+    }
+  }
+}
+
+
+// Fast path for the k = 5 table (D = D_keep = 512, no column gather): the row lives in registers
+// (lane owns columns 64 m + 2 lane + {0,1}, m = 0..7: 8-byte loads, 16-byte stores, every warp
+// instruction covers one contiguous 256 B / 512 B run), column sums and column max|v| are kept in
+// registers across all rows of the warp and reduced once per CTA in a fixed order.
+template <int METHOD>
+__global__ void __launch_bounds__(NWARPS * 32)
+normalize512_kernel(const int32_t *__restrict__ counts, int64_t n_out, const int64_t *__restrict__ row_index,
+                    double *__restrict__ out, double *__restrict__ psum, double *__restrict__ pmax) {
+  constexpr int D = 512;
+  extern __shared__ double sm[];
+  double *logt = sm;          // LOGT
+  double *red = sm + LOGT;    // NWARPS * D (only when psum != nullptr)
+  for (int i = threadIdx.x; i < LOGT; i += blockDim.x) logt[i] = log((double)(i + 1));
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double csum[16], cmax[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { csum[i] = 0.0; cmax[i] = 0.0; }
+  const int64_t wstride = (int64_t)gridDim.x * NWARPS;
+  for (int64_t r = (int64_t)blockIdx.x * NWARPS + warp; r < n_out; r += wstride) {
+    const int64_t src = row_index ? row_index[r] : r;
+    const int2 *x2 = reinterpret_cast<const int2 *>(counts + src * D) + lane;
+    int xv[16];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int2 t = __ldcs(x2 + 32 * m);
+      xv[2 * m] = t.x;
+      xv[2 * m + 1] = t.y;
+    }
+    double l[16];
+    if (METHOD == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { l[i] = log_int(logt, xv[i] + 1); s += l[i]; }
+      const double mean = warp_sum(s) / (double)D;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) l[i] -= mean;
+    } else {
+      double S = 0.0;
+      int z = 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { S += (double)xv[i]; z += (xv[i] == 0); }
+      S = warp_sum(S);
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) z += __shfl_xor_sync(FULL, z, o2);
+      const double delta = (1.0 / (double)D) * (1.0 / (double)D);
+      const double scale = 1.0 - (double)z * delta;
+      double Q = 0.0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) Q += xv[i] == 0 ? delta : scale * ((double)xv[i] / S);
+      Q = warp_sum(Q);
+      const double lzero = log(delta / Q);
+      const double lscale = log(scale / S / Q);
+      double sl = 0.0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { l[i] = xv[i] == 0 ? lzero : (log_int(logt, xv[i]) + lscale); sl += l[i]; }
+      const double mean = warp_sum(sl) / (double)D;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) l[i] -= mean;
+    }
+    double2 *o2p = reinterpret_cast<double2 *>(out + r * D) + lane;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) __stcs(o2p + 32 * m, make_double2(l[2 * m], l[2 * m + 1]));
+    if (psum) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { csum[i] += l[i]; cmax[i] = fmax(cmax[i], fabs(l[i])); }
+    }
+  }
+  if (psum) {
+    // cross-warp reduction in a fixed order: sums, then maxima, through the same buffer
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      red[warp * D + 64 * m + 2 * lane] = csum[2 * m];
+      red[warp * D + 64 * m + 2 * lane + 1] = csum[2 * m + 1];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < NWARPS; ++w) t += red[w * D + j];
+      psum[(int64_t)blockIdx.x * D + j] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      red[warp * D + 64 * m + 2 * lane] = cmax[2 * m];
+      red[warp * D + 64 * m + 2 * lane + 1] = cmax[2 * m + 1];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < NWARPS; ++w) t = fmax(t, red[w * D + j]);
+      pmax[(int64_t)blockIdx.x * D + j] = t;
     }
   }
 }
@@ -189,13 +295,15 @@ ilr_kernel(const int32_t *__restrict__ counts, int64_t n_out, int D,
   }
 }
 
-__global__ void reduce_partials_kernel(const double *__restrict__ partials, int n_parts, int D,
-                                       double *__restrict__ colsum) {
+__global__ void reduce_partials_kernel(const double *__restrict__ partials, const double *__restrict__ pmax,
+                                       int n_parts, int D, double *__restrict__ colsum,
+                                       double *__restrict__ colmax) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= D) return;
-  double s = 0.0;
-  for (int p = 0; p < n_parts; ++p) s += partials[(int64_t)p * D + j];
+  double s = 0.0, m = 0.0;
+  for (int p = 0; p < n_parts; ++p) { s += partials[(int64_t)p * D + j]; m = fmax(m, pmax[(int64_t)p * D + j]); }
   colsum[j] += s;
+  if (colmax) colmax[j] = fmax(colmax[j], m);
 }
 
 int norm_grid(int64_t n_rows) {
@@ -208,18 +316,19 @@ int norm_grid(int64_t n_rows) {
 }  // namespace
 
 extern "C" int64_t am_normalize_work_bytes(int D) {
-  return (int64_t)am::num_sms() * 4 * D * (int64_t)sizeof(double);
+  return 2 * (int64_t)am::num_sms() * 4 * D * (int64_t)sizeof(double);
 }
 
 extern "C" int am_normalize(const int32_t *d_counts, int64_t n_rows_out, int D,
                             const int64_t *d_row_index, const int32_t *d_col_index, int D_keep,
-                            int method, double *d_out, double *d_colsum, void *d_work,
-                            void *stream) {
+                            int method, double *d_out, double *d_colsum, double *d_colmaxabs,
+                            void *d_work, void *stream) {
   if (D < 1 || D > MAXD || D_keep < 1 || D_keep > D) return am::fail(AM_EINVAL, "am_normalize: bad D");
   if (method < 0 || method > 2) return am::fail(AM_EINVAL, "am_normalize: bad method");
   if (n_rows_out == 0) return AM_OK;
   if (!d_counts || !d_out || n_rows_out < 0) return am::fail(AM_EINVAL, "am_normalize: null pointer");
   if (d_colsum && !d_work) return am::fail(AM_EINVAL, "am_normalize: d_colsum needs d_work");
+  if (d_colmaxabs && !d_colsum) return am::fail(AM_EINVAL, "am_normalize: d_colmaxabs needs d_colsum");
   if (method == AM_NORM_ILR && (d_colsum || D_keep < 2))
     return am::fail(AM_EINVAL, "am_normalize: ilr does not produce column sums / needs D>=2");
   cudaStream_t st = (cudaStream_t)stream;
@@ -236,22 +345,39 @@ extern "C" int am_normalize(const int32_t *d_counts, int64_t n_rows_out, int D,
     return AM_OK;
   }
   double *partials = d_colsum ? (double *)d_work : nullptr;
-  const size_t smem = (size_t)(LOGT + (partials ? NWARPS * D_keep : 0)) * sizeof(double);
+  double *pmax = partials ? partials + (int64_t)am::num_sms() * 4 * D : nullptr;
+  if (D == 512 && D_keep == 512 && !d_col_index) {
+    const size_t smem5 = (size_t)(LOGT + (partials ? NWARPS * 512 : 0)) * sizeof(double);
+    if (method == AM_NORM_AM_CLR) {
+      AM_CUDA(cudaFuncSetAttribute(normalize512_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+      normalize512_kernel<0><<<grid, NWARPS * 32, smem5, st>>>(d_counts, n_rows_out, d_row_index, d_out, partials, pmax);
+    } else {
+      AM_CUDA(cudaFuncSetAttribute(normalize512_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+      normalize512_kernel<1><<<grid, NWARPS * 32, smem5, st>>>(d_counts, n_rows_out, d_row_index, d_out, partials, pmax);
+    }
+    AM_LAUNCHED("normalize512_kernel");
+    if (partials) {
+      reduce_partials_kernel<<<(D_keep + 127) / 128, 128, 0, st>>>(partials, pmax, grid, D_keep, d_colsum, d_colmaxabs);
+      AM_LAUNCHED("reduce_partials_kernel");
+    }
+    return AM_OK;
+  }
+  const size_t smem = (size_t)(LOGT + (partials ? 2 * NWARPS * D_keep : 0)) * sizeof(double);
   if (smem > 227 * 1024) return am::fail(AM_EINVAL, "am_normalize: row too wide for fused column sums");
   if (method == AM_NORM_AM_CLR) {
     if (smem > 48 * 1024)
       AM_CUDA(cudaFuncSetAttribute(normalize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     normalize_kernel<0><<<grid, NWARPS * 32, smem, st>>>(d_counts, n_rows_out, D, d_row_index,
-                                                         d_col_index, D_keep, d_out, partials);
+                                                         d_col_index, D_keep, d_out, partials, pmax);
   } else {
     if (smem > 48 * 1024)
       AM_CUDA(cudaFuncSetAttribute(normalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     normalize_kernel<1><<<grid, NWARPS * 32, smem, st>>>(d_counts, n_rows_out, D, d_row_index,
-                                                         d_col_index, D_keep, d_out, partials);
+                                                         d_col_index, D_keep, d_out, partials, pmax);
   }
   AM_LAUNCHED("normalize_kernel");
   if (partials) {
-    reduce_partials_kernel<<<(D_keep + 127) / 128, 128, 0, st>>>(partials, grid, D_keep, d_colsum);
+    reduce_partials_kernel<<<(D_keep + 127) / 128, 128, 0, st>>>(partials, pmax, grid, D_keep, d_colsum, d_colmaxabs);
     AM_LAUNCHED("reduce_partials_kernel");
   }
   return AM_OK;

@@ -102,7 +102,7 @@ def _work(dev, nbytes: int, tag: str):
 
 
 def normalize_counts(counts, method: str = "am_clr", row_index=None, col_index=None, out=None,
-                     colsum=None):
+                     colsum=None, colmaxabs=None):
     """Kernel 2. ``counts`` int32 [N x D] on device; optional gathers fuse am_clr's
     row/column drops.  Returns float64 [N_out x D_out]."""
     import torch
@@ -124,7 +124,7 @@ def normalize_counts(counts, method: str = "am_clr", row_index=None, col_index=N
         L.check(
             L.lib.am_normalize(
                 L.t_ptr(counts), n_out, D, L.t_ptr(row_index), L.t_ptr(col_index), Dk, m,
-                L.t_ptr(out), L.t_ptr(colsum), L.t_ptr(work), L.stream_ptr(dev),
+                L.t_ptr(out), L.t_ptr(colsum), L.t_ptr(colmaxabs), L.t_ptr(work), L.stream_ptr(dev),
             )
         )
     return out

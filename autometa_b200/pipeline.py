@@ -54,17 +54,18 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
         Dk = D if col_index is None else int(col_index.numel())
         Dout = Dk - 1 if method == "ilr" else Dk
         cs = torch.zeros(Dout, dtype=torch.float64, device=dev)
-        if method == "ilr":
+        cm = torch.zeros(Dout, dtype=torch.float64, device=dev)  # column max|x|: fixed-point scale of the Gram
+        if method == "ilr" or Dout > 1024:
             X = _dev.normalize_counts(counts, method, row_index, col_index)
-            _dev.colsum(X, out=cs)
+            _dev.colstats(X, cs, cm)
         else:
-            X = _dev.normalize_counts(counts, method, row_index, col_index, colsum=cs)
+            X = _dev.normalize_counts(counts, method, row_index, col_index, colsum=cs, colmaxabs=cm)
         mark("normalise")
         n_t = torch.tensor([float(X.shape[0])], dtype=torch.float64, device=dev)
         if distributed:
             _dist.allreduce_sum_([cs, n_t], group)
         mu = cs / n_t
-        G = _dev.gram_centered(X, mu)
+        G = _dev.gram_centered_i8(X, mu, cm)
         if distributed:
             _dist.allreduce_sum_([G], group)
         C = G / (n_t - 1.0)

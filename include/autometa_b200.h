@@ -158,14 +158,17 @@ int am_count_kmers(const uint32_t *d_codes, const uint32_t *d_exc_bitmap,
  *   d_colsum   [D_out] float64 or NULL: column sums of the output are ADDED here
  *              (caller zeroes) — the PCA mean comes for free.  Deterministic:
  *              per-CTA partials in d_work (am_normalize_work_bytes(D) bytes) are
- *              reduced in a fixed order.  Not available for ilr (use am_colsum).
+ *              reduced in a fixed order.  Not available for ilr (use am_colstats).
+ *   d_colmaxabs[D_out] float64 or NULL (needs d_colsum): column max|out| is max-ed in
+ *              (caller zeroes) — sizes the fixed-point scale of am_gram_i8.
  * am_clr: out = log1p(x) - mean_j log1p(x)   (== log(((x+1)/S)/gmean((x+1)/S)))
  * clr/ilr: p = x/S; zeros -> 1/D^2, others * (1 - z/D^2); log; centre; (ilr: Helmert basis)
  * ------------------------------------------------------------------------- */
 int64_t am_normalize_work_bytes(int D);
 int am_normalize(const int32_t *d_counts, int64_t n_rows_out, int D,
                  const int64_t *d_row_index, const int32_t *d_col_index, int D_keep,
-                 int method, double *d_out, double *d_colsum, void *d_work, void *stream);
+                 int method, double *d_out, double *d_colsum, double *d_colmaxabs, void *d_work,
+                 void *stream);
 
 /* ---------------------------------------------------------------------------
  * Kernel 3 — PCA (sklearn 1.9 PCA, svd_solver="covariance_eigh", the branch
