@@ -11,8 +11,11 @@
 //      row-major like X, so K = contig rows and the operands are MN-major for the MMA).
 //   2. gram_i8_kernel: sum_r q_ri q_rj = sum_{s,t} 256^(2(S-1)-s-t) sum_r a_s[r,i] a_t[r,j];
 //      the digit products are exact in int32 and each weight d = s+t gets its own TMEM
-//      accumulator P_d (S accumulators of 128 x 64 int32).  Pairs with s+t >= S (relative weight
-//      <= 2^-8S) are dropped.  One persistent CTA per SM: warp 0 = TMA producer (planes -> smem,
+//      accumulator P_d (128 x 64 int32, adjacent TMEM columns).  Because the accumulators of
+//      A_s x B_t, t = 0..S-1-s, are adjacent and the B planes are adjacent in shared memory, one
+//      tcgen05.mma with N = 64 (S-s) (<= 256) covers a whole row of pairs: 9 instructions per K
+//      step instead of 22.  Pairs with s+t >= S (relative weight <= 2^-8S) are dropped, except
+//      the square term (S/2, S/2), the only one with a systematic contribution (diag of G).  One persistent CTA per SM: warp 0 = TMA producer (planes -> smem,
 //      128B/64B swizzle), warp 1 = single-thread tcgen05.mma issuer, warps 2-5 = epilogue
 //      (tcgen05.ld -> fp64 combine sum_d 2^-8d P_d -> partial tile in the workspace).
 //   3. gram_i8_reduce_kernel: partial tiles are summed over row chunks in a FIXED order
@@ -96,8 +99,11 @@ struct GramI8Params {
   int n_tiles;        // upper-triangular tiles: sum_I (TJ - 2I)
   int stages;
   int n_acc;          // TMEM accumulators (distinct weights d = s + t)
-  int n_pairs;        // digit-plane pairs multiplied per K step
-  uint8_t ps[32], pt[32], pd[32], pfirst[32];  // pair i: planes (s, t) -> accumulator d; first pair of its d
+  int n_ops;          // MMA instructions per K step
+  // op i: A plane os[i] (128 cols) x B planes [ot[i], ot[i] + on[i]) side by side (N = 64 * on[i])
+  // -> accumulators od[i] .. od[i] + on[i] - 1 (adjacent TMEM columns); ofirst[i]: bit j set when
+  // accumulator od[i] + j is written for the first time in the K step (overwrite on the first K step)
+  uint8_t os[16], ot[16], on[16], od[16], ofirst[16];
 };
 
 __device__ __forceinline__ void decode_tile(int tile, int TJ, int &I, int &Jb) {
@@ -166,9 +172,9 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      // instruction descriptor: D=S32, A=B=signed int8, both MN-major, N=64, M=128
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(GI_N >> 3) << 17) | ((uint32_t)(GI_M >> 4) << 24);
+      // instruction descriptor: D=S32, A=B=signed int8, both MN-major, M=128; N is set per op
+      const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                              ((uint32_t)(GI_M >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -183,12 +189,25 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)stage * stage_bytes;
           const uint32_t sb = sa + (uint32_t)S * GI_A_BYTES;
-          for (int i = 0; i < p.n_pairs; ++i) {
+          for (int i = 0; i < p.n_ops; ++i) {
             // A: 128 cols x 32 rows, 128B swizzle (atom = 128 B x 8 rows -> SBO 1024)
-            const uint64_t da = make_desc(sa + (uint32_t)p.ps[i] * GI_A_BYTES, GI_K * 128, 1024, 2);
-            // B: 64 cols x 32 rows, 64B swizzle (atom = 64 B x 8 rows -> SBO 512)
-            const uint64_t db = make_desc(sb + (uint32_t)p.pt[i] * GI_B_BYTES, GI_K * 64, 512, 4);
-            umma_i8(tmem + (uint32_t)p.pd[i] * GI_N, da, db, idesc, (first && p.pfirst[i]) ? 0u : 1u);
+            const uint64_t da = make_desc(sa + (uint32_t)p.os[i] * GI_A_BYTES, GI_K * 128, 1024, 2);
+            // B: on[i] planes side by side = on[i] atoms of 64 cols x 32 rows along N, 64B swizzle
+            // (atom = 64 B x 8 rows -> SBO 512; next atom along N = next plane -> LBO 2048)
+            const uint64_t db = make_desc(sb + (uint32_t)p.ot[i] * GI_B_BYTES, GI_B_BYTES, 512, 4);
+            const uint32_t idesc = idesc0 | ((uint32_t)((GI_N * p.on[i]) >> 3) << 17);
+            const uint32_t td = tmem + (uint32_t)p.od[i] * GI_N;
+            if (first && p.ofirst[i]) {
+              // some accumulators of this op are touched for the first time in this item: issue them
+              // one plane at a time so each gets its own overwrite/accumulate flag
+              for (int j = 0; j < p.on[i]; ++j) {
+                const uint64_t dbj = make_desc(sb + (uint32_t)(p.ot[i] + j) * GI_B_BYTES, GI_B_BYTES, 512, 4);
+                const uint32_t idj = idesc0 | ((uint32_t)(GI_N >> 3) << 17);
+                umma_i8(td + (uint32_t)j * GI_N, da, dbj, idj, ((p.ofirst[i] >> j) & 1) ? 0u : 1u);
+              }
+            } else {
+              umma_i8(td, da, db, idesc, 1u);
+            }
           }
           first = false;
           umma_commit(bar_empty + 8u * stage);  // frees the smem stage when the MMAs have read it
@@ -292,7 +311,7 @@ gram_i8_reduce_kernel(const double *__restrict__ part, GramI8Params p, int D, co
   const int tile = blockIdx.x;
   int I, Jb;
   decode_tile(tile, p.TJ, I, Jb);
-  for (int el = threadIdx.x; el < GI_M * GI_N; el += blockDim.x) {
+  for (int el = blockIdx.y * blockDim.x + threadIdx.x; el < GI_M * GI_N; el += gridDim.y * blockDim.x) {
     const int i = I * GI_M + el / GI_N, j = Jb * GI_N + el % GI_N;
     if (i >= D || j >= D || j < i) continue;
     double s = 0.0;
@@ -352,18 +371,24 @@ void gram_i8_shape(int64_t n_rows, int D, int S, GramI8Params *p) {
   p->stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
   // pairs kept: s + t <= S-1, plus the square term (S/2, S/2) of weight S when S is even — the only
   // dropped term with a systematic (non zero-mean) contribution, on the diagonal of G
-  int np = 0;
   const int dmax = (S % 2 == 0 && S * 64 + 64 <= 512) ? S : S - 1;
-  for (int d = 0; d <= dmax; ++d)
-    for (int s = 0; s <= d; ++s) {
-      const int t = d - s;
-      if (s >= S || t >= S) continue;
-      if (d == S && s != t) continue;
-      p->ps[np] = (uint8_t)s; p->pt[np] = (uint8_t)t; p->pd[np] = (uint8_t)d;
-      p->pfirst[np] = (np == 0 || p->pd[np - 1] != d) ? 1 : 0;
-      ++np;
-    }
-  p->n_pairs = np;
+  int nops = 0;
+  bool seen[8] = {false, false, false, false, false, false, false, false};
+  auto add_op = [&](int s, int t0, int nt) {
+    p->os[nops] = (uint8_t)s; p->ot[nops] = (uint8_t)t0; p->on[nops] = (uint8_t)nt; p->od[nops] = (uint8_t)(s + t0);
+    uint8_t f = 0;
+    for (int j = 0; j < nt; ++j)
+      if (!seen[s + t0 + j]) { f |= (uint8_t)(1u << j); seen[s + t0 + j] = true; }
+    p->ofirst[nops] = f;
+    ++nops;
+  };
+  for (int s = 0; s < S; ++s) {
+    // A_s against B_0 .. B_{S-1-s}  (weights d = s .. S-1), at most 4 planes (N = 256) per MMA
+    int t0 = 0, left = S - s;
+    while (left > 0) { const int nt = std::min(left, 4); add_op(s, t0, nt); t0 += nt; left -= nt; }
+  }
+  if (dmax == S) add_op(S / 2, S / 2, 1);  // the square term of weight S
+  p->n_ops = nops;
   p->n_acc = dmax + 1;
 }
 
@@ -440,7 +465,7 @@ extern "C" int am_gram_i8(const double *d_X, int64_t n_rows, int D, const double
     gram_i8_kernel<<<grid, GI_THREADS, smem, st>>>(tmA, tmB, p, w.part);
     AM_LAUNCHED("gram_i8_kernel");
   }
-  gram_i8_reduce_kernel<<<p.n_tiles, 256, 0, st>>>(w.part, p, D, w.e, d_G);
+  gram_i8_reduce_kernel<<<dim3(p.n_tiles, GI_M * GI_N / 256), 256, 0, st>>>(w.part, p, D, w.e, d_G);
   AM_LAUNCHED("gram_i8_reduce_kernel");
   return AM_OK;
 }

@@ -298,12 +298,22 @@ ilr_kernel(const int32_t *__restrict__ counts, int64_t n_out, int D,
 __global__ void reduce_partials_kernel(const double *__restrict__ partials, const double *__restrict__ pmax,
                                        int n_parts, int D, double *__restrict__ colsum,
                                        double *__restrict__ colmax) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= D) return;
+  // blockDim = (32 columns, 32 part lanes): lane y sums parts y, y+32, ... (fixed order), then a
+  // fixed-order tree over the 32 lanes -> deterministic
+  __shared__ double rs[32][33], rm[32][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
   double s = 0.0, m = 0.0;
-  for (int p = 0; p < n_parts; ++p) { s += partials[(int64_t)p * D + j]; m = fmax(m, pmax[(int64_t)p * D + j]); }
-  colsum[j] += s;
-  if (colmax) colmax[j] = fmax(colmax[j], m);
+  if (j < D)
+    for (int p = threadIdx.y; p < n_parts; p += 32) { s += partials[(int64_t)p * D + j]; m = fmax(m, pmax[(int64_t)p * D + j]); }
+  rs[threadIdx.y][threadIdx.x] = s;
+  rm[threadIdx.y][threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < D) {
+    double t = 0.0, tm = 0.0;
+    for (int y = 0; y < 32; ++y) { t += rs[y][threadIdx.x]; tm = fmax(tm, rm[y][threadIdx.x]); }
+    colsum[j] += t;
+    if (colmax) colmax[j] = fmax(colmax[j], tm);
+  }
 }
 
 int norm_grid(int64_t n_rows) {
@@ -357,7 +367,7 @@ extern "C" int am_normalize(const int32_t *d_counts, int64_t n_rows_out, int D,
     }
     AM_LAUNCHED("normalize512_kernel");
     if (partials) {
-      reduce_partials_kernel<<<(D_keep + 127) / 128, 128, 0, st>>>(partials, pmax, grid, D_keep, d_colsum, d_colmaxabs);
+      reduce_partials_kernel<<<(D_keep + 31) / 32, dim3(32, 32), 0, st>>>(partials, pmax, grid, D_keep, d_colsum, d_colmaxabs);
       AM_LAUNCHED("reduce_partials_kernel");
     }
     return AM_OK;
@@ -377,7 +387,7 @@ extern "C" int am_normalize(const int32_t *d_counts, int64_t n_rows_out, int D,
   }
   AM_LAUNCHED("normalize_kernel");
   if (partials) {
-    reduce_partials_kernel<<<(D_keep + 127) / 128, 128, 0, st>>>(partials, pmax, grid, D_keep, d_colsum, d_colmaxabs);
+    reduce_partials_kernel<<<(D_keep + 31) / 32, dim3(32, 32), 0, st>>>(partials, pmax, grid, D_keep, d_colsum, d_colmaxabs);
     AM_LAUNCHED("reduce_partials_kernel");
   }
   return AM_OK;
