@@ -67,10 +67,9 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
   double *rows = sm;                          // RL x np
   double *vb = rows + (size_t)RL * np;        // 2 x np
   double *wb = vb + 2 * np;                   // 2 x np
-  double *x = wb + 2 * np;                    // np
-  double *gP = x + np;                        // 2 x np  (all-gathered p slices)
+  double *gP = wb + 2 * np;                   // 2 x np  (all-gathered p slices)
   double *gA = gP + 2 * np;                   // 2 x np  (all-gathered next-column slices)
-  double *red = gA + 2 * np;                  // 32
+  double *red = gA + 2 * np;                  // 4 x TW
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   // load own rows (symmetrised), zero the vectors
@@ -83,7 +82,6 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
     }
   }
   for (int j = tid; j < 2 * np; j += TT) { vb[j] = 0.0; wb[j] = 0.0; gP[j] = 0.0; gA[j] = 0.0; }
-  for (int j = tid; j < np; j += TT) x[j] = 0.0;
   __syncthreads();
   cluster.sync();  // every CTA's buffers exist and are zeroed before any remote store
 
@@ -96,13 +94,29 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
     }
   }
   cluster.sync();
+  // x (the current column below the diagonal) lives in registers: thread t owns rows t and t + TT
+  double x0 = 0.0, x1 = 0.0;
   double sig_part = 0.0;
-  for (int i = tid; i < np; i += TT) {
-    const double xv = (i >= 1 && i < n) ? gA[np + i] : 0.0;
-    x[i] = xv;
-    if (i >= 2) sig_part += xv * xv;
+  {
+    const int i0 = tid, i1 = tid + TT;
+    if (i0 >= 1 && i0 < n) x0 = gA[np + i0];
+    if (i1 >= 1 && i1 < n) x1 = gA[np + i1];
+    if (i0 >= 2) sig_part += x0 * x0;
+    sig_part += x1 * x1;
   }
-  double sigma = block_sum<TW>(sig_part, red);
+  int rslot = 0;
+  auto block_sum1 = [&](double v) -> double {
+    // one barrier per reduction: four rotating slots keep successive reductions apart
+    double *r = red + (rslot & 3) * TW;
+    ++rslot;
+    v = warp_sum(v);
+    if (lane == 0) r[warp] = v;
+    __syncthreads();
+    double t = lane < TW ? r[lane] : 0.0;
+    return warp_sum(t);
+  };
+  double sigma = block_sum1(sig_part);
+  double alpha = (n > 1) ? gA[np + 1] : 0.0;  // x[k+1] for k = 0, same value in every thread
 
   long long tA = 0, tB = 0, tS = 0, tC = 0, t0 = clock64(), t1;
 #define AM_TICK(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
@@ -110,23 +124,26 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
     double *vcur = vb + (k & 1) * np, *wcur = wb + (k & 1) * np;
     const double *vprev = vb + ((k + 1) & 1) * np, *wprev = wb + ((k + 1) & 1) * np;
     // ---- A. reflector from x (replicated in every CTA)
-    const double alpha = x[k + 1];
     double beta, tau, scale;
     if (!(sigma > 1e-290)) {
       beta = alpha; tau = 0.0; scale = 0.0;
     } else {
-      beta = -copysign(sqrt(alpha * alpha + sigma), alpha);
+      beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
       tau = (beta - alpha) / beta;
       scale = 1.0 / (alpha - beta);
     }
-    __syncthreads();  // all reads of x[k+1] / previous vcur slot done before overwriting
-    for (int i = tid; i < np; i += TT)
-      vcur[i] = (i == k + 1) ? 1.0 : ((i > k + 1 && i < n) ? x[i] * scale : 0.0);
-    if (c == 0 && tid == 0) { out.e[k] = beta; out.tau[k] = tau; }
+    {
+      const int i0 = tid, i1 = tid + TT;
+      const double v0 = (i0 == k + 1) ? 1.0 : ((i0 > k + 1 && i0 < n) ? x0 * scale : 0.0);
+      if (i0 < np) vcur[i0] = v0;
+      if (i1 < np) vcur[i1] = (i1 == k + 1) ? 1.0 : ((i1 > k + 1 && i1 < n) ? x1 * scale : 0.0);
+      if (c == (k % TC)) {
+        if (i0 < np) out.V[(size_t)k * np + i0] = v0;
+        if (i1 < np) out.V[(size_t)k * np + i1] = vcur[i1];
+        if (tid == 0) { out.e[k] = beta; out.tau[k] = tau; }
+      }
+    }
     __syncthreads();
-    if (c == (k % TC))
-      for (int i = tid; i < np; i += TT) out.V[(size_t)k * np + i] = vcur[i];
-
     AM_TICK(tA);
     // ---- B. fused pass over own rows >= k: apply pending update (k-1), p = tau * A v_k
     {
@@ -141,6 +158,7 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
         if (lr < RL && i < n && i >= k) { lrs[r] = lr; vpi[r] = vprev[i]; wpi[r] = wprev[i]; nr = r + 1; }
       }
       if (nr > 0) {
+#pragma unroll 2
         for (int j = (k & ~31) + lane; j < np; j += 32) {
           const double vpj = vprev[j], wpj = wprev[j], vcj = vcur[j];
 #pragma unroll
@@ -175,27 +193,31 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
     cluster.sync();
     AM_TICK(tS);
 
-    // ---- C. w_k, next column x_{k+1} (replicated)
+    // ---- C. w_k and the next column x_{k+1} (replicated; two one-barrier reductions)
     const double *P = gP + (k & 1) * np, *AC = gA + (k & 1) * np;
-    double part = 0.0;
-    for (int j = tid; j < np; j += TT)
-      if (j >= k + 1 && j < n) part = fma(P[j], vcur[j], part);
-    const double gamma = block_sum<TW>(part, red);
+    const int i0 = tid, i1 = tid + TT;
+    const bool in0 = (i0 >= k + 1 && i0 < n), in1 = (i1 >= k + 1 && i1 < n);
+    const double p0 = in0 ? P[i0] : 0.0, p1 = in1 ? P[i1] : 0.0;
+    const double v0 = (i0 < np) ? vcur[i0] : 0.0, v1 = (i1 < np) ? vcur[i1] : 0.0;
+    const double gamma = block_sum1(fma(p0, v0, p1 * v1));
     const double Kc = 0.5 * tau * gamma;
-    for (int j = tid; j < np; j += TT) wcur[j] = (j >= k + 1 && j < n) ? fma(-Kc, vcur[j], P[j]) : 0.0;
-    __syncthreads();
-    const double wk1 = wcur[k + 1];
-    sig_part = 0.0;
-    for (int i = tid; i < np; i += TT) {
-      double xv = 0.0;
-      if (i >= k + 2 && i < n) xv = AC[i] - vcur[i] * wk1 - wcur[i];
-      x[i] = xv;
-      if (i >= k + 3) sig_part += xv * xv;
+    const double w0 = in0 ? fma(-Kc, v0, p0) : 0.0, w1 = in1 ? fma(-Kc, v1, p1) : 0.0;
+    if (i0 < np) wcur[i0] = w0;
+    if (i1 < np) wcur[i1] = w1;
+    const double wk1 = P[k + 1] - Kc;  // w_k[k+1]  (v_k[k+1] = 1)
+    x0 = (i0 >= k + 2 && i0 < n) ? AC[i0] - v0 * wk1 - w0 : 0.0;
+    x1 = (i1 >= k + 2 && i1 < n) ? AC[i1] - v1 * wk1 - w1 : 0.0;
+    sig_part = ((i0 >= k + 3) ? x0 * x0 : 0.0) + ((i1 >= k + 3) ? x1 * x1 : 0.0);
+    sigma = block_sum1(sig_part);
+    // alpha of the next step = x_{k+1}[k+2], recomputed by every thread from the gathered vectors
+    if (k + 2 < n) {
+      const double vk2 = vcur[k + 2];
+      alpha = AC[k + 2] - vk2 * wk1 - fma(-Kc, vk2, P[k + 2]);
     }
-    sigma = block_sum<TW>(sig_part, red);
     AM_TICK(tC);
   }
   if (out.dbg && c == 0 && tid == 0) { out.dbg[0] = tA; out.dbg[1] = tB; out.dbg[2] = tS; out.dbg[3] = tC; }
+  __syncthreads();
 
   // epilogue: pending update (n-3) on rows/cols >= n-2, then d and the last e
   {
@@ -229,16 +251,31 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
 // ------------------------------------------------------------------ 2. bisection
 constexpr int BT = 512;  // shifts per round
 
-__device__ __forceinline__ int sturm_count(const double *d, const double *e2, int n, double x, double pivmin) {
-  // number of eigenvalues of T that are < x (LAPACK dlaebz recurrence)
-  int cnt = 0;
-  double q = d[0] - x;
-  if (fabs(q) < pivmin) q = -pivmin;
-  cnt += q < 0.0;
+// Number of eigenvalues of T that are < x, from the sign changes of the leading principal minors
+// u_j = (d_j - x) u_{j-1} - e_{j-1}^2 u_{j-2}  (Sturm sequence).  One FMA on the dependent chain per
+// row instead of a division; both running minors are rescaled by a power of two every 4 rows.  An
+// exactly zero minor takes the sign opposite to its predecessor (LAPACK dlaebz's pivmin rule).
+__device__ __forceinline__ int sturm_count(const double *d, const double *e2, int n, double x) {
+  double um = 1.0, u = d[0] - x;   // u_{-1}, u_0
+  bool sm = false;                 // "negative" flag of u_{j-1} (pseudo-sign with the zero rule)
+  bool sc = (u < 0.0) || (u == 0.0);
+  int cnt = sc ? 1 : 0;
   for (int i = 1; i < n; ++i) {
-    q = (d[i] - x) - e2[i - 1] / q;
-    if (fabs(q) < pivmin) q = -pivmin;
-    cnt += q < 0.0;
+    const double t = e2[i - 1] * um;
+    const double un = fma(d[i] - x, u, -t);
+    um = u;
+    u = un;
+    sm = sc;
+    sc = (u == 0.0) ? !sm : (u < 0.0);
+    cnt += (sc != sm);
+    if ((i & 3) == 3) {
+      const int ex = max((__double2hiint(u) >> 20) & 0x7ff, (__double2hiint(um) >> 20) & 0x7ff);
+      if (ex > 0 && ex < 2046) {
+        const double f = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023 - ex)
+        u *= f;
+        um *= f;
+      }
+    }
   }
   return cnt;
 }
@@ -276,16 +313,23 @@ bisect_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int 
   tr = block_sum<BT / 32>(tr, red);
   if (blockIdx.x == 0 && tid == 0 && trace) *trace = tr;
   const double tnorm = fmax(fabs(gl), fabs(gu));
-  const double pivmin = 2.2250738585072014e-308 * fmax(1.0, emax);
   const double ulp = 2.220446049250313e-16;
-  double lo = gl - 2.0 * tnorm * ulp * n - 2.0 * pivmin;
-  double hi = gu + 2.0 * tnorm * ulp * n + 2.0 * pivmin;
+  // work on T / 2^ex (|entries| <= 1): the minors then grow by at most 3x per row
+  int ex = 0;
+  if (tnorm > 0.0) frexp(tnorm, &ex);
+  const double sdn = ldexp(1.0, -ex), sup = ldexp(1.0, ex);
+  for (int i = tid; i < n; i += BT) { d[i] *= sdn; e2[i] *= sdn * sdn; }
+  __syncthreads();
+  gl *= sdn; gu *= sdn;
+  const double pivmin = 1e-290;
+  double lo = gl - 2.0 * ulp * n - 2.0 * pivmin;
+  double hi = gu + 2.0 * ulp * n + 2.0 * pivmin;
   const int target = n - jtop;  // want smallest x with count(x) >= target  (lambda index n-1-jtop ascending)
   for (int round = 0; round < 12; ++round) {
     const double width = hi - lo;
     if (!(width > 2.0 * ulp * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin)) break;
     const double xt = lo + width * ((double)(tid + 1) / (double)(BT + 1));
-    const int cnt = sturm_count(d, e2, n, xt, pivmin);
+    const int cnt = sturm_count(d, e2, n, xt);
     const unsigned ball = __ballot_sync(FULL, cnt >= target);
     if (lane == 0) first_warp[warp] = ball ? (warp * 32 + __ffs(ball) - 1) : -1;
     __syncthreads();
@@ -303,7 +347,18 @@ bisect_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int 
     lo = s_lo; hi = s_hi;
     __syncthreads();
   }
-  if (tid == 0) lam[jtop] = 0.5 * (lo + hi);
+  if (tid == 0) lam[jtop] = 0.5 * (lo + hi) * sup;
+}
+
+// 1/q to full double precision without the IEEE-division slow path (q is finite, non-zero, normal)
+__device__ __forceinline__ double fast_rcp(double q) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(q));
+  double e = fma(-q, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-q, r, 1.0);
+  r = fma(r, e, r);
+  return r;
 }
 
 // ------------------------------------------------------------------ 3. inverse iteration
@@ -347,13 +402,13 @@ invit_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int n
       if (fabs(dd[i]) >= fabs(dl[i])) {
         piv[i] = 0;
         if (fabs(dd[i]) < tinyp) dd[i] = copysign(tinyp, dd[i]);
-        const double fact = dl[i] / dd[i];
+        const double fact = dl[i] * fast_rcp(dd[i]);
         dl[i] = fact;
         dd[i + 1] -= fact * du[i];
         du2[i] = 0.0;
       } else {
         piv[i] = 1;
-        const double fact = dd[i] / dl[i];
+        const double fact = dd[i] * fast_rcp(dl[i]);
         dd[i] = dl[i];
         dl[i] = fact;
         const double temp = du[i];
@@ -367,7 +422,9 @@ invit_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int n
   __syncwarp();
   for (int i = lane; i < n; i += 32) rdd[i] = 1.0 / dd[i];
   __syncwarp();
-  for (int it = 0; it < 3; ++it) {
+  // dstein-style: start from a vector of norm ~ eps |T|, stop once the solve has grown it to O(1)
+  // (the shift is an eigenvalue to working precision, so one or two solves suffice)
+  for (int it = 0; it < 4; ++it) {
     if (lane == 0) {
       for (int i = 0; i < n - 1; ++i) {
         if (!piv[i]) {
@@ -389,6 +446,9 @@ invit_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int n
     const double inv = mx > 0.0 ? 1.0 / mx : 1.0;
     for (int i = lane; i < n; i += 32) b[i] *= inv;
     __syncwarp();
+    // growth of a unit-max vector by ~1/(eps |T|) means the iterate is the eigenvector; the second
+    // solve polishes it
+    if (it >= 1 && mx * tnorm * ulp * (double)n >= 1e-3) break;
   }
   double ss = 0.0;
   for (int i = lane; i < n; i += 32) ss += b[i] * b[i];
@@ -399,11 +459,9 @@ invit_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int n
 
 // ------------------------------------------------------------------ 4. CholeskyQR2 on the P rows of Y
 constexpr int CT = 1024;
-__global__ void __launch_bounds__(CT)
-cholqr_kernel(double *__restrict__ Y, int n, int np, int P) {
-  extern __shared__ double sm[];
-  double *G = sm;  // P x P (row-major), becomes L (lower)
+__device__ void orthonormalise_rows(double *Y, double *G, int n, int np, int P, bool have_m) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double s_emax[CT / 32];
   for (int pass = 0; pass < 2; ++pass) {
     const int npairs = P * (P + 1) / 2;
     for (int pr = warp; pr < npairs; pr += CT / 32) {
@@ -418,6 +476,65 @@ cholqr_kernel(double *__restrict__ Y, int n, int np, int P) {
       if (lane == 0) { G[a * P + bb] = s; G[bb * P + a] = s; }
     }
     __syncthreads();
+    // departure from orthonormality E = G - I
+    double em = 0.0;
+    for (int q = tid; q < P * P; q += CT) em = fmax(em, fabs(G[q] - ((q / P == q % P) ? 1.0 : 0.0)));
+    for (int o = 16; o > 0; o >>= 1) em = fmax(em, __shfl_xor_sync(FULL, em, o));
+    if (lane == 0) s_emax[warp] = em;
+    __syncthreads();
+    em = 0.0;
+    for (int w = 0; w < CT / 32; ++w) em = fmax(em, s_emax[w]);
+    __syncthreads();
+    if (em <= 4e-16) return;  // already orthonormal to working precision
+    if (em <= 1e-5 && have_m) {
+      // well separated eigenvalues: symmetric (Loewdin) orthogonalisation, second order in E:
+      // Y <- (I - E/2 + 3 E^2 / 8) Y, error O(E^3) <= 1e-15.  No sequential dependence.
+      double *M = G + P * P;  // second P x P buffer
+      for (int q = tid; q < P * P; q += CT) {
+        const int a = q / P, b = q % P;
+        double e2 = 0.0;
+        for (int m = 0; m < P; ++m) {
+          const double ea = G[a * P + m] - (a == m ? 1.0 : 0.0), eb = G[m * P + b] - (m == b ? 1.0 : 0.0);
+          e2 = fma(ea, eb, e2);
+        }
+        const double e1 = G[q] - (a == b ? 1.0 : 0.0);
+        M[q] = (a == b ? 1.0 : 0.0) - 0.5 * e1 + 0.375 * e2;
+      }
+      __syncthreads();
+      // Y <- M Y with register accumulators: one work unit = 16 rows a of one element column i
+      constexpr int AG = 16;
+      const int ngroups = (P + AG - 1) / AG;
+      const int nwork = ngroups * n;
+      const int rounds = (nwork + CT - 1) / CT;
+      for (int rd = 0; rd < rounds; ++rd) {
+        const int work = rd * CT + tid;
+        const int g = work / n, i = work % n;
+        double acc[AG];
+#pragma unroll
+        for (int aa = 0; aa < AG; ++aa) acc[aa] = 0.0;
+        if (work < nwork) {
+          for (int b = 0; b < P; ++b) {
+            const double y = Y[(size_t)b * np + i];
+#pragma unroll
+            for (int aa = 0; aa < AG; ++aa) {
+              const int a = g * AG + aa;
+              if (a < P) acc[aa] = fma(M[a * P + b], y, acc[aa]);
+            }
+          }
+        }
+        // rows of column i are read by the other groups of the same column in this round only
+        __syncthreads();
+        if (work < nwork) {
+#pragma unroll
+          for (int aa = 0; aa < AG; ++aa) {
+            const int a = g * AG + aa;
+            if (a < P) Y[(size_t)a * np + i] = acc[aa];
+          }
+        }
+        __syncthreads();
+      }
+      return;
+    }
     if (warp == 0) {
       for (int cidx = 0; cidx < P; ++cidx) {
         double dsum = G[cidx * P + cidx];
@@ -448,6 +565,22 @@ cholqr_kernel(double *__restrict__ Y, int n, int np, int P) {
   }
 }
 
+__global__ void __launch_bounds__(CT)
+cholqr_kernel(double *__restrict__ Yg, int n, int np, int P, int y_in_smem, int have_m) {
+  extern __shared__ double sm[];
+  double *G = sm;                 // P x P (+ a second P x P buffer when have_m)
+  double *Ys = sm + (have_m ? 2 : 1) * P * P;    // P x np when it fits (the 50 x 512 case: 200 KB)
+  if (y_in_smem) {
+    for (int q = threadIdx.x; q < P * np; q += CT) Ys[q] = Yg[q];
+    __syncthreads();
+    orthonormalise_rows(Ys, G, n, np, P, have_m != 0);
+    __syncthreads();
+    for (int q = threadIdx.x; q < P * np; q += CT) Yg[q] = Ys[q];
+  } else {
+    orthonormalise_rows(Yg, G, n, np, P, have_m != 0);
+  }
+}
+
 // ------------------------------------------------------------------ 5. back-transformation + sign + output
 constexpr int KT = 128;
 __global__ void __launch_bounds__(KT)
@@ -461,16 +594,47 @@ backtransform_kernel(const double *__restrict__ V, const double *__restrict__ ta
   __shared__ int s_idx[KT / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = blockIdx.x;
-  for (int i = tid; i < np; i += KT) z[i] = Y[(size_t)j * np + i];
-  __syncthreads();
+  // z in registers: thread t owns rows t + KT*m; the reflector of the NEXT step is prefetched while
+  // the current one is reduced (one barrier per step, rotating reduction slots)
+  constexpr int ZM = 5;  // np <= 576 -> <= 5 rows per thread at KT = 128
+  double zr[ZM], vn[ZM], vc[ZM];
+#pragma unroll
+  for (int m = 0; m < ZM; ++m) {
+    const int i = tid + KT * m;
+    zr[m] = (i < np) ? Y[(size_t)j * np + i] : 0.0;
+    vn[m] = (i < np && n >= 3) ? __ldg(V + (size_t)(n - 3) * np + i) : 0.0;
+  }
+  int slot = 0;
   for (int k = n - 3; k >= 0; --k) {
-    const double *vk = V + (size_t)k * np;
     const double tk = __ldg(tau + k);
+#pragma unroll
+    for (int m = 0; m < ZM; ++m) vc[m] = vn[m];
+    if (k > 0) {
+#pragma unroll
+      for (int m = 0; m < ZM; ++m) {
+        const int i = tid + KT * m;
+        vn[m] = (i < np) ? __ldg(V + (size_t)(k - 1) * np + i) : 0.0;
+      }
+    }
     double part = 0.0;
-    for (int i = (k & ~(KT - 1)) + tid; i < n; i += KT) part = fma(__ldg(vk + i), z[i], part);  // v_k is 0 up to k
-    const double s = tk * block_sum<KT / 32>(part, red);
-    for (int i = (k & ~(KT - 1)) + tid; i < n; i += KT) z[i] = fma(-s, __ldg(vk + i), z[i]);
-    // the block_sum of the next step synchronises before any z is read by another thread
+#pragma unroll
+    for (int m = 0; m < ZM; ++m) part = fma(vc[m], zr[m], part);
+    part = warp_sum(part);
+    double *r = red + (slot & 3) * (KT / 32);
+    ++slot;
+    if (lane == 0) r[warp] = part;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < KT / 32; ++w) tot += r[w];
+    const double sc = tk * tot;
+#pragma unroll
+    for (int m = 0; m < ZM; ++m) zr[m] = fma(-sc, vc[m], zr[m]);
+  }
+#pragma unroll
+  for (int m = 0; m < ZM; ++m) {
+    const int i = tid + KT * m;
+    if (i < np) z[i] = zr[m];
   }
   __syncthreads();
   // sklearn svd_flip(u_based_decision=False): largest-|.| entry (first occurrence) made positive
@@ -544,7 +708,7 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
 
   // 1. tridiagonalisation (one cluster of 16 CTAs)
   {
-    const size_t smem = ((size_t)RL * np + 9 * (size_t)np + 32) * sizeof(double);
+    const size_t smem = ((size_t)RL * np + 8 * (size_t)np + 4 * TW) * sizeof(double);
     if (smem > 227 * 1024) return am::fail(AM_EINVAL, "am_eigh_topk: matrix does not fit the cluster's shared memory");
     AM_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AM_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -579,10 +743,13 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
   }
   // 4. CholeskyQR2
   if (P > 1) {
-    const size_t smem = (size_t)P * P * sizeof(double);
+    const int have_m = (P <= 64) ? 1 : 0;  // second P x P buffer for the Loewdin fast path
+    size_t smem = (size_t)(have_m ? 2 : 1) * P * P * sizeof(double);
+    int y_in_smem = 0;
+    if (smem + (size_t)P * np * sizeof(double) <= 227 * 1024) { smem += (size_t)P * np * sizeof(double); y_in_smem = 1; }
     if (smem > 48 * 1024)
       AM_CUDA(cudaFuncSetAttribute(cholqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cholqr_kernel<<<1, CT, smem, st>>>(w.Y, n, np, P);
+    cholqr_kernel<<<1, CT, smem, st>>>(w.Y, n, np, P, y_in_smem, have_m);
     AM_LAUNCHED("cholqr_kernel");
   }
   // 5. back-transformation
