@@ -56,18 +56,26 @@ _SIGS = {
     "am_count_kmers": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p]),
     "am_normalize_work_bytes": (_i64, [_i32]),
     "am_normalize": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _i32, _p, _p, _p, _p, _p]),
+    "am_normalize_planes": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "am_colsum_work_bytes": (_i64, [_i32]),
     "am_colsum": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "am_colstats_work_bytes": (_i64, [_i32]),
     "am_colstats": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
     "am_gram_i8_work_bytes": (_i64, [_i64, _i32, _i32]),
     "am_gram_i8": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _p]),
+    "am_planes_bytes": (_i64, [_i64, _i32, _i32]),
+    "am_plane_scales": (C.c_int, [_p, _p, _f64, _i32, _i32, _p, _p, _p]),
+    "am_quantize_planes": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _p, _p]),
+    "am_gram_planes_work_bytes": (_i64, [_i64, _i32, _i32]),
+    "am_gram_planes": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p]),
     "am_gram_work_bytes": (_i64, [_i32]),
     "am_gram": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
     "am_eigh_work_bytes": (_i64, [_i32]),
     "am_eigh": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _f64, _p]),
     "am_eigh_topk_work_bytes": (_i64, [_i32, _i32]),
     "am_eigh_topk": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p]),
+    "am_project_planes_work_bytes": (_i64, [_i32, _i32]),
+    "am_project_planes": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "am_project": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _p, _p]),
     "am_dbscan_work_bytes": (_i64, [_i64]),
     "am_eps_union": (C.c_int, [_p, _i64, _i32, _f64, _p, _p, _p, _p, _p]),

@@ -20,6 +20,7 @@ SOURCES = [
     "am_normalize.cu",
     "am_pca.cu",
     "am_gram_i8.cu",
+    "am_project_i8.cu",
     "am_eigh.cu",
     "am_eigtop.cu",
     "am_dbscan.cu",

@@ -22,9 +22,8 @@
 //      (deterministic), scaled by 2^(e_i+e_j-12) and mirrored into the symmetric G.
 // With S = 6 the quantisation step is 2^-46 of the column range; the integer arithmetic adds no
 // rounding at all, so G is at least as accurate as an fp64 BLAS Gram.
-#include <cuda.h>
-
 #include "am_common.cuh"
+#include "am_tc.cuh"
 
 namespace {
 
@@ -36,58 +35,7 @@ constexpr int GI_THREADS = 192;
 constexpr int GI_A_BYTES = GI_M * GI_K;  // 4096 per plane per stage
 constexpr int GI_B_BYTES = GI_N * GI_K;  // 2048 per plane per stage
 
-// ------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// shared-memory matrix descriptor, MN-major operand, one swizzle atom wide (SM100 format:
-// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64))
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout << 61;
-  return d;
-}
+using namespace amtc;
 
 struct GramI8Params {
   int S;              // digit planes
@@ -261,11 +209,13 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------ 1. quantisation into digit planes
-__global__ void prep_scales_kernel(const double *__restrict__ mu, const double *__restrict__ colmaxabs, int D,
-                                   int S, int *__restrict__ e, double *__restrict__ sc) {
+__global__ void prep_scales_kernel(const double *__restrict__ mu, const double *__restrict__ colmaxabs,
+                                   double bound_all, int D, int S, int *__restrict__ e,
+                                   double *__restrict__ sc) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= D) return;
-  const double bound = colmaxabs[j] + fabs(mu[j]);
+  // |x - centre| <= max|x| + |centre|; max|x| per column when given, else the caller's global bound
+  const double bound = (colmaxabs ? colmaxabs[j] : bound_all) + fabs(mu[j]);
   int ej = 0;
   if (bound > 0.0 && isfinite(bound)) ej = ilogb(bound) + 1;  // 2^ej > bound >= max|x - mu|
   e[j] = ej;
@@ -323,29 +273,6 @@ gram_i8_reduce_kernel(const double *__restrict__ part, GramI8Params p, int D, co
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-struct I8Work {
-  int8_t *planes;
-  double *part;
-  int *e;
-  double *sc;
-};
-
 inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 void gram_i8_shape(int64_t n_rows, int D, int S, GramI8Params *p) {
@@ -392,31 +319,91 @@ void gram_i8_shape(int64_t n_rows, int D, int S, GramI8Params *p) {
   p->n_acc = dmax + 1;
 }
 
-int64_t carve_i8(void *base, int64_t n_rows, int D, int S, I8Work *w) {
-  GramI8Params p;
-  gram_i8_shape(n_rows, D, S, &p);
-  const int Dp = (D + 15) & ~15;
-  int64_t off = 0;
-  char *b = (char *)base;
-  auto take = [&](int64_t bytes) {
-    char *q = b ? b + off : nullptr;
-    off += align256(bytes);
-    return q;
-  };
-  I8Work t;
-  t.planes = (int8_t *)take((int64_t)S * n_rows * Dp + 1024);
-  t.part = (double *)take((int64_t)p.n_chunks * p.n_tiles * GI_M * GI_N * 8);
-  t.e = (int *)take((int64_t)D * 4);
-  t.sc = (double *)take((int64_t)D * 8);
-  if (w) *w = t;
-  return off;
-}
+inline int plane_pitch(int D) { return (D + 15) & ~15; }
 
 }  // namespace
 
+extern "C" int64_t am_planes_bytes(int64_t n_rows, int D, int S) {
+  if (n_rows < 0 || D < 1 || S < 2 || S > GI_MAXS) return 0;
+  return align256((int64_t)S * n_rows * plane_pitch(D) + 1024);
+}
+
+extern "C" int am_plane_scales(const double *d_center, const double *d_colmaxabs, double bound, int D, int S,
+                               int32_t *d_e, double *d_sc, void *stream) {
+  if (D < 1 || S < 2 || S > GI_MAXS) return am::fail(AM_EINVAL, "am_plane_scales: bad D or S");
+  if (!d_center || !d_e || !d_sc) return am::fail(AM_EINVAL, "am_plane_scales: null pointer");
+  if (!d_colmaxabs && !(bound >= 0.0)) return am::fail(AM_EINVAL, "am_plane_scales: need colmaxabs or a bound");
+  prep_scales_kernel<<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_center, d_colmaxabs, bound, D, S, d_e, d_sc);
+  AM_LAUNCHED("prep_scales_kernel");
+  return AM_OK;
+}
+
+extern "C" int am_quantize_planes(const double *d_X, int64_t n_rows, int D, const double *d_center,
+                                  const double *d_sc, int S, int8_t *d_planes, void *stream) {
+  if (D < 1 || n_rows < 0 || S < 2 || S > GI_MAXS) return am::fail(AM_EINVAL, "am_quantize_planes: bad shape");
+  if (n_rows == 0) return AM_OK;
+  if (!d_X || !d_center || !d_sc || !d_planes) return am::fail(AM_EINVAL, "am_quantize_planes: null pointer");
+  const int Dp = plane_pitch(D);
+  const int64_t total = n_rows * (Dp / 8);
+  const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)am::num_sms() * 16);
+  quantize_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_X, n_rows, D, Dp, d_center, d_sc, S, d_planes);
+  AM_LAUNCHED("quantize_planes_kernel");
+  return AM_OK;
+}
+
+extern "C" int64_t am_gram_planes_work_bytes(int64_t n_rows, int D, int S) {
+  if (n_rows < 1 || D < 1 || S < 2 || S > GI_MAXS) return 0;
+  GramI8Params p;
+  gram_i8_shape(n_rows, D, S, &p);
+  return align256((int64_t)p.n_chunks * p.n_tiles * GI_M * GI_N * 8);
+}
+
+extern "C" int am_gram_planes(const int8_t *d_planes, int64_t n_rows, int D, int S, const int32_t *d_e,
+                              double *d_G, void *d_work, void *stream) {
+  if (D < 1 || n_rows < 0 || n_rows > 0x7fffffff) return am::fail(AM_EINVAL, "am_gram_planes: bad shape");
+  if (S < 2 || S > GI_MAXS) return am::fail(AM_EINVAL, "am_gram_planes: S (digit planes) must be in 2..7");
+  if (n_rows == 0) return AM_OK;
+  if (!d_planes || !d_e || !d_G || !d_work) return am::fail(AM_EINVAL, "am_gram_planes: null pointer");
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return am::fail(AM_ECUDA, "am_gram_planes: cuTensorMapEncodeTiled entry point unavailable");
+  cudaStream_t st = (cudaStream_t)stream;
+  GramI8Params p;
+  gram_i8_shape(n_rows, D, S, &p);
+  const int Dp = plane_pitch(D);
+  double *part = (double *)d_work;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)n_rows, (cuuint64_t)S};
+    cuuint64_t gstr[2] = {(cuuint64_t)Dp, (cuuint64_t)Dp * (cuuint64_t)n_rows};
+    cuuint32_t estr[3] = {1, 1, 1};
+    cuuint32_t boxA[3] = {GI_M, GI_K, 1};
+    cuuint32_t boxB[3] = {GI_N, GI_K, 1};
+    CUresult r1 = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)d_planes, gdim, gstr, boxA, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)d_planes, gdim, gstr, boxB, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return am::fail(AM_ECUDA, "am_gram_planes: cuTensorMapEncodeTiled failed");
+  }
+  {
+    const size_t smem = (size_t)p.stages * S * (GI_A_BYTES + GI_B_BYTES) + 16 * (size_t)p.stages + 64 + 1024;
+    AM_CUDA(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_items = p.n_chunks * p.n_tiles;
+    const int grid = std::min(n_items, am::num_sms());
+    gram_i8_kernel<<<grid, GI_THREADS, smem, st>>>(tmA, tmB, p, part);
+    AM_LAUNCHED("gram_i8_kernel");
+  }
+  gram_i8_reduce_kernel<<<dim3(p.n_tiles, GI_M * GI_N / 256), 256, 0, st>>>(part, p, D, d_e, d_G);
+  AM_LAUNCHED("gram_i8_reduce_kernel");
+  return AM_OK;
+}
+
+// convenience: scales from (mu, colmaxabs) + quantise + Gram of the planes, all in d_work
 extern "C" int64_t am_gram_i8_work_bytes(int64_t n_rows, int D, int S) {
   if (n_rows < 1 || D < 1 || S < 2 || S > GI_MAXS) return 0;
-  return carve_i8(nullptr, n_rows, D, S, nullptr);
+  return am_planes_bytes(n_rows, D, S) + am_gram_planes_work_bytes(n_rows, D, S) + align256((int64_t)D * 4) +
+         align256((int64_t)D * 8);
 }
 
 extern "C" int am_gram_i8(const double *d_X, int64_t n_rows, int D, const double *d_mu,
@@ -425,47 +412,17 @@ extern "C" int am_gram_i8(const double *d_X, int64_t n_rows, int D, const double
   if (S < 2 || S > GI_MAXS) return am::fail(AM_EINVAL, "am_gram_i8: S (digit planes) must be in 2..7");
   if (n_rows == 0) return AM_OK;
   if (!d_X || !d_mu || !d_colmaxabs || !d_G || !d_work) return am::fail(AM_EINVAL, "am_gram_i8: null pointer");
-  EncodeTiledFn encode = get_encode();
-  if (!encode) return am::fail(AM_ECUDA, "am_gram_i8: cuTensorMapEncodeTiled entry point unavailable");
-  cudaStream_t st = (cudaStream_t)stream;
-  GramI8Params p;
-  gram_i8_shape(n_rows, D, S, &p);
-  I8Work w;
-  carve_i8(d_work, n_rows, D, S, &w);
-  const int Dp = (D + 15) & ~15;
-
-  prep_scales_kernel<<<(D + 127) / 128, 128, 0, st>>>(d_mu, d_colmaxabs, D, S, w.e, w.sc);
-  AM_LAUNCHED("prep_scales_kernel");
-  {
-    const int64_t total = n_rows * (Dp / 8);
-    const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)am::num_sms() * 16);
-    quantize_planes_kernel<<<grid, 256, 0, st>>>(d_X, n_rows, D, Dp, d_mu, w.sc, S, w.planes);
-    AM_LAUNCHED("quantize_planes_kernel");
-  }
-  CUtensorMap tmA, tmB;
-  {
-    cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)n_rows, (cuuint64_t)S};
-    cuuint64_t gstr[2] = {(cuuint64_t)Dp, (cuuint64_t)Dp * (cuuint64_t)n_rows};
-    cuuint32_t estr[3] = {1, 1, 1};
-    cuuint32_t boxA[3] = {GI_M, GI_K, 1};
-    cuuint32_t boxB[3] = {GI_N, GI_K, 1};
-    CUresult r1 = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, w.planes, gdim, gstr, boxA, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CUresult r2 = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, w.planes, gdim, gstr, boxB, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return am::fail(AM_ECUDA, "am_gram_i8: cuTensorMapEncodeTiled failed");
-  }
-  {
-    const size_t smem = (size_t)p.stages * S * (GI_A_BYTES + GI_B_BYTES) + 16 * (size_t)p.stages + 64 + 1024;
-    AM_CUDA(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int n_items = p.n_chunks * p.n_tiles;
-    const int grid = std::min(n_items, am::num_sms());
-    gram_i8_kernel<<<grid, GI_THREADS, smem, st>>>(tmA, tmB, p, w.part);
-    AM_LAUNCHED("gram_i8_kernel");
-  }
-  gram_i8_reduce_kernel<<<dim3(p.n_tiles, GI_M * GI_N / 256), 256, 0, st>>>(w.part, p, D, w.e, d_G);
-  AM_LAUNCHED("gram_i8_reduce_kernel");
-  return AM_OK;
+  char *b = (char *)d_work;
+  int8_t *planes = (int8_t *)b;
+  b += am_planes_bytes(n_rows, D, S);
+  void *gwork = b;
+  b += am_gram_planes_work_bytes(n_rows, D, S);
+  int32_t *e = (int32_t *)b;
+  b += align256((int64_t)D * 4);
+  double *sc = (double *)b;
+  int rc = am_plane_scales(d_mu, d_colmaxabs, -1.0, D, S, e, sc, stream);
+  if (rc) return rc;
+  rc = am_quantize_planes(d_X, n_rows, D, d_mu, sc, S, planes, stream);
+  if (rc) return rc;
+  return am_gram_planes(planes, n_rows, D, S, e, d_G, gwork, stream);
 }

@@ -220,6 +220,126 @@ normalize512_kernel(const int32_t *__restrict__ counts, int64_t n_out, const int
   }
 }
 
+// balanced base-256 digits (most significant first) of q = round(v), |v| <= 2^46
+__device__ __forceinline__ void digits6(double v, int (&a)[6]) {
+  const long long q = __double2ll_rn(v);
+  int lo = (int)((unsigned)(q + 0x800000LL) & 0xFFFFFFu) - 0x800000;  // balanced low 24 bits
+  int hi = (int)((q - lo) >> 24);
+  a[5] = ((lo + 128) & 255) - 128; lo = (lo - a[5]) >> 8;
+  a[4] = ((lo + 128) & 255) - 128; lo = (lo - a[4]) >> 8;
+  a[3] = ((lo + 128) & 255) - 128; hi += (lo - a[3]) >> 8;  // carry into the high half
+  a[2] = ((hi + 128) & 255) - 128; hi = (hi - a[2]) >> 8;
+  a[1] = ((hi + 128) & 255) - 128; hi = (hi - a[1]) >> 8;
+  a[0] = hi;
+}
+
+// Fused normalise + quantise (D = 512, S = 6): besides the fp64 row and the column sums, every
+// value is written as the six int8 digit planes that the tensor-core Gram (am_gram_planes) and
+// projection (am_project_planes) consume, so the normalised matrix is never re-read.  Values are
+// taken about a provisional centre (the exact mean is only known after this pass; the Gram is
+// corrected by n (mu - centre)(mu - centre)^T afterwards).  Lane owns columns 128 m + 4 lane + e:
+// 16-byte count loads, 4-byte digit stores (128 contiguous bytes per warp instruction).
+template <int METHOD>
+__global__ void __launch_bounds__(NWARPS * 32)
+normalize512_planes_kernel(const int32_t *__restrict__ counts, int64_t n_out,
+                           const int64_t *__restrict__ row_index, double *__restrict__ out,
+                           double *__restrict__ psum, const double *__restrict__ center,
+                           const double *__restrict__ sc, int8_t *__restrict__ planes) {
+  constexpr int D = 512;
+  extern __shared__ double sm[];
+  double *logt = sm;              // LOGT
+  double *cen = sm + LOGT;        // [16][32] permuted: value i of lane l at i*32 + l
+  double *scl = cen + D;          // same layout
+  double *red = scl + D;          // NWARPS * D
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < LOGT; i += blockDim.x) logt[i] = log((double)(i + 1));
+  for (int q = threadIdx.x; q < D; q += blockDim.x) {
+    const int i = q >> 5, l = q & 31;
+    const int col = 128 * (i >> 2) + 4 * l + (i & 3);
+    cen[q] = center[col];
+    scl[q] = sc[col];
+  }
+  __syncthreads();
+  double csum[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) csum[i] = 0.0;
+  const double lim = 70368744177664.0;  // 2^46
+  const int64_t wstride = (int64_t)gridDim.x * NWARPS;
+  for (int64_t r = (int64_t)blockIdx.x * NWARPS + warp; r < n_out; r += wstride) {
+    const int64_t src = row_index ? row_index[r] : r;
+    const int4 *x4 = reinterpret_cast<const int4 *>(counts + src * D) + lane;
+    int xv[16];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int4 t = __ldcs(x4 + 32 * m);
+      xv[4 * m] = t.x; xv[4 * m + 1] = t.y; xv[4 * m + 2] = t.z; xv[4 * m + 3] = t.w;
+    }
+    double l[16];
+    if (METHOD == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { l[i] = log_int(logt, xv[i] + 1); s += l[i]; }
+      const double mean = warp_sum(s) / (double)D;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) l[i] -= mean;
+    } else {
+      double S = 0.0;
+      int z = 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { S += (double)xv[i]; z += (xv[i] == 0); }
+      S = warp_sum(S);
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) z += __shfl_xor_sync(FULL, z, o2);
+      const double delta = (1.0 / (double)D) * (1.0 / (double)D);
+      const double scale = 1.0 - (double)z * delta;
+      double Q = 0.0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) Q += xv[i] == 0 ? delta : scale * ((double)xv[i] / S);
+      Q = warp_sum(Q);
+      const double lzero = log(delta / Q);
+      const double lscale = log(scale / S / Q);
+      double sl = 0.0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { l[i] = xv[i] == 0 ? lzero : (log_int(logt, xv[i]) + lscale); sl += l[i]; }
+      const double mean = warp_sum(sl) / (double)D;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) l[i] -= mean;
+    }
+    double2 *o2p = reinterpret_cast<double2 *>(out + r * D) + 2 * lane;
+    uint32_t *pl = reinterpret_cast<uint32_t *>(planes + (size_t)r * D) + lane;
+    const size_t plane_words = (size_t)n_out * (D / 4);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      __stcs(o2p + 64 * m, make_double2(l[4 * m], l[4 * m + 1]));
+      __stcs(o2p + 64 * m + 1, make_double2(l[4 * m + 2], l[4 * m + 3]));
+      uint32_t word[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * m + e;
+        csum[i] += l[i];
+        double v = (l[i] - cen[i * 32 + lane]) * scl[i * 32 + lane];
+        v = fmin(fmax(v, -lim), lim);
+        int a[6];
+        digits6(v, a);
+#pragma unroll
+        for (int s = 0; s < 6; ++s) word[s] |= (uint32_t)(a[s] & 255) << (8 * e);
+      }
+#pragma unroll
+      for (int s = 0; s < 6; ++s) __stcs(pl + (size_t)s * plane_words + 32 * m, word[s]);
+    }
+  }
+  // column sums: cross-warp reduction in a fixed order
+#pragma unroll
+  for (int i = 0; i < 16; ++i) red[warp * D + 128 * (i >> 2) + 4 * lane + (i & 3)] = csum[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) t += red[w * D + j];
+    psum[(int64_t)blockIdx.x * D + j] = t;
+  }
+}
+
 // ilr: l_j as in clr (before centring; centring cancels), then
 //   out_{i-1} = sqrt(i/(i+1)) * (mean(l[0:i]) - l[i]),  i = 1..Dk-1
 __global__ void __launch_bounds__(NWARPS * 32)
@@ -304,7 +424,10 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partials, cons
   const int j = blockIdx.x * 32 + threadIdx.x;
   double s = 0.0, m = 0.0;
   if (j < D)
-    for (int p = threadIdx.y; p < n_parts; p += 32) { s += partials[(int64_t)p * D + j]; m = fmax(m, pmax[(int64_t)p * D + j]); }
+    for (int p = threadIdx.y; p < n_parts; p += 32) {
+      s += partials[(int64_t)p * D + j];
+      if (pmax) m = fmax(m, pmax[(int64_t)p * D + j]);
+    }
   rs[threadIdx.y][threadIdx.x] = s;
   rm[threadIdx.y][threadIdx.x] = m;
   __syncthreads();
@@ -390,5 +513,33 @@ extern "C" int am_normalize(const int32_t *d_counts, int64_t n_rows_out, int D,
     reduce_partials_kernel<<<(D_keep + 31) / 32, dim3(32, 32), 0, st>>>(partials, pmax, grid, D_keep, d_colsum, d_colmaxabs);
     AM_LAUNCHED("reduce_partials_kernel");
   }
+  return AM_OK;
+}
+
+extern "C" int am_normalize_planes(const int32_t *d_counts, int64_t n_rows_out, int D,
+                                   const int64_t *d_row_index, int method, double *d_out,
+                                   double *d_colsum, const double *d_center, const double *d_sc, int S,
+                                   int8_t *d_planes, void *d_work, void *stream) {
+  if (D != 512 || S != 6) return am::fail(AM_EINVAL, "am_normalize_planes: only D = 512 (k = 5) and S = 6");
+  if (method != AM_NORM_AM_CLR && method != AM_NORM_CLR) return am::fail(AM_EINVAL, "am_normalize_planes: am_clr or clr");
+  if (n_rows_out == 0) return AM_OK;
+  if (!d_counts || !d_out || !d_colsum || !d_center || !d_sc || !d_planes || !d_work || n_rows_out < 0)
+    return am::fail(AM_EINVAL, "am_normalize_planes: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = norm_grid(n_rows_out);
+  double *partials = (double *)d_work;
+  const size_t smem = (size_t)(LOGT + 2 * 512 + NWARPS * 512) * sizeof(double);
+  if (method == AM_NORM_AM_CLR) {
+    AM_CUDA(cudaFuncSetAttribute(normalize512_planes_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    normalize512_planes_kernel<0><<<grid, NWARPS * 32, smem, st>>>(d_counts, n_rows_out, d_row_index, d_out, partials,
+                                                                   d_center, d_sc, d_planes);
+  } else {
+    AM_CUDA(cudaFuncSetAttribute(normalize512_planes_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    normalize512_planes_kernel<1><<<grid, NWARPS * 32, smem, st>>>(d_counts, n_rows_out, d_row_index, d_out, partials,
+                                                                   d_center, d_sc, d_planes);
+  }
+  AM_LAUNCHED("normalize512_planes_kernel");
+  reduce_partials_kernel<<<(512 + 31) / 32, dim3(32, 32), 0, st>>>(partials, nullptr, grid, 512, d_colsum, nullptr);
+  AM_LAUNCHED("reduce_partials_kernel");
   return AM_OK;
 }

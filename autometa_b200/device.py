@@ -193,6 +193,78 @@ def gram_centered_i8(X, mu, colmaxabs, out=None, slices: int = GRAM_SLICES):
     return out
 
 
+def plane_scales(center, colmaxabs=None, bound: float = -1.0, slices: int = GRAM_SLICES):
+    """Fixed-point scale of the digit planes: ``e[j]`` with ``2^e[j] > max|x_j| + |center_j|`` (per-column
+    ``colmaxabs`` or one scalar ``bound``) and ``sc[j] = 2^(8S-2-e[j])``."""
+    import torch
+
+    dev = center.device
+    D = center.numel()
+    with torch.cuda.device(dev):
+        e = torch.empty(D, dtype=torch.int32, device=dev)
+        sc = torch.empty(D, dtype=torch.float64, device=dev)
+        L.check(L.lib.am_plane_scales(L.t_ptr(center), L.t_ptr(colmaxabs), float(bound), D, slices, L.t_ptr(e),
+                                      L.t_ptr(sc), L.stream_ptr(dev)))
+    return e, sc
+
+
+def alloc_planes(n: int, D: int, dev, slices: int = GRAM_SLICES):
+    import torch
+
+    return torch.empty(max(256, L.lib.am_planes_bytes(n, D, slices)), dtype=torch.int8, device=dev)
+
+
+def normalize_planes(counts, method: str, row_index, center, sc, colsum, out=None, planes=None,
+                     slices: int = GRAM_SLICES):
+    """Fused kernel 2 + quantisation (D = 512): fp64 rows, column sums and the int8 digit planes of
+    ``round((x - center) * sc)`` in one pass."""
+    import torch
+
+    dev = counts.device
+    m = L.NORM_METHODS[method]
+    n_in, D = counts.shape
+    n_out = n_in if row_index is None else int(row_index.numel())
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((n_out, D), dtype=torch.float64, device=dev)
+        if planes is None:
+            planes = alloc_planes(n_out, D, dev, slices)
+        work = _work(dev, L.lib.am_normalize_work_bytes(D), "norm")
+        L.check(
+            L.lib.am_normalize_planes(L.t_ptr(counts), n_out, D, L.t_ptr(row_index), m, L.t_ptr(out),
+                                      L.t_ptr(colsum), L.t_ptr(center), L.t_ptr(sc), slices, L.t_ptr(planes),
+                                      L.t_ptr(work), L.stream_ptr(dev))
+        )
+    return out, planes
+
+
+def quantize_planes(X, center, sc, planes=None, slices: int = GRAM_SLICES):
+    import torch
+
+    dev = X.device
+    n, D = X.shape
+    with torch.cuda.device(dev):
+        if planes is None:
+            planes = alloc_planes(n, D, dev, slices)
+        L.check(L.lib.am_quantize_planes(L.t_ptr(X), n, D, L.t_ptr(center), L.t_ptr(sc), slices, L.t_ptr(planes),
+                                         L.stream_ptr(dev)))
+    return planes
+
+
+def gram_planes(planes, n: int, D: int, e, out=None, slices: int = GRAM_SLICES):
+    """G += sum_r (x_r - center)(x_r - center)^T from the digit planes (tcgen05 kind::i8)."""
+    import torch
+
+    dev = planes.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.zeros((D, D), dtype=torch.float64, device=dev)
+        work = _work(dev, L.lib.am_gram_planes_work_bytes(n, D, slices), "gram_planes")
+        L.check(L.lib.am_gram_planes(L.t_ptr(planes), n, D, slices, L.t_ptr(e), L.t_ptr(out), L.t_ptr(work),
+                                     L.stream_ptr(dev)))
+    return out
+
+
 def eigh_desc(A, max_sweeps: int = 30, tol: float = 0.0):
     """All eigenpairs of symmetric A, descending; rows of the returned matrix are
     eigenvectors with sklearn's svd_flip(u_based_decision=False) sign."""
@@ -251,6 +323,21 @@ def project(X, mu, comps, out=None):
         L.check(
             L.lib.am_project(L.t_ptr(X), n, D, L.t_ptr(mu), L.t_ptr(comps), P, L.t_ptr(out), L.stream_ptr(dev))
         )
+    return out
+
+
+def project_planes(planes, n: int, D: int, e, center, mu, comps, out=None, slices: int = GRAM_SLICES):
+    """scores = (X - mu) @ comps^T from the int8 digit planes (tcgen05 kind::i8); P <= 64."""
+    import torch
+
+    dev = planes.device
+    P = comps.shape[0]
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((n, P), dtype=torch.float64, device=dev)
+        work = _work(dev, L.lib.am_project_planes_work_bytes(D, slices), "project_planes")
+        L.check(L.lib.am_project_planes(L.t_ptr(planes), n, D, slices, L.t_ptr(e), L.t_ptr(center), L.t_ptr(mu),
+                                        L.t_ptr(comps), P, L.t_ptr(out), L.t_ptr(work), L.stream_ptr(dev)))
     return out
 
 

@@ -54,27 +54,59 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
         Dk = D if col_index is None else int(col_index.numel())
         Dout = Dk - 1 if method == "ilr" else Dk
         cs = torch.zeros(Dout, dtype=torch.float64, device=dev)
-        cm = torch.zeros(Dout, dtype=torch.float64, device=dev)  # column max|x|: fixed-point scale of the Gram
-        if method == "ilr" or Dout > 1024:
+        n_out = packed.n_contigs if row_index is None else int(row_index.numel())
+        fused = method in ("am_clr", "clr") and D == 512 and col_index is None and n_out > 0
+        if fused:
+            # provisional centre from a strided row sample (the exact mean needs the full pass);
+            # fixed-point range from the hard bound of the transform: |am_clr| <= log1p(longest
+            # contig), |clr| <= log(D^2) + 1
+            ns = min(n_out, 2048)
+            sample = torch.div(torch.arange(ns, device=dev, dtype=torch.int64) * n_out, ns, rounding_mode="floor")
+            if row_index is not None:
+                sample = row_index[sample]
+            cs_s = torch.zeros(D, dtype=torch.float64, device=dev)
+            _dev.normalize_counts(counts, method, sample, None, colsum=cs_s)
+            ns_t = torch.tensor([float(ns)], dtype=torch.float64, device=dev)
+            if distributed:
+                _dist.allreduce_sum_([cs_s, ns_t], group)
+            center = cs_s / ns_t
+            if method == "am_clr":
+                bound = float(np.log1p(float(packed.lengths.max()) if packed.n_contigs else 1.0))
+            else:
+                bound = float(2.0 * np.log(D) + 1.0)
+            e, sc = _dev.plane_scales(center, None, bound)
+            X, planes = _dev.normalize_planes(counts, method, row_index, center, sc, cs)
+        elif method == "ilr" or Dout > 1024:
             X = _dev.normalize_counts(counts, method, row_index, col_index)
+            cm = torch.zeros(Dout, dtype=torch.float64, device=dev)
             _dev.colstats(X, cs, cm)
         else:
+            cm = torch.zeros(Dout, dtype=torch.float64, device=dev)  # column max|x|: fixed-point scale
             X = _dev.normalize_counts(counts, method, row_index, col_index, colsum=cs, colmaxabs=cm)
         mark("normalise")
         n_t = torch.tensor([float(X.shape[0])], dtype=torch.float64, device=dev)
         if distributed:
             _dist.allreduce_sum_([cs, n_t], group)
         mu = cs / n_t
-        G = _dev.gram_centered_i8(X, mu, cm)
+        if fused:
+            G = _dev.gram_planes(planes, X.shape[0], D, e)
+        else:
+            G = _dev.gram_centered_i8(X, mu, cm)
         if distributed:
             _dist.allreduce_sum_([G], group)
+        if fused:
+            dlt = mu - center
+            G = G - n_t * torch.outer(dlt, dlt)
         C = G / (n_t - 1.0)
         mark("gram")
         P = min(n_components, Dout)
         evals, comps, total = _dev.eigh_topk(C, P)
         mark("eigh")
         evals = torch.clamp(evals, min=0.0)
-        scores = _dev.project(X, mu, comps)
+        if fused and P <= 64:
+            scores = _dev.project_planes(planes, X.shape[0], D, e, center, mu, comps)
+        else:
+            scores = _dev.project(X, mu, comps)
         mark("project")
         out = dict(
             scores=scores,

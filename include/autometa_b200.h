@@ -170,6 +170,16 @@ int am_normalize(const int32_t *d_counts, int64_t n_rows_out, int D,
                  int method, double *d_out, double *d_colsum, double *d_colmaxabs, void *d_work,
                  void *stream);
 
+/* Fused normalise + quantise for the k = 5 table (D = 512, S = 6, am_clr or clr): one pass writes
+ * the fp64 rows, adds the column sums and writes the int8 digit planes of
+ * round((out - centre_j) sc_j) (layout of am_quantize_planes) that am_gram_planes and
+ * am_project_planes consume.  d_center[512] is a provisional centre (e.g. the column means of a
+ * row sample normalised first); d_sc from am_plane_scales. */
+int am_normalize_planes(const int32_t *d_counts, int64_t n_rows_out, int D,
+                        const int64_t *d_row_index, int method, double *d_out, double *d_colsum,
+                        const double *d_center, const double *d_sc, int S, int8_t *d_planes,
+                        void *d_work, void *stream);
+
 /* ---------------------------------------------------------------------------
  * Kernel 3 — PCA (sklearn 1.9 PCA, svd_solver="covariance_eigh", the branch
  * kmers.py:605 takes for N >= 10*D; sklearn/decomposition/_pca.py:560,604-646).
@@ -201,6 +211,23 @@ int am_gram(const double *d_X, int64_t n_rows, int D, const double *d_mu,
  * (from am_colstats or the normalise kernel).  d_work: am_gram_i8_work_bytes(n_rows, D, S)
  * bytes (digit planes S*n_rows*D int8 + partial tiles). */
 int64_t am_gram_i8_work_bytes(int64_t n_rows, int D, int S);
+/* The same pipeline in pieces, so the digit planes can be produced elsewhere (fused into the
+ * normalise pass: am_normalize_planes) and shared with am_project_planes:
+ *   am_plane_scales   e[j] = exponent with 2^e[j] > max|x_j| + |centre_j| (max|x_j| = d_colmaxabs[j],
+ *                     or the scalar `bound` for every column when d_colmaxabs is NULL);
+ *                     sc[j] = 2^(8S-2-e[j])
+ *   am_quantize_planes planes[S][n_rows][pitch] int8, pitch = D rounded up to 16: balanced
+ *                     base-256 digits (most significant plane first) of round((x - centre_j) sc[j])
+ *   am_gram_planes    G[D x D] += sum_r (x_r - centre)(x_r - centre)^T from the planes.  The centre
+ *                     need not be the mean: the caller subtracts n (mu - centre)(mu - centre)^T. */
+int64_t am_planes_bytes(int64_t n_rows, int D, int S);
+int am_plane_scales(const double *d_center, const double *d_colmaxabs, double bound, int D, int S,
+                    int32_t *d_e, double *d_sc, void *stream);
+int am_quantize_planes(const double *d_X, int64_t n_rows, int D, const double *d_center,
+                       const double *d_sc, int S, int8_t *d_planes, void *stream);
+int64_t am_gram_planes_work_bytes(int64_t n_rows, int D, int S);
+int am_gram_planes(const int8_t *d_planes, int64_t n_rows, int D, int S, const int32_t *d_e,
+                   double *d_G, void *d_work, void *stream);
 int am_gram_i8(const double *d_X, int64_t n_rows, int D, const double *d_mu,
                const double *d_colmaxabs, int S, double *d_G, void *d_work, void *stream);
 int64_t am_eigh_work_bytes(int D);
@@ -215,6 +242,13 @@ int am_eigh(const double *d_A, int D, double *d_evals, double *d_evecs,
 int64_t am_eigh_topk_work_bytes(int D, int P);
 int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, double *d_evecs,
                  double *d_trace, void *d_work, void *stream);
+/* Tensor-core projection from the digit planes (tcgen05 kind::i8, K-major operands):
+ * scores[n_rows x P] = (X - mu) @ comps^T, where the planes hold round((x - centre_j) 2^(46-e_j))
+ * (am_normalize_planes / am_quantize_planes with S = 6) and mu is the exact mean.  P <= 64. */
+int64_t am_project_planes_work_bytes(int D, int S);
+int am_project_planes(const int8_t *d_planes, int64_t n_rows, int D, int S, const int32_t *d_e,
+                      const double *d_center, const double *d_mu, const double *d_comps, int P,
+                      double *d_scores, void *d_work, void *stream);
 int am_project(const double *d_X, int64_t n_rows, int D, const double *d_mu,
                const double *d_comps, int P, double *d_scores, void *stream);
 
