@@ -50,6 +50,25 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
   return s;
 }
 
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// 8-byte remote store that also counts 8 bytes on the receiver's mbarrier (data-carrying sync)
+__device__ __forceinline__ void st_async_f64(uint32_t raddr, double v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               ::"r"(raddr), "l"(__double_as_longlong(v)), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+
 struct TriOut {
   double *V;     // [n][np] reflectors (v_k in row k; zeros up to k, 1 at k+1)
   double *tau;   // [n]
@@ -70,7 +89,10 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
   double *gP = wb + 2 * np;                   // 2 x np  (all-gathered p slices)
   double *gA = gP + 2 * np;                   // 2 x np  (all-gathered next-column slices)
   double *red = gA + 2 * np;                  // 4 x TW
+  __shared__ __align__(8) unsigned long long s_mbar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t mbar0 = (uint32_t)__cvta_generic_to_shared(&s_mbar[0]);
+  const uint32_t gP_s = (uint32_t)__cvta_generic_to_shared(gP), gA_s = (uint32_t)__cvta_generic_to_shared(gA);
 
   // load own rows (symmetrised), zero the vectors
   for (int lr = 0; lr < RL; ++lr) {
@@ -82,8 +104,13 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
     }
   }
   for (int j = tid; j < 2 * np; j += TT) { vb[j] = 0.0; wb[j] = 0.0; gP[j] = 0.0; gA[j] = 0.0; }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  cluster.sync();  // every CTA's buffers exist and are zeroed before any remote store
+  cluster.sync();  // every CTA's buffers and mbarriers exist before any remote store
 
   // prologue: all-gather column 0 into gA[1]
   for (int lr = warp; lr < RL; lr += TW) {
@@ -143,6 +170,10 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
         if (tid == 0) { out.e[k] = beta; out.tau[k] = tau; }
       }
     }
+    // arm this step's inbox: rows k+1..n-1 each deliver p and their entry of the next column
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                   ::"r"(mbar0 + 8u * (k & 1)), "r"((uint32_t)(n - k - 1) * 16u) : "memory");
     __syncthreads();
     AM_TICK(tA);
     // ---- B. fused pass over own rows >= k: apply pending update (k-1), p = tau * A v_k
@@ -175,6 +206,7 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
         }
         __syncwarp();
         const int buf = k & 1;
+        const uint32_t rbar = mapa_u32(mbar0 + 8u * buf, (uint32_t)(lane & (TC - 1)));
 #pragma unroll
         for (int r = 0; r < MAXRPW; ++r) {
           if (lrs[r] >= 0) {
@@ -182,15 +214,16 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
             const double p = tau * warp_sum(acc[r]);
             const double a1 = rows[(size_t)lrs[r] * np + (k + 1)];  // post-update A[i][k+1]
             if (i >= k + 1) {
-              if (lane < TC) *cluster.map_shared_rank(gP + buf * np + i, lane) = p;
-              else *cluster.map_shared_rank(gA + buf * np + i, lane - TC) = a1;
+              // data-carrying all-gather: the store itself signals the receiver's mbarrier
+              if (lane < TC) st_async_f64(mapa_u32(gP_s + (uint32_t)(buf * np + i) * 8u, lane), p, rbar);
+              else st_async_f64(mapa_u32(gA_s + (uint32_t)(buf * np + i) * 8u, lane - TC), a1, rbar);
             }
           }
         }
       }
     }
     AM_TICK(tB);
-    cluster.sync();
+    mbar_wait_cluster(mbar0 + 8u * (k & 1), (uint32_t)((k >> 1) & 1));  // all slices of step k have landed
     AM_TICK(tS);
 
     // ---- C. w_k and the next column x_{k+1} (replicated; two one-barrier reductions)
