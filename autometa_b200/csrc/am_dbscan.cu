@@ -91,10 +91,23 @@ __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
   }
 }
 
+// per bucket: do all its points already belong to ONE component?  (roots at the start of the step:
+// the forest is flattened after every step, so root(i) = parent[i])
+__global__ void bucket_roots_kernel(int n, const unsigned *__restrict__ bucket_of, const int *__restrict__ parent,
+                                    int *__restrict__ rmin_inv, int *__restrict__ rmax) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = parent[i];
+  const unsigned b = bucket_of[i];
+  atomicMax(rmin_inv + b, 0x7fffffff - r);
+  atomicMax(rmax + b, r);
+}
+
 // one thread per point (in bucket-sorted order)
 __global__ void __launch_bounds__(128)
 eps_union_kernel(int n, GridParams gp, double eps2, const unsigned *__restrict__ bucket_start,
                  const int *__restrict__ sorted_idx, const double *__restrict__ sorted_x,
+                 const int *__restrict__ rmin_inv, const int *__restrict__ rmax,
                  int *__restrict__ parent) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= n) return;
@@ -104,6 +117,10 @@ eps_union_kernel(int n, GridParams gp, double eps2, const unsigned *__restrict__
   for (int d = 0; d < F; ++d) x[d] = sorted_x[(int64_t)d * n + pos];
   cell_of(x, gp, c);
   const int me = sorted_idx[pos];
+  // root at the start of the step (other threads only ever hook roots under smaller roots, so a
+  // bucket that was uniformly in my component then is still entirely connected to me)
+  // (a late read may return a smaller ancestor instead: still a vertex I am connected to)
+  const int myroot0 = *((volatile int *)(parent + me));
   int ncomb = 1;
   for (int d = 0; d < F; ++d) ncomb *= 3;
   unsigned seen[81];  // buckets already scanned by this thread (3^4 max)
@@ -120,6 +137,7 @@ eps_union_kernel(int n, GridParams gp, double eps2, const unsigned *__restrict__
     for (int s = 0; s < nseen; ++s) dup |= (seen[s] == b);
     if (dup) continue;
     seen[nseen++] = b;
+    if (__ldg(rmax + b) == myroot0 && 0x7fffffff - __ldg(rmin_inv + b) == myroot0) continue;  // nothing to merge
     const unsigned beg = bucket_start[b], end = bucket_start[b + 1];
     for (unsigned j = beg; j < end; ++j) {
       const int other = sorted_idx[j];
@@ -196,6 +214,9 @@ struct Work {
   unsigned *is_root;       // n
   unsigned *root_rank;     // n + 1
   int *root_of_label;      // n
+  int *rmin_inv;           // nb
+  int *rmax;               // nb
+  unsigned *scan_tmp;      // scan_tmp_words(max(n, nb))
 };
 
 inline int64_t align_up(int64_t x) { return (x + 255) & ~(int64_t)255; }
@@ -219,6 +240,9 @@ int64_t carve(void *base, int64_t n, Work *w) {
   t.is_root = (unsigned *)take(n * 4);
   t.root_rank = (unsigned *)take((n + 1) * 4);
   t.root_of_label = (int *)take(n * 4);
+  t.rmin_inv = (int *)take((int64_t)nb * 4);
+  t.rmax = (int *)take((int64_t)nb * 4);
+  t.scan_tmp = (unsigned *)take(am::scan_tmp_words(std::max<int64_t>(n + 1, nb + 1)) * 4);
   if (w) *w = t;
   return off;
 }
@@ -269,13 +293,17 @@ extern "C" int am_eps_union(const double *d_X, int64_t n_points, int F, double e
   const int blocks = (n + 255) / 256;
   bucket_count_kernel<<<blocks, 256, 0, st>>>(d_X, n, gp, w.bucket_of, w.counts);
   AM_LAUNCHED("bucket_count_kernel");
-  am::exclusive_scan_kernel<<<1, 1024, 0, st>>>(w.counts, w.bucket_start, (int)nb);
-  AM_LAUNCHED("exclusive_scan_kernel");
+  am::g_launches.fetch_add(am::exclusive_scan(w.counts, w.bucket_start, (int)nb, w.scan_tmp, st) - 1);
+  AM_LAUNCHED("exclusive_scan");
   bucket_scatter_kernel<<<blocks, 256, 0, st>>>(d_X, n, F, w.bucket_of, w.bucket_start, w.fill,
                                                 w.sorted_idx, w.sorted_x);
   AM_LAUNCHED("bucket_scatter_kernel");
+  AM_CUDA(cudaMemsetAsync(w.rmin_inv, 0, (size_t)nb * 4, st));
+  AM_CUDA(cudaMemsetAsync(w.rmax, 0xFF, (size_t)nb * 4, st));
+  bucket_roots_kernel<<<blocks, 256, 0, st>>>(n, w.bucket_of, d_parent, w.rmin_inv, w.rmax);
+  AM_LAUNCHED("bucket_roots_kernel");
   eps_union_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, gp, eps * eps, w.bucket_start, w.sorted_idx,
-                                                    w.sorted_x, d_parent);
+                                                    w.sorted_x, w.rmin_inv, w.rmax, d_parent);
   AM_LAUNCHED("eps_union_kernel");
   return AM_OK;
 }
@@ -293,8 +321,8 @@ extern "C" int am_labels_from_parent(int32_t *d_parent, int64_t n_points, int64_
   const int blocks = (n + 255) / 256;
   compress_kernel<<<blocks, 256, 0, st>>>(d_parent, n, w.is_root);
   AM_LAUNCHED("compress_kernel");
-  am::exclusive_scan_kernel<<<1, 1024, 0, st>>>(w.is_root, w.root_rank, n);
-  AM_LAUNCHED("exclusive_scan_kernel");
+  am::g_launches.fetch_add(am::exclusive_scan(w.is_root, w.root_rank, n, w.scan_tmp, st) - 1);
+  AM_LAUNCHED("exclusive_scan");
   relabel_kernel<<<blocks, 256, 0, st>>>(d_parent, n, w.root_rank, d_labels, d_n_clusters);
   AM_LAUNCHED("relabel_kernel");
   // flatten the forest (parent[i] = root) so the next, larger eps starts from depth-1 trees

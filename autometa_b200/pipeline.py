@@ -18,14 +18,95 @@ from . import dist as _dist
 from .assembly import HostAssembly, PackedAssembly, pack_device_arrays, pack_plan
 
 
+def _sample_rows(n_out: int, dev, cache: dict):
+    """Strided row sample (<= 2048 rows) for the provisional centre; cached per (n_out, device)."""
+    import torch
+
+    key = ("sample", n_out, dev.index)
+    t = cache.get(key)
+    if t is None:
+        ns = min(n_out, 2048)
+        t = torch.div(torch.arange(ns, device=dev, dtype=torch.int64) * n_out, ns, rounding_mode="floor")
+        cache[key] = t
+    return t
+
+
+def _fit_project(packed, counts, method, n_components, row_index, col_index, group, distributed, mark):
+    """normalise -> PCA fit -> scores for the given row/column selection (device only, no host sync)."""
+    import torch
+
+    dev = counts.device
+    D = counts.shape[1]
+    Dk = D if col_index is None else int(col_index.numel())
+    Dout = Dk - 1 if method == "ilr" else Dk
+    n_out = counts.shape[0] if row_index is None else int(row_index.numel())
+    cs = torch.zeros(Dout, dtype=torch.float64, device=dev)
+    fused = method in ("am_clr", "clr") and D == 512 and col_index is None and n_out > 0
+    planes = e = center = None
+    if fused:
+        # provisional centre from a strided row sample (the exact mean needs the full pass);
+        # fixed-point range from the hard bound of the transform: |am_clr| <= log1p(longest
+        # contig), |clr| <= log(D^2) + 1
+        sample = _sample_rows(n_out, dev, packed._plans)
+        ns = int(sample.numel())
+        if row_index is not None:
+            sample = row_index[sample]
+        cs_s = torch.zeros(D + 1, dtype=torch.float64, device=dev)
+        cs_s[D] = float(ns)
+        _dev.normalize_counts(counts, method, sample, None, colsum=cs_s[:D])
+        if distributed:
+            _dist.allreduce_sum_([cs_s], group)
+        center = cs_s[:D] / cs_s[D]
+        if method == "am_clr":
+            bound = float(np.log1p(float(packed.lengths.max()) if packed.n_contigs else 1.0))
+        else:
+            bound = float(2.0 * np.log(D) + 1.0)
+        e, sc = _dev.plane_scales(center, None, bound)
+        X, planes = _dev.normalize_planes(counts, method, row_index, center, sc, cs)
+    elif method == "ilr" or Dout > 1024:
+        X = _dev.normalize_counts(counts, method, row_index, col_index)
+        cm = torch.zeros(Dout, dtype=torch.float64, device=dev)
+        _dev.colstats(X, cs, cm)
+    else:
+        cm = torch.zeros(Dout, dtype=torch.float64, device=dev)  # column max|x|: fixed-point scale
+        X = _dev.normalize_counts(counts, method, row_index, col_index, colsum=cs, colmaxabs=cm)
+    mark("normalise")
+    n_t = torch.tensor([float(X.shape[0])], dtype=torch.float64, device=dev)
+    if distributed:
+        _dist.allreduce_sum_([cs, n_t], group)
+    mu = cs / n_t
+    if fused:
+        G = _dev.gram_planes(planes, X.shape[0], D, e)
+    else:
+        G = _dev.gram_centered_i8(X, mu, cm)
+    if distributed:
+        _dist.allreduce_sum_([G], group)
+    if fused:
+        dlt = mu - center
+        G = G - n_t * torch.outer(dlt, dlt)
+    C = G / (n_t - 1.0)
+    mark("gram")
+    P = min(n_components, Dout)
+    evals, comps, total = _dev.eigh_topk(C, P)
+    mark("eigh")
+    evals = torch.clamp(evals, min=0.0)
+    if fused and P <= 64:
+        scores = _dev.project_planes(planes, X.shape[0], D, e, center, mu, comps)
+    else:
+        scores = _dev.project(X, mu, comps)
+    mark("project")
+    return dict(scores=scores, explained_variance=evals, explained_variance_ratio=evals / total,
+                components=comps, mean=mu, row_index=row_index, col_index=col_index, normalized=X)
+
+
 def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_components: int = 50,
               group=None, distributed: bool = False, keep: bool = True, marks=None) -> Dict[str, Any]:
     """counts, normalised matrix and PCA scores of this rank's contig shard.
 
-    am_clr's global column drop (kmers.py:369) is handled optimistically: the
-    normalise kernel runs assuming every column is present somewhere and every
-    contig has counts; the flags are read back once at the end together with the
-    results and the rare other case re-runs with explicit gathers.
+    am_clr's global column drop and all-NA row drop (kmers.py:369) are handled optimistically:
+    the whole pass runs on the stream assuming every column occurs somewhere and every contig has
+    counts (true for any real assembly at k = 5); the two flags are read back ONCE, after the last
+    kernel has been queued, and the rare other case re-runs with explicit row/column gathers.
     """
     import torch
 
@@ -35,88 +116,27 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
         mark("start")
         counts, present, row_sum = _dev.count_packed(packed, k)
         mark("count")
-        D = counts.shape[1]
         if distributed:
             _dist.allreduce_max_(present, group)
-        row_index = col_index = None
-        rows_ok = True
-        if method == "am_clr":
-            flags = torch.stack([present.min(), (row_sum.min() > 0).to(torch.int32) if packed.n_contigs else present.min()])
-            flags_h = flags.cpu().numpy()  # one small D2H; also orders the stream for the host decision
-            if flags_h[0] == 0:
-                col_index = torch.nonzero(present > 0).flatten().to(torch.int32)
-            if flags_h[1] == 0:
-                rows_ok = False
-                row_index = torch.nonzero(row_sum > 0).flatten()
+        if packed.n_contigs:
+            flags = torch.stack([present.min(), row_sum.min()])
         else:
-            if packed.n_contigs and int((row_sum.min()).item()) == 0:
+            flags = torch.ones(2, dtype=torch.int32, device=dev)
+        res = None
+        if packed.n_contigs:
+            res = _fit_project(packed, counts, method, n_components, None, None, group, distributed, mark)
+        flags_h = flags.cpu().numpy()  # the only host sync: after everything has been queued
+        cols_ok, rows_ok = bool(flags_h[0] > 0), bool(flags_h[1] > 0)
+        if method != "am_clr":
+            if packed.n_contigs and not rows_ok:
                 raise ValueError("Input matrix cannot have rows with all zeros")
-        Dk = D if col_index is None else int(col_index.numel())
-        Dout = Dk - 1 if method == "ilr" else Dk
-        cs = torch.zeros(Dout, dtype=torch.float64, device=dev)
-        n_out = packed.n_contigs if row_index is None else int(row_index.numel())
-        fused = method in ("am_clr", "clr") and D == 512 and col_index is None and n_out > 0
-        if fused:
-            # provisional centre from a strided row sample (the exact mean needs the full pass);
-            # fixed-point range from the hard bound of the transform: |am_clr| <= log1p(longest
-            # contig), |clr| <= log(D^2) + 1
-            ns = min(n_out, 2048)
-            sample = torch.div(torch.arange(ns, device=dev, dtype=torch.int64) * n_out, ns, rounding_mode="floor")
-            if row_index is not None:
-                sample = row_index[sample]
-            cs_s = torch.zeros(D, dtype=torch.float64, device=dev)
-            _dev.normalize_counts(counts, method, sample, None, colsum=cs_s)
-            ns_t = torch.tensor([float(ns)], dtype=torch.float64, device=dev)
-            if distributed:
-                _dist.allreduce_sum_([cs_s, ns_t], group)
-            center = cs_s / ns_t
-            if method == "am_clr":
-                bound = float(np.log1p(float(packed.lengths.max()) if packed.n_contigs else 1.0))
-            else:
-                bound = float(2.0 * np.log(D) + 1.0)
-            e, sc = _dev.plane_scales(center, None, bound)
-            X, planes = _dev.normalize_planes(counts, method, row_index, center, sc, cs)
-        elif method == "ilr" or Dout > 1024:
-            X = _dev.normalize_counts(counts, method, row_index, col_index)
-            cm = torch.zeros(Dout, dtype=torch.float64, device=dev)
-            _dev.colstats(X, cs, cm)
-        else:
-            cm = torch.zeros(Dout, dtype=torch.float64, device=dev)  # column max|x|: fixed-point scale
-            X = _dev.normalize_counts(counts, method, row_index, col_index, colsum=cs, colmaxabs=cm)
-        mark("normalise")
-        n_t = torch.tensor([float(X.shape[0])], dtype=torch.float64, device=dev)
-        if distributed:
-            _dist.allreduce_sum_([cs, n_t], group)
-        mu = cs / n_t
-        if fused:
-            G = _dev.gram_planes(planes, X.shape[0], D, e)
-        else:
-            G = _dev.gram_centered_i8(X, mu, cm)
-        if distributed:
-            _dist.allreduce_sum_([G], group)
-        if fused:
-            dlt = mu - center
-            G = G - n_t * torch.outer(dlt, dlt)
-        C = G / (n_t - 1.0)
-        mark("gram")
-        P = min(n_components, Dout)
-        evals, comps, total = _dev.eigh_topk(C, P)
-        mark("eigh")
-        evals = torch.clamp(evals, min=0.0)
-        if fused and P <= 64:
-            scores = _dev.project_planes(planes, X.shape[0], D, e, center, mu, comps)
-        else:
-            scores = _dev.project(X, mu, comps)
-        mark("project")
-        out = dict(
-            scores=scores,
-            explained_variance=evals,
-            explained_variance_ratio=evals / total,
-            components=comps,
-            mean=mu,
-            row_index=row_index,
-            col_index=col_index,
-        )
+        elif res is None or not (cols_ok and rows_ok):
+            col_index = None if cols_ok else torch.nonzero(present > 0).flatten().to(torch.int32)
+            row_index = None if rows_ok else torch.nonzero(row_sum > 0).flatten()
+            res = _fit_project(packed, counts, method, n_components, row_index, col_index, group, distributed,
+                               lambda name: None)
+        out = res
+        X = out.pop("normalized")
         if keep:
             out.update(counts=counts, normalized=X, col_present=present, row_sum=row_sum)
         return out
