@@ -81,6 +81,9 @@ _SIGS = {
     "am_eps_union": (C.c_int, [_p, _i64, _i32, _f64, _p, _p, _p, _p, _p]),
     "am_labels_from_parent": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
     "am_iota_i32": (C.c_int, [_p, _i64, _p]),
+    "am_metrics_work_bytes": (_i64, [_i64, _i32]),
+    "am_cluster_metrics": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _i32, _p, _p, _f64, _f64, _f64, _f64,
+                                     _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -107,22 +107,37 @@ def recursive_dbscan(
     gc = table["gc_content"].to_numpy(dtype=np.float64)
     rows, cols, vals = markers_coo(markers_df, table.index)
     n_ref = markers_df.shape[1]
+    dev = sweep.dev
+    metrics = _dev.ClusterMetrics(
+        n_samples, rows, cols, vals, n_ref, coverage, gc,
+        (completeness_cutoff, purity_cutoff, coverage_stddev_cutoff, gc_content_stddev_cutoff), dev,
+    )
 
+    # The loop keeps labels and metrics on the device; per eps only the 3-number summary
+    # (cluster count, median completeness of passing clusters, number passing) comes back,
+    # because the eps schedule and the best-eps rule are host control flow (:189-215).
     eps, step = 0.3, 0.1
     clustering_rounds = {0: 0}
     n_clusters = float("inf")
     best_median = float("-inf")
-    best = None  # (labels, metrics)
+    best = None  # (labels, metrics) on the host, fetched when an eps becomes the best so far
+    import torch
+
+    best_labels_d = torch.empty(n_samples, dtype=torch.int64, device=dev)
+    best_keep = None
     while n_clusters > 1:
         labels_d = sweep.step(eps)
-        labels = labels_d.cpu().numpy()
-        n_clusters = int(sweep.n_clusters.item())
-        m = cluster_metrics_arrays(labels, n_clusters, rows, cols, vals, n_ref, coverage, gc)
-        ok = passing_mask(m, completeness_cutoff, purity_cutoff, coverage_stddev_cutoff, gc_content_stddev_cutoff)
-        median_completeness = float(np.median(m["completeness"][ok])) if ok.any() else float("-inf")
+        summ = metrics.compute(labels_d, sweep.n_clusters).cpu().numpy()  # the only sync per eps
+        n_clusters = int(summ[0])
+        median_completeness = float(summ[1])
         if median_completeness >= best_median:
             best_median = median_completeness
-            best = (labels, m)
+            best_labels_d.copy_(labels_d)
+            best_keep = {k2: v.clone() for k2, v in dict(
+                completeness=metrics.completeness[:n_clusters], purity=metrics.purity[:n_clusters],
+                coverage_stddev=metrics.cov_std[:n_clusters], gc_content_stddev=metrics.gc_std[:n_clusters],
+                present_marker_count=metrics.present[:n_clusters], single_copy_marker_count=metrics.single[:n_clusters],
+            ).items()}
         clustering_rounds[n_clusters] = clustering_rounds.get(n_clusters, 0) + 1
         if clustering_rounds[n_clusters] > 10:
             step *= 10
@@ -136,6 +151,10 @@ def recursive_dbscan(
                 f" Completeness: Median={median_completeness:4.2f} Best={best_median:4.2f}"
             )
         eps += step
+    m = {k2: v.cpu().numpy() for k2, v in best_keep.items()}
+    for k2 in ("present_marker_count", "single_copy_marker_count"):
+        m[k2] = m[k2].astype(np.int64)
+    best = (best_labels_d.cpu().numpy(), m)
     labels, m = best
     best_df = table.copy()
     best_df["cluster"] = labels

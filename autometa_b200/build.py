@@ -24,6 +24,7 @@ SOURCES = [
     "am_eigh.cu",
     "am_eigtop.cu",
     "am_dbscan.cu",
+    "am_metrics.cu",
 ]
 NVCC_FLAGS = [
     "-gencode",

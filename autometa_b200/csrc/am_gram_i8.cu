@@ -22,6 +22,8 @@
 //      (deterministic), scaled by 2^(e_i+e_j-12) and mirrored into the symmetric G.
 // With S = 6 the quantisation step is 2^-46 of the column range; the integer arithmetic adds no
 // rounding at all, so G is at least as accurate as an fp64 BLAS Gram.
+#include <stdlib.h>
+
 #include "am_common.cuh"
 #include "am_tc.cuh"
 
@@ -52,6 +54,8 @@ struct GramI8Params {
   // -> accumulators od[i] .. od[i] + on[i] - 1 (adjacent TMEM columns); ofirst[i]: bit j set when
   // accumulator od[i] + j is written for the first time in the K step (overwrite on the first K step)
   uint8_t os[16], ot[16], on[16], od[16], ofirst[16];
+  int dbg_mode;       // AM_GRAM_DBG: 0 normal; 1 = no MMA issue (TMA pipeline only); 2 = no TMA (MMAs on
+                      // stale smem, garbage result) — the two halves of the pipeline timed in isolation
 };
 
 __device__ __forceinline__ void decode_tile(int tile, int TJ, int &I, int &Jb) {
@@ -106,6 +110,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int r = row0; r < row1; r += GI_K) {
           mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
           const uint32_t fb = bar_full + 8u * stage;
+          if (p.dbg_mode == 2) { mbar_arrive(fb); if (++stage == NS) { stage = 0; phase ^= 1u; } continue; }
           mbar_expect_tx(fb, stage_bytes);
           const uint32_t sa = base + (uint32_t)stage * stage_bytes;
           const uint32_t sb = sa + (uint32_t)S * GI_A_BYTES;
@@ -137,7 +142,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)stage * stage_bytes;
           const uint32_t sb = sa + (uint32_t)S * GI_A_BYTES;
-          for (int i = 0; i < p.n_ops; ++i) {
+          for (int i = 0; i < (p.dbg_mode == 1 ? 0 : p.n_ops); ++i) {
             // A: 128 cols x 32 rows, 128B swizzle (atom = 128 B x 8 rows -> SBO 1024)
             const uint64_t da = make_desc(sa + (uint32_t)p.os[i] * GI_A_BYTES, GI_K * 128, 1024, 2);
             // B: on[i] planes side by side = on[i] atoms of 64 cols x 32 rows along N, 64B swizzle
@@ -317,6 +322,8 @@ void gram_i8_shape(int64_t n_rows, int D, int S, GramI8Params *p) {
   if (dmax == S) add_op(S / 2, S / 2, 1);  // the square term of weight S
   p->n_ops = nops;
   p->n_acc = dmax + 1;
+  const char *dm = getenv("AM_GRAM_DBG");
+  p->dbg_mode = dm ? atoi(dm) : 0;
 }
 
 inline int plane_pitch(int D) { return (D + 15) & ~15; }

@@ -391,3 +391,64 @@ class EpsSweep:
                                             L.t_ptr(self.n_clusters), L.t_ptr(self.work), st)
             )
         return self.labels[: self.n]
+
+
+class ClusterMetrics:
+    """Device-side add_metrics + apply_binning_metrics_filter + median completeness for the sweep
+    (reference binning/utilities.py:125-262, recursive_dbscan.py:180-192)."""
+
+    def __init__(self, n_points: int, marker_rows, marker_cols, marker_vals, n_ref_markers: int, coverage, gc,
+                 cutoffs, device):
+        import torch
+
+        self.dev = device
+        self.n = int(n_points)
+        self.M = int(n_ref_markers)
+        self.cutoffs = tuple(float(c) for c in cutoffs)
+        with torch.cuda.device(device):
+            t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device)
+            self.nnz = int(len(marker_rows))
+            self.rows = t(marker_rows if self.nnz else np.zeros(1), np.int32)
+            self.cols = t(marker_cols if self.nnz else np.zeros(1), np.int32)
+            self.vals = t(marker_vals if self.nnz else np.zeros(1), np.int32)
+            self.cov = t(coverage, np.float64)
+            self.gc = t(gc, np.float64)
+            n1 = max(self.n, 1)
+            self.completeness = torch.empty(n1, dtype=torch.float64, device=device)
+            self.purity = torch.empty(n1, dtype=torch.float64, device=device)
+            self.cov_std = torch.empty(n1, dtype=torch.float64, device=device)
+            self.gc_std = torch.empty(n1, dtype=torch.float64, device=device)
+            self.present = torch.empty(n1, dtype=torch.int32, device=device)
+            self.single = torch.empty(n1, dtype=torch.int32, device=device)
+            self.summary = torch.zeros(4, dtype=torch.float64, device=device)
+            self.work = torch.zeros(max(256, L.lib.am_metrics_work_bytes(self.n, self.M)), dtype=torch.uint8,
+                                    device=device)
+
+    def compute(self, labels, n_clusters):
+        """Queue the metrics of one eps; returns the device summary [n_clusters, median, n_pass]."""
+        import torch
+
+        c = self.cutoffs
+        with torch.cuda.device(self.dev):
+            L.check(
+                L.lib.am_cluster_metrics(
+                    L.t_ptr(labels), self.n, L.t_ptr(n_clusters), L.t_ptr(self.rows), L.t_ptr(self.cols),
+                    L.t_ptr(self.vals), self.nnz, self.M, L.t_ptr(self.cov), L.t_ptr(self.gc), c[0], c[1], c[2], c[3],
+                    L.t_ptr(self.completeness), L.t_ptr(self.purity), L.t_ptr(self.cov_std), L.t_ptr(self.gc_std),
+                    L.t_ptr(self.present), L.t_ptr(self.single), L.t_ptr(self.summary), L.t_ptr(self.work),
+                    L.stream_ptr(self.dev),
+                )
+            )
+        return self.summary
+
+    def arrays(self, n_clusters: int):
+        """Host copies of the per-cluster metrics of the LAST compute() call."""
+        k = int(n_clusters)
+        return dict(
+            completeness=self.completeness[:k].cpu().numpy(),
+            purity=self.purity[:k].cpu().numpy(),
+            coverage_stddev=self.cov_std[:k].cpu().numpy(),
+            gc_content_stddev=self.gc_std[:k].cpu().numpy(),
+            present_marker_count=self.present[:k].cpu().numpy().astype(np.int64),
+            single_copy_marker_count=self.single[:k].cpu().numpy().astype(np.int64),
+        )

@@ -225,6 +225,24 @@ def sweep_bench(dev, torch, cpu=True, reps=3):
         "achieved_GBps_algorithmic": (8 * 3 * n + 8 * n) * len(grid) / t / 1e9,
         "note": "latency/ALU-bound (6.4 MB per eps is HBM-trivial); incremental union-find forest across eps",
     }
+    # the same sweep through the reference-facing API (recursive_dbscan.py:114-234 semantics: eps
+    # schedule until one cluster remains, per-eps metrics + cutoff filter + best-eps rule), host
+    # DataFrames in, (clustered_df, unclustered_df) out, metrics on the device
+    try:
+        from autometa_b200.binning import recursive_dbscan as R
+
+        _, markers = synth.make_sweep_input()
+        tb = table.copy()
+        R.recursive_dbscan(tb, markers, 20.0, 95.0, 25.0, 5.0)  # warm-up
+        tb = table.copy()
+        t0 = time.perf_counter()
+        cl, un = R.recursive_dbscan(tb, markers, 20.0, 95.0, 25.0, 5.0)
+        out["api"] = {"value": time.perf_counter() - t0, "unit": "s",
+                      "call": "recursive_dbscan(table, markers_df, 20, 95, 25, 5) incl. DataFrame in/out, all eps "
+                              "until one cluster remains, device-side add_metrics/filter/median",
+                      "clustered": int(cl.shape[0]), "unclustered": int(un.shape[0])}
+    except Exception as exc:  # keep the bench line even if the API leg fails
+        out["api"] = {"error": repr(exc)}
     if cpu:
         # reference arm of the same metric: what recursive_dbscan.py:109 executes, on the host cores,
         # at 4 of the 48 eps values (bounded sample), scaled to the grid

@@ -274,6 +274,26 @@ int am_labels_from_parent(int32_t *d_parent, int64_t n_points, int64_t *d_labels
                           int32_t *d_n_clusters, void *d_work, void *stream);
 int am_iota_i32(int32_t *d_v, int64_t n, void *stream);
 
+/* ---------------------------------------------------------------------------
+ * Per-eps cluster metrics, cutoff filter and median completeness of the passing clusters —
+ * replaces add_metrics / apply_binning_metrics_filter (autometa/binning/utilities.py:125-262)
+ * as used inside the sweep (recursive_dbscan.py:180-192).
+ *   d_labels[n_points] int64 (0-based, from am_labels_from_parent), d_n_clusters int32[1];
+ *   contig x marker counts in COO form (rows index points), n_markers = reference marker count M;
+ *   outputs per cluster c < n_clusters: completeness, purity (NaN when nothing present),
+ *   coverage / GC sigma (ddof 1, NaN for singletons), present / single-copy marker counts;
+ *   d_summary[3] = {n_clusters, median completeness of passing clusters (-inf if none), n passing}.
+ * d_work: am_metrics_work_bytes(n_points, M) bytes, zero-filled once by the caller. */
+int64_t am_metrics_work_bytes(int64_t n_points, int n_markers);
+int am_cluster_metrics(const int64_t *d_labels, int64_t n_points, const int32_t *d_n_clusters,
+                       const int32_t *d_marker_rows, const int32_t *d_marker_cols,
+                       const int32_t *d_marker_vals, int64_t nnz, int n_markers,
+                       const double *d_coverage, const double *d_gc, double completeness_cutoff,
+                       double purity_cutoff, double coverage_stddev_cutoff,
+                       double gc_content_stddev_cutoff, double *d_completeness, double *d_purity,
+                       double *d_cov_std, double *d_gc_std, int32_t *d_present, int32_t *d_single,
+                       double *d_summary, void *d_work, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

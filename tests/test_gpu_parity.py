@@ -393,3 +393,37 @@ def test_sweep_full_size_c4(torch_cuda):
         if i in check:
             ref = DBSCAN(eps=eps, min_samples=1, n_jobs=-1).fit(X).labels_
             assert np.array_equal(lab.cpu().numpy(), ref.astype(np.int64)), eps
+
+
+def test_device_cluster_metrics_match_host_mirror(torch_cuda):
+    """am_cluster_metrics (device add_metrics + filter + median) vs the numpy mirror of
+    binning/utilities.py:125-262 at several eps of a synthetic sweep."""
+    import torch
+
+    from autometa_b200 import device as D, synth
+    from autometa_b200.binning.utilities import cluster_metrics_arrays, markers_coo, passing_mask
+
+    table, markers = synth.make_sweep_input(n_points=20000, n_clusters=40, n_markers=60, seed=9)
+    X = np.ascontiguousarray(table[["x_1", "x_2", "coverage"]].to_numpy())
+    cov = table["coverage"].to_numpy(dtype=np.float64)
+    gc = table["gc_content"].to_numpy(dtype=np.float64)
+    rows, cols, vals = markers_coo(markers, table.index)
+    cut = (20.0, 90.0, 25.0, 5.0)
+    sweep = D.EpsSweep(torch.from_numpy(X).cuda())
+    met = D.ClusterMetrics(len(table), rows, cols, vals, markers.shape[1], cov, gc, cut, sweep.dev)
+    for eps in (0.3, 0.8999999999999999, 2.0, 3.5000000000000004, 6.0, 30.0):
+        lab_d = sweep.step(eps)
+        summ = met.compute(lab_d, sweep.n_clusters).cpu().numpy()
+        lab = lab_d.cpu().numpy()
+        k = int(sweep.n_clusters.item())
+        ref = cluster_metrics_arrays(lab, k, rows, cols, vals, markers.shape[1], cov, gc)
+        got = met.arrays(k)
+        assert int(summ[0]) == k
+        assert np.array_equal(got["present_marker_count"], ref["present_marker_count"])
+        assert np.array_equal(got["single_copy_marker_count"], ref["single_copy_marker_count"])
+        for name in ("completeness", "purity", "coverage_stddev", "gc_content_stddev"):
+            np.testing.assert_allclose(got[name], ref[name], rtol=1e-11, atol=1e-11, equal_nan=True)
+        ok = passing_mask(ref, *cut)
+        med = float(np.median(ref["completeness"][ok])) if ok.any() else float("-inf")
+        assert summ[1] == med or (np.isinf(med) and np.isinf(summ[1])), (eps, summ[1], med)
+        assert int(summ[2]) == int(ok.sum())
