@@ -1,0 +1,13 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from autometa_b200 import assembly, device as D, synth
+asm = synth.make_assembly(200000, 1000000000, seed=20261019 + 2)
+packed = assembly.pack_to_device(asm, device="cuda:0", on_device=True)
+for _ in range(3): D.count_packed(packed, 5)
+torch.cuda.synchronize()
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): c = D.count_packed(packed, 5)
+e1.record(); torch.cuda.synchronize()
+print("count_packed: %.3f ms  checksum %d" % (e0.elapsed_time(e1) / 10, int(c[0].sum().item())))

@@ -427,3 +427,55 @@ def test_device_cluster_metrics_match_host_mirror(torch_cuda):
         med = float(np.median(ref["completeness"][ok])) if ok.any() else float("-inf")
         assert summ[1] == med or (np.isinf(med) and np.isinf(summ[1])), (eps, summ[1], med)
         assert int(summ[2]) == int(ok.sum())
+
+
+@pytest.mark.parametrize("method", ["clr", "ilr"])
+def test_featurise_clr_ilr_vs_oracle_and_sklearn(torch_cuda, method):
+    """Whole device pipeline for the skbio-style transforms: clr takes the fused normalise + int8
+    digit-plane path (tcgen05 Gram and projection), ilr the generic path (511 columns)."""
+    from sklearn.decomposition import PCA
+
+    from autometa_b200 import assembly as A, pipeline, synth
+
+    asm = synth.make_assembly(5600, 5600 * 3400, seed=123)
+    packed = A.pack_to_device(asm, device="cuda:0", on_device=True)
+    res = pipeline.featurise(packed, 5, method, 50)
+    ref_counts, _ = O.count_sequences(synth.sequences(asm), 5)
+    refX = (O.clr if method == "clr" else O.ilr)(ref_counts.astype(np.float64))
+    X = res["normalized"].cpu().numpy()
+    assert X.shape == refX.shape
+    assert np.max(np.abs(X - refX) / np.max(np.abs(refX), axis=1, keepdims=True)) <= 1e-12
+    p = PCA(n_components=50, random_state=np.random.RandomState(42))
+    sc = p.fit_transform(refX)
+    assert p._fit_svd_solver == "covariance_eigh"
+    ref = dict(explained_variance=p.explained_variance_, explained_variance_ratio=p.explained_variance_ratio_,
+               components=p.components_, scores=sc)
+    got = {k: res[k].cpu().numpy() for k in ref}
+    _check_pca(got, ref)
+
+
+def test_digit_planes_fused_equals_generic_quantiser(torch_cuda):
+    """The planes written by the fused normalise kernel are byte-identical to quantising its fp64
+    output with the generic kernel (same centre and scale), and the tcgen05 Gram of the planes
+    agrees with the fp64 CUDA-core Gram."""
+    import torch
+
+    from autometa_b200 import device as D
+
+    rng = np.random.default_rng(11)
+    counts = rng.poisson(6.0, size=(4100, 512)).astype(np.int32)
+    counts[3, :17] = rng.integers(3000, 200000, size=17)
+    d = torch.from_numpy(counts).cuda()
+    center = torch.from_numpy(rng.normal(0, 0.3, size=512)).cuda()
+    e, sc = D.plane_scales(center, None, float(np.log1p(200000.0)))
+    cs = torch.zeros(512, dtype=torch.float64, device="cuda")
+    X, planes = D.normalize_planes(d, "am_clr", None, center, sc, cs)
+    planes2 = D.quantize_planes(X, center, sc)
+    n = X.shape[0]
+    assert torch.equal(planes[: 6 * n * 512], planes2[: 6 * n * 512])
+    np.testing.assert_allclose(cs.cpu().numpy(), X.sum(dim=0).cpu().numpy(), rtol=0, atol=1e-9)
+    G8 = D.gram_planes(planes, n, 512, e).cpu().numpy()
+    G64 = D.gram_centered(X, center).cpu().numpy()
+    scale = np.sqrt(np.outer(np.diag(G64), np.diag(G64)))
+    assert np.max(np.abs(G8 - G64) / scale) <= 5e-12
+    assert np.array_equal(G8, G8.T)
