@@ -213,6 +213,198 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------ 2b. CTA-pair version (cta_group::2)
+// The 1-CTA kernel is bound by the tensor pipe's operand consumption from shared memory (profiles/:
+// MMA-only time = full time).  tcgen05.mma.cta_group::2 lets two SMs work on one instruction: M = 256
+// rows (128 per CTA) share ONE B operand of which each CTA supplies half the columns.  Here the two
+// 128-row halves are not two row blocks of G but two DIGIT PLANES of the same 128 G rows: CTA0 holds
+// the even planes (s = 0, 2, 4), CTA1 the odd ones (s + 1), so the pair computes
+//     CTA0: A_s  x [B_t0 .. B_t0+nt-1]  -> weights s + t        (accumulator index = weight)
+//     CTA1: A_s+1 x the same B planes    -> weights s + 1 + t    (accumulator index = weight - 1)
+// with 4 MMAs per K step (N = 256, 128, 256, 128) instead of 10, and each CTA stages only 3 A planes
+// and 4 B planes (20 KB per stage instead of 36 KB).  CTA1 also forms the weight-6 pairs (1,5), (3,3),
+// (5,1): more of the exact product, not less.  Both CTAs write a partial tile; the reduce kernel sums.
+constexpr int G2_STAGES = 8;
+constexpr uint32_t G2_STAGE_BYTES = 3u * GI_A_BYTES + 4u * GI_B_BYTES;  // 20480
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2,
+                                                uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_THREADS, 1)
+gram_i8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 GramI8Params p, double *__restrict__ part) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr int NS = G2_STAGES;
+  const uint32_t bars = base + (uint32_t)NS * G2_STAGE_BYTES;
+  const uint32_t bar_full = bars, bar_empty = bars + 8u * NS, bar_accf = bars + 16u * NS, bar_acce = bar_accf + 8u;
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_items = p.n_chunks * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, 1); }
+    mbar_init(bar_accf, 1);
+    mbar_init(bar_acce, 8);  // 4 epilogue warps x 2 CTAs, counted in the leader
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; every load signals the LEADER's full barrier) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int bplane[2][4] = {{0, 1, 4, 0}, {2, 3, 5, 1}};
+      for (int item = pair; item < n_items; item += n_pairs) {
+        const int chunk = item / p.n_tiles, tile = item % p.n_tiles;
+        int I, Jb;
+        decode_tile(tile, p.TJ, I, Jb);
+        const int row0 = chunk * p.rows_per_chunk;
+        const int row1 = min(p.n_rows, row0 + p.rows_per_chunk);
+        for (int r = row0; r < row1; r += GI_K) {
+          mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+          const uint32_t lfb = mapa_shared(bar_full + 8u * stage, 0);
+          if (rank == 0) mbar_expect_tx(bar_full + 8u * stage, 2u * G2_STAGE_BYTES);
+          const uint32_t sa = base + (uint32_t)stage * G2_STAGE_BYTES;
+          const uint32_t sb = sa + 3u * GI_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) tma_load_3d_2sm(sa + (uint32_t)k * GI_A_BYTES, &tmA, I * GI_M, r, 2 * k + (int)rank, lfb);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tma_load_3d_2sm(sb + (uint32_t)q * GI_B_BYTES, &tmB, Jb * GI_N, r, bplane[rank][q], lfb);
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA drives both SMs =====
+    if (lane == 0 && rank == 0) {
+      // D = S32, A = B = signed int8, both MN-major, M = 256 (128 rows per CTA)
+      const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t id256 = idesc0 | ((uint32_t)(256 >> 3) << 17), id128 = idesc0 | ((uint32_t)(128 >> 3) << 17);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int item = pair; item < n_items; item += n_pairs) {
+        const int chunk = item / p.n_tiles;
+        const int row0 = chunk * p.rows_per_chunk;
+        const int row1 = min(p.n_rows, row0 + p.rows_per_chunk);
+        mbar_wait(bar_acce, acc_phase ^ 1u);
+        tc_fence_after();
+        uint32_t acc = 0u;
+        for (int r = row0; r < row1; r += GI_K) {
+          mbar_wait(bar_full + 8u * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)stage * G2_STAGE_BYTES;
+          const uint32_t sb = sa + 3u * GI_A_BYTES;
+          const uint64_t a0 = make_desc(sa, GI_K * 128, 1024, 2), a1 = make_desc(sa + GI_A_BYTES, GI_K * 128, 1024, 2),
+                         a2 = make_desc(sa + 2u * GI_A_BYTES, GI_K * 128, 1024, 2);
+          const uint64_t b0 = make_desc(sb, GI_B_BYTES, 512, 4), b2 = make_desc(sb + 2u * GI_B_BYTES, GI_B_BYTES, 512, 4),
+                         b3 = make_desc(sb + 3u * GI_B_BYTES, GI_B_BYTES, 512, 4);
+          umma_i8_2sm(tmem + 0u * GI_N, a0, b0, id256, acc);   // planes (0|1) x B(0,1 | 2,3)   -> idx 0..3
+          umma_i8_2sm(tmem + 4u * GI_N, a0, b2, id128, acc);   // planes (0|1) x B(4 | 5)       -> idx 4,5
+          umma_i8_2sm(tmem + 2u * GI_N, a1, b0, id256, 1u);    // planes (2|3) x B(0,1 | 2,3)   -> idx 2..5
+          umma_i8_2sm(tmem + 4u * GI_N, a2, b3, id128, 1u);    // planes (4|5) x B(0 | 1)       -> idx 4,5
+          acc = 1u;
+          umma_commit_2sm(bar_empty + 8u * stage);
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(bar_accf);
+        acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): accumulator index a holds weight a + rank =====
+    const int q = warp & 3;
+    uint32_t acc_phase = 0;
+    const uint32_t leader_acce = mapa_shared(bar_acce, 0);
+    for (int item = pair; item < n_items; item += n_pairs) {
+      mbar_wait(bar_accf, acc_phase);
+      tc_fence_after();
+      const int chunk = item / p.n_tiles, tile = item % p.n_tiles;
+      const size_t pidx = ((size_t)(chunk + (int)rank * p.n_chunks) * p.n_tiles + tile);
+      double *out = part + (pidx * GI_M + (size_t)(q * 32 + lane)) * GI_N;
+      for (int c = 0; c < GI_N / 16; ++c) {
+        double g[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) g[j] = 0.0;
+        double wd = rank ? (1.0 / 256.0) : 1.0;
+        for (int d = 0; d < 6; ++d) {
+          uint32_t v[16];
+          const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * GI_N + c * 16);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              : "r"(ta));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g[j] = fma((double)(int32_t)v[j], wd, g[j]);
+          wd *= 1.0 / 256.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2 *>(out + c * 16 + j) = make_double2(g[j], g[j + 1]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(leader_acce);
+      acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ 1. quantisation into digit planes
 __global__ void prep_scales_kernel(const double *__restrict__ mu, const double *__restrict__ colmaxabs,
                                    double bound_all, int D, int S, int *__restrict__ e,
@@ -261,8 +453,8 @@ quantize_planes_kernel(const double *__restrict__ X, int64_t n, int D, int Dp, c
 
 // ------------------------------------------------------------------ 3. fixed-order reduction + scaling + mirror
 __global__ void __launch_bounds__(256)
-gram_i8_reduce_kernel(const double *__restrict__ part, GramI8Params p, int D, const int *__restrict__ e,
-                      double *__restrict__ G) {
+gram_i8_reduce_kernel(const double *__restrict__ part, GramI8Params p, int n_parts, int D,
+                      const int *__restrict__ e, double *__restrict__ G) {
   const int tile = blockIdx.x;
   int I, Jb;
   decode_tile(tile, p.TJ, I, Jb);
@@ -270,7 +462,7 @@ gram_i8_reduce_kernel(const double *__restrict__ part, GramI8Params p, int D, co
     const int i = I * GI_M + el / GI_N, j = Jb * GI_N + el % GI_N;
     if (i >= D || j >= D || j < i) continue;
     double s = 0.0;
-    for (int ch = 0; ch < p.n_chunks; ++ch) s += part[((size_t)ch * p.n_tiles + tile) * (GI_M * GI_N) + el];
+    for (int ch = 0; ch < n_parts; ++ch) s += part[((size_t)ch * p.n_tiles + tile) * (GI_M * GI_N) + el];
     const double g = ldexp(s, e[i] + e[j] - 12);
     G[(size_t)i * D + j] += g;
     if (j != i) G[(size_t)j * D + i] += g;
@@ -362,7 +554,7 @@ extern "C" int64_t am_gram_planes_work_bytes(int64_t n_rows, int D, int S) {
   if (n_rows < 1 || D < 1 || S < 2 || S > GI_MAXS) return 0;
   GramI8Params p;
   gram_i8_shape(n_rows, D, S, &p);
-  return align256((int64_t)p.n_chunks * p.n_tiles * GI_M * GI_N * 8);
+  return align256((int64_t)2 * p.n_chunks * p.n_tiles * GI_M * GI_N * 8);  // x2: the CTA-pair kernel writes two partials
 }
 
 extern "C" int am_gram_planes(const int8_t *d_planes, int64_t n_rows, int D, int S, const int32_t *d_e,
@@ -393,7 +585,19 @@ extern "C" int am_gram_planes(const int8_t *d_planes, int64_t n_rows, int D, int
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return am::fail(AM_ECUDA, "am_gram_planes: cuTensorMapEncodeTiled failed");
   }
-  {
+  int n_parts = p.n_chunks;
+  const char *pm = getenv("AM_GRAM_PAIR");
+  const bool use_pair = (S == 6) && !(pm && pm[0] == '0') && p.dbg_mode == 0;
+  if (use_pair) {
+    // CTA pairs (cta_group::2): one cluster of 2 per work item
+    const size_t smem = (size_t)G2_STAGES * G2_STAGE_BYTES + 16 * (size_t)G2_STAGES + 64 + 1024;
+    AM_CUDA(cudaFuncSetAttribute(gram_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_items = p.n_chunks * p.n_tiles;
+    const int pairs = std::max(1, std::min(n_items, am::num_sms() / 2));
+    gram_i8x2_kernel<<<2 * pairs, GI_THREADS, smem, st>>>(tmA, tmB, p, part);
+    AM_LAUNCHED("gram_i8x2_kernel");
+    n_parts = 2 * p.n_chunks;
+  } else {
     const size_t smem = (size_t)p.stages * S * (GI_A_BYTES + GI_B_BYTES) + 16 * (size_t)p.stages + 64 + 1024;
     AM_CUDA(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_items = p.n_chunks * p.n_tiles;
@@ -401,7 +605,7 @@ extern "C" int am_gram_planes(const int8_t *d_planes, int64_t n_rows, int D, int
     gram_i8_kernel<<<grid, GI_THREADS, smem, st>>>(tmA, tmB, p, part);
     AM_LAUNCHED("gram_i8_kernel");
   }
-  gram_i8_reduce_kernel<<<dim3(p.n_tiles, GI_M * GI_N / 256), 256, 0, st>>>(part, p, D, d_e, d_G);
+  gram_i8_reduce_kernel<<<dim3(p.n_tiles, GI_M * GI_N / 256), 256, 0, st>>>(part, p, n_parts, D, d_e, d_G);
   AM_LAUNCHED("gram_i8_reduce_kernel");
   return AM_OK;
 }

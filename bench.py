@@ -424,16 +424,18 @@ def main():
             # tensor-bound: credited FLOPs = 2 N D^2 over the stage time; the kernel
             # actually executes 22 exact int8 digit-pair products on the upper-triangular tiles
             t_s = stage_ms[dom] * 1e-3
-            executed_ops = 2.0 * 22 * shard_n * 20 * 128 * 64
+            # CTA-pair kernel: per 32-row K step and 128x64 tile, 768 accumulator columns x 256 rows x K=32
+            executed_ops = 2.0 * shard_n * 20 * 768 * 256
             roofline = {
-                "kernel": "gram (gram_i8_kernel: tcgen05.mma kind::i8 + fixed-order reduce)", "bound": "tensor",
+                "kernel": "gram (gram_i8x2_kernel: tcgen05.mma.cta_group::2 kind::i8 + fixed-order reduce)", "bound": "tensor",
                 "achieved": round(acct[dom]["flops"] / t_s / 1e12, 2), "peak": bf16, "unit": "TFLOP/s",
                 "frac": round(acct[dom]["flops"] / t_s / 1e12 / bf16, 4), "traffic": traffic,
                 "peak_source": f"{how} (MEASURED_PEAKS.json bf16_tflops, burst)",
                 "executed_int8_TOPs": round(executed_ops / t_s / 1e12, 1),
                 "executed_frac_of_2x_bf16_peak": round(executed_ops / t_s / 1e12 / (2 * bf16), 4),
-                "note": "achieved credits 2*N*D^2 fp64-equivalent FLOPs; fp64 accuracy costs 22 int8 digit-pair "
-                        "products (int8 dense peak = 2x bf16), executed_* count those",
+                "note": "achieved credits 2*N*D^2 fp64-equivalent FLOPs; fp64 accuracy costs 24 int8 digit-pair "
+                        "products on the 20 upper-triangular 128x64 tiles (nominal int8 dense peak = 2x bf16), "
+                        "executed_* count those",
             }
         else:
             roofline = {
