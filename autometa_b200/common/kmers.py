@@ -244,7 +244,10 @@ def pca_device(Xd, n_components: int, group=None) -> Dict[str, Any]:
         dist.all_reduce(n_t, group=group if group is not True else None)
     n = n_t  # stays on device: no host sync in the fit
     mu = cs / n
-    G = _dev.gram_centered_i8(Xd, mu, cm)  # tcgen05 int8 digit-plane product, exact integer accumulation
+    # tcgen05 int8 digit-plane product (exact integer accumulation); the planes are reused by the projection
+    e, sc = _dev.plane_scales(mu, cm)
+    planes = _dev.quantize_planes(Xd, mu, sc)
+    G = _dev.gram_planes(planes, n_local, D, e)
     if group is not None:
         import torch.distributed as dist
 
@@ -254,7 +257,10 @@ def pca_device(Xd, n_components: int, group=None) -> Dict[str, Any]:
     evals, comps, total = _dev.eigh_topk(C, n_components)
     evals = torch.clamp(evals, min=0.0)  # _pca.py:630
     total = total.reshape(())
-    scores = _dev.project(Xd, mu, comps)
+    if n_components <= 64:
+        scores = _dev.project_planes(planes, n_local, D, e, mu, mu, comps)
+    else:
+        scores = _dev.project(Xd, mu, comps)
     return dict(
         scores=scores,
         mean=mu,

@@ -422,31 +422,44 @@ __global__ void prep_scales_kernel(const double *__restrict__ mu, const double *
 __global__ void __launch_bounds__(256)
 quantize_planes_kernel(const double *__restrict__ X, int64_t n, int D, int Dp, const double *__restrict__ mu,
                        const double *__restrict__ sc, int S, int8_t *__restrict__ planes) {
-  // one thread = 8 consecutive columns of one row
-  const int groups = Dp / 8;
+  // one thread = 4 consecutive columns of one row: a warp reads 1 KB of the row and writes 128
+  // contiguous bytes per plane
+  const int groups = Dp / 4;
   const int64_t total = n * groups;
   const double lim = ldexp(1.0, 8 * S - 2);
+  const bool vec_ok = (D % 2 == 0);  // rows are 16-byte aligned only for even D
   for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = w / groups;
-    const int c0 = (int)(w % groups) * 8;
-    long long q[8];
+    const int c0 = (int)(w % groups) * 4;
+    double x[4] = {0.0, 0.0, 0.0, 0.0};
+    const double *xr = X + r * D + c0;
+    if (vec_ok && c0 + 3 < D) {
+      const double2 a = __ldcs(reinterpret_cast<const double2 *>(xr));
+      const double2 b2 = __ldcs(reinterpret_cast<const double2 *>(xr) + 1);
+      x[0] = a.x; x[1] = a.y; x[2] = b2.x; x[3] = b2.y;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j)
+        if (c0 + j < D) x[j] = __ldcs(xr + j);
+    }
+    long long q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
       const int c = c0 + j;
       double v = 0.0;
-      if (c < D) v = (__ldcs(X + r * D + c) - __ldg(mu + c)) * __ldg(sc + c);
+      if (c < D) v = (x[j] - __ldg(mu + c)) * __ldg(sc + c);
       v = fmin(fmax(v, -lim), lim);
       q[j] = __double2ll_rn(v);
     }
     for (int s = S - 1; s >= 0; --s) {
-      unsigned long long packed = 0ull;
+      uint32_t packed = 0u;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         const int a = (int)((q[j] + 128) & 255) - 128;  // balanced digit in [-128, 127]
         q[j] = (q[j] - a) >> 8;
-        packed |= (unsigned long long)(unsigned)(a & 255) << (8 * j);
+        packed |= (uint32_t)(a & 255) << (8 * j);
       }
-      *reinterpret_cast<unsigned long long *>(planes + ((size_t)s * n + r) * Dp + c0) = packed;
+      *reinterpret_cast<uint32_t *>(planes + ((size_t)s * n + r) * Dp + c0) = packed;
     }
   }
 }
@@ -543,7 +556,7 @@ extern "C" int am_quantize_planes(const double *d_X, int64_t n_rows, int D, cons
   if (n_rows == 0) return AM_OK;
   if (!d_X || !d_center || !d_sc || !d_planes) return am::fail(AM_EINVAL, "am_quantize_planes: null pointer");
   const int Dp = plane_pitch(D);
-  const int64_t total = n_rows * (Dp / 8);
+  const int64_t total = n_rows * (Dp / 4);
   const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)am::num_sms() * 16);
   quantize_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_X, n_rows, D, Dp, d_center, d_sc, S, d_planes);
   AM_LAUNCHED("quantize_planes_kernel");

@@ -75,10 +75,13 @@ def _fit_project(packed, counts, method, n_components, row_index, col_index, gro
     if distributed:
         _dist.allreduce_sum_([cs, n_t], group)
     mu = cs / n_t
-    if fused:
-        G = _dev.gram_planes(planes, X.shape[0], D, e)
-    else:
-        G = _dev.gram_centered_i8(X, mu, cm)
+    if not fused and X.shape[0] > 0:
+        # generic route to the same tensor-core kernels: quantise the fp64 matrix about its exact mean
+        center = mu
+        e, sc = _dev.plane_scales(center, cm)
+        planes = _dev.quantize_planes(X, center, sc)
+    G = _dev.gram_planes(planes, X.shape[0], Dout, e) if planes is not None else torch.zeros(
+        (Dout, Dout), dtype=torch.float64, device=dev)
     if distributed:
         _dist.allreduce_sum_([G], group)
     if fused:
@@ -90,8 +93,8 @@ def _fit_project(packed, counts, method, n_components, row_index, col_index, gro
     evals, comps, total = _dev.eigh_topk(C, P)
     mark("eigh")
     evals = torch.clamp(evals, min=0.0)
-    if fused and P <= 64:
-        scores = _dev.project_planes(planes, X.shape[0], D, e, center, mu, comps)
+    if planes is not None and P <= 64:
+        scores = _dev.project_planes(planes, X.shape[0], Dout, e, center, mu, comps)
     else:
         scores = _dev.project(X, mu, comps)
     mark("project")
