@@ -288,26 +288,32 @@ constexpr int BT = 512;  // shifts per round
 // u_j = (d_j - x) u_{j-1} - e_{j-1}^2 u_{j-2}  (Sturm sequence).  One FMA on the dependent chain per
 // row instead of a division; both running minors are rescaled by a power of two every 4 rows.  An
 // exactly zero minor takes the sign opposite to its predecessor (LAPACK dlaebz's pivmin rule).
-__device__ __forceinline__ int sturm_count(const double *d, const double *e2, int n, double x) {
-  double um = 1.0, u = d[0] - x;   // u_{-1}, u_0
-  bool sm = false;                 // "negative" flag of u_{j-1} (pseudo-sign with the zero rule)
-  bool sc = (u < 0.0) || (u == 0.0);
-  int cnt = sc ? 1 : 0;
-  for (int i = 1; i < n; ++i) {
-    const double t = e2[i - 1] * um;
-    const double un = fma(d[i] - x, u, -t);
-    um = u;
-    u = un;
-    sm = sc;
-    sc = (u == 0.0) ? !sm : (u < 0.0);
-    cnt += (sc != sm);
-    if ((i & 3) == 3) {
-      const int ex = max((__double2hiint(u) >> 20) & 0x7ff, (__double2hiint(um) >> 20) & 0x7ff);
-      if (ex > 0 && ex < 2046) {
-        const double f = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023 - ex)
-        u *= f;
-        um *= f;
-      }
+__device__ __forceinline__ int sturm_count(const double2 *__restrict__ de, int n, double x) {
+  // de[i] = {d_i, e_{i-1}^2}: one 16-byte broadcast load per row (the kernel is otherwise bound by
+  // load-issue slots: 16 warps x 2 loads per row).  Only the FMA is on the dependent chain; signs are
+  // read off the sign bits (an exactly zero minor has sign bit 0: a measure-zero event that moves the
+  // bracket by at most one ulp), and both running minors are rescaled by a power of two every 16 rows
+  // (growth per row <= 3 after the |T| <= 1 scaling, so 16 rows stay far inside the double range).
+  double um = 1.0, u = de[0].x - x;
+  int cnt = (__double2hiint(u) >> 31) & 1;
+  for (int i0 = 1; i0 < n; i0 += 16) {
+    const int i1 = min(n, i0 + 16);
+    for (int i = i0; i < i1; ++i) {
+      const double2 v = de[i];
+      const double t = v.y * um;
+      const double un = fma(v.x - x, u, -t);
+      cnt += ((__double2hiint(un) ^ __double2hiint(u)) >> 31) & 1;
+      um = u;
+      u = un;
+    }
+    const int ex = max((__double2hiint(u) >> 20) & 0x7ff, (__double2hiint(um) >> 20) & 0x7ff);
+    if (ex > 0 && ex < 2046) {
+      const double f = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023 - ex)
+      u *= f;
+      um *= f;
+    } else if (ex == 0) {
+      u = (__double2hiint(u) < 0) ? -1.0 : 1.0;  // both minors vanished: restart from the sign only
+      um = 0.0;
     }
   }
   return cnt;
@@ -351,7 +357,8 @@ bisect_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int 
   int ex = 0;
   if (tnorm > 0.0) frexp(tnorm, &ex);
   const double sdn = ldexp(1.0, -ex), sup = ldexp(1.0, ex);
-  for (int i = tid; i < n; i += BT) { d[i] *= sdn; e2[i] *= sdn * sdn; }
+  double2 *de = reinterpret_cast<double2 *>(sm + 2 * n + 64);  // packed {d_i, e_{i-1}^2}, scaled
+  for (int i = tid; i < n; i += BT) de[i] = make_double2(d[i] * sdn, i > 0 ? e2[i - 1] * sdn * sdn : 0.0);
   __syncthreads();
   gl *= sdn; gu *= sdn;
   const double pivmin = 1e-290;
@@ -362,7 +369,7 @@ bisect_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int 
     const double width = hi - lo;
     if (!(width > 2.0 * ulp * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin)) break;
     const double xt = lo + width * ((double)(tid + 1) / (double)(BT + 1));
-    const int cnt = sturm_count(d, e2, n, xt);
+    const int cnt = sturm_count(de, n, xt);
     const unsigned ball = __ballot_sync(FULL, cnt >= target);
     if (lane == 0) first_warp[warp] = ball ? (warp * 32 + __ffs(ball) - 1) : -1;
     __syncthreads();
@@ -430,27 +437,34 @@ invit_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int n
   }
   __syncwarp();
   if (lane == 0) {
-    // LU with partial pivoting of the tridiagonal (LAPACK dgttrf)
+    // LU with partial pivoting of the tridiagonal (LAPACK dgttrf); the running diagonal / super-
+    // diagonal entries are carried in registers so that only the division is on the dependent chain
+    double dcur = dd[0], ducur = du[0];
     for (int i = 0; i < n - 1; ++i) {
-      if (fabs(dd[i]) >= fabs(dl[i])) {
+      const double dli = dl[i], dnext = dd[i + 1], dunext = (i < n - 2) ? du[i + 1] : 0.0;
+      if (fabs(dcur) >= fabs(dli)) {
         piv[i] = 0;
-        if (fabs(dd[i]) < tinyp) dd[i] = copysign(tinyp, dd[i]);
-        const double fact = dl[i] * fast_rcp(dd[i]);
+        if (fabs(dcur) < tinyp) dcur = copysign(tinyp, dcur);
+        const double fact = dli * fast_rcp(dcur);
+        dd[i] = dcur;
+        du[i] = ducur;
         dl[i] = fact;
-        dd[i + 1] -= fact * du[i];
         du2[i] = 0.0;
+        dcur = fma(-fact, ducur, dnext);
+        ducur = dunext;
       } else {
         piv[i] = 1;
-        const double fact = dd[i] * fast_rcp(dl[i]);
-        dd[i] = dl[i];
+        const double fact = dcur * fast_rcp(dli);
+        dd[i] = dli;
         dl[i] = fact;
-        const double temp = du[i];
-        du[i] = dd[i + 1];
-        dd[i + 1] = temp - fact * dd[i + 1];
-        if (i < n - 2) { du2[i] = du[i + 1]; du[i + 1] = -fact * du[i + 1]; }
+        du[i] = dnext;
+        du2[i] = dunext;
+        dcur = fma(-fact, dnext, ducur);
+        ducur = -fact * dunext;
       }
     }
-    if (fabs(dd[n - 1]) < tinyp) dd[n - 1] = copysign(tinyp, dd[n - 1]);
+    if (fabs(dcur) < tinyp) dcur = copysign(tinyp, dcur);
+    dd[n - 1] = dcur;
   }
   __syncwarp();
   for (int i = lane; i < n; i += 32) rdd[i] = 1.0 / dd[i];
@@ -459,18 +473,27 @@ invit_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int n
   // (the shift is an eigenvalue to working precision, so one or two solves suffice)
   for (int it = 0; it < 4; ++it) {
     if (lane == 0) {
+      // forward substitution (dgtts2), running entry in a register
+      double cur = b[0];
       for (int i = 0; i < n - 1; ++i) {
+        const double nxt = b[i + 1], l = dl[i];
         if (!piv[i]) {
-          b[i + 1] -= dl[i] * b[i];
+          b[i] = cur;
+          cur = fma(-l, cur, nxt);
         } else {
-          const double temp = b[i];
-          b[i] = b[i + 1];
-          b[i + 1] = temp - dl[i] * b[i];
+          b[i] = nxt;
+          cur = fma(-l, nxt, cur);
         }
       }
-      b[n - 1] *= rdd[n - 1];
-      if (n > 1) b[n - 2] = (b[n - 2] - du[n - 2] * b[n - 1]) * rdd[n - 2];
-      for (int i = n - 3; i >= 0; --i) b[i] = (b[i] - du[i] * b[i + 1] - du2[i] * b[i + 2]) * rdd[i];
+      // back substitution, two running entries in registers
+      double x1 = cur * rdd[n - 1], x2 = 0.0;
+      b[n - 1] = x1;
+      for (int i = n - 2; i >= 0; --i) {
+        const double xi = (b[i] - du[i] * x1 - du2[i] * x2) * rdd[i];
+        b[i] = xi;
+        x2 = x1;
+        x1 = xi;
+      }
     }
     __syncwarp();
     double mx = 0.0;
@@ -615,81 +638,85 @@ cholqr_kernel(double *__restrict__ Yg, int n, int np, int P, int y_in_smem, int 
 }
 
 // ------------------------------------------------------------------ 5. back-transformation + sign + output
-constexpr int KT = 128;
+// One WARP per eigenvector (no block barrier in the loop), z in registers (lane owns rows lane + 32 m),
+// and TWO reflectors per reduction round: for H_b H_a z with a = k, b = k-1,
+//   alpha = v_a.z,  beta = v_b.(z - tau_a alpha v_a) = v_b.z - tau_a alpha (v_b.v_a),
+// so the three dot products v_a.z, v_b.z, v_b.v_a are reduced together (one shuffle tree), then
+// z -= tau_a alpha v_a + tau_b beta v_b.  The reflector pair of the next round is prefetched.
+constexpr int KT = 128;            // 4 warps = 4 eigenvectors per CTA
+constexpr int ZL = SMEM_N_MAX / 32;  // rows per lane
 __global__ void __launch_bounds__(KT)
-backtransform_kernel(const double *__restrict__ V, const double *__restrict__ tau, int n, int np,
+backtransform_kernel(const double *__restrict__ V, const double *__restrict__ tau, int n, int np, int P,
                      const double *__restrict__ Y, const double *__restrict__ lam,
                      double *__restrict__ evals, double *__restrict__ evecs) {
-  extern __shared__ double sm[];
-  double *z = sm;             // np
-  double *red = sm + np;      // 32
-  __shared__ double s_best[KT / 32];
-  __shared__ int s_idx[KT / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int j = blockIdx.x;
-  // z in registers: thread t owns rows t + KT*m; the reflector of the NEXT step is prefetched while
-  // the current one is reduced (one barrier per step, rotating reduction slots)
-  constexpr int ZM = 5;  // np <= 576 -> <= 5 rows per thread at KT = 128
-  double zr[ZM], vn[ZM], vc[ZM];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * (KT / 32) + warp;
+  if (j >= P) return;
+  double z[ZL], va[ZL], vb[ZL], na[ZL], nb[ZL];
 #pragma unroll
-  for (int m = 0; m < ZM; ++m) {
-    const int i = tid + KT * m;
-    zr[m] = (i < np) ? Y[(size_t)j * np + i] : 0.0;
-    vn[m] = (i < np && n >= 3) ? __ldg(V + (size_t)(n - 3) * np + i) : 0.0;
+  for (int m = 0; m < ZL; ++m) {
+    const int i = lane + 32 * m;
+    z[m] = (i < np) ? Y[(size_t)j * np + i] : 0.0;
+    na[m] = 0.0; nb[m] = 0.0;
   }
-  int slot = 0;
-  for (int k = n - 3; k >= 0; --k) {
-    const double tk = __ldg(tau + k);
+  auto load_pair = [&](int k, double (&xa)[ZL], double (&xb)[ZL]) {
+    // reflectors k and k-1 (k-1 < 0 -> zero vector, tau treated as 0)
 #pragma unroll
-    for (int m = 0; m < ZM; ++m) vc[m] = vn[m];
-    if (k > 0) {
-#pragma unroll
-      for (int m = 0; m < ZM; ++m) {
-        const int i = tid + KT * m;
-        vn[m] = (i < np) ? __ldg(V + (size_t)(k - 1) * np + i) : 0.0;
-      }
+    for (int m = 0; m < ZL; ++m) {
+      const int i = lane + 32 * m;
+      xa[m] = (i < np && k >= 0) ? __ldg(V + (size_t)k * np + i) : 0.0;
+      xb[m] = (i < np && k >= 1) ? __ldg(V + (size_t)(k - 1) * np + i) : 0.0;
     }
-    double part = 0.0;
+  };
+  int k = n - 3;
+  if (k >= 0) load_pair(k, na, nb);
+  for (; k >= 0; k -= 2) {
 #pragma unroll
-    for (int m = 0; m < ZM; ++m) part = fma(vc[m], zr[m], part);
-    part = warp_sum(part);
-    double *r = red + (slot & 3) * (KT / 32);
-    ++slot;
-    if (lane == 0) r[warp] = part;
-    __syncthreads();
-    double tot = 0.0;
+    for (int m = 0; m < ZL; ++m) { va[m] = na[m]; vb[m] = nb[m]; }
+    if (k - 2 >= 0) load_pair(k - 2, na, nb);
+    const double ta = __ldg(tau + k), tb = (k >= 1) ? __ldg(tau + k - 1) : 0.0;
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-    for (int w = 0; w < KT / 32; ++w) tot += r[w];
-    const double sc = tk * tot;
+    for (int m = 0; m < ZL; ++m) {
+      s1 = fma(va[m], z[m], s1);
+      s2 = fma(vb[m], z[m], s2);
+      s3 = fma(vb[m], va[m], s3);
+    }
 #pragma unroll
-    for (int m = 0; m < ZM; ++m) zr[m] = fma(-sc, vc[m], zr[m]);
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(FULL, s1, o);
+      s2 += __shfl_xor_sync(FULL, s2, o);
+      s3 += __shfl_xor_sync(FULL, s3, o);
+    }
+    const double ca = ta * s1;
+    const double cb = tb * fma(-ca, s3, s2);
+#pragma unroll
+    for (int m = 0; m < ZL; ++m) z[m] = fma(-cb, vb[m], fma(-ca, va[m], z[m]));
   }
-#pragma unroll
-  for (int m = 0; m < ZM; ++m) {
-    const int i = tid + KT * m;
-    if (i < np) z[i] = zr[m];
-  }
-  __syncthreads();
   // sklearn svd_flip(u_based_decision=False): largest-|.| entry (first occurrence) made positive
-  double best = -1.0;
+  double best = -1.0, bval = 0.0;
   int bidx = 0;
-  for (int i = tid; i < n; i += KT) {
-    const double a = fabs(z[i]);
-    if (a > best) { best = a; bidx = i; }
+#pragma unroll
+  for (int m = 0; m < ZL; ++m) {
+    const int i = lane + 32 * m;
+    if (i < n) {
+      const double a = fabs(z[m]);
+      if (a > best) { best = a; bidx = i; bval = z[m]; }
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     const double ob = __shfl_xor_sync(FULL, best, o);
     const int oi = __shfl_xor_sync(FULL, bidx, o);
-    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    const double ov = __shfl_xor_sync(FULL, bval, o);
+    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; bval = ov; }
   }
-  if (lane == 0) { s_best[warp] = best; s_idx[warp] = bidx; }
-  __syncthreads();
-  best = s_best[0]; bidx = s_idx[0];
-  for (int w = 1; w < KT / 32; ++w)
-    if (s_best[w] > best || (s_best[w] == best && s_idx[w] < bidx)) { best = s_best[w]; bidx = s_idx[w]; }
-  const double sgn = z[bidx] < 0.0 ? -1.0 : 1.0;
-  for (int i = tid; i < n; i += KT) evecs[(size_t)j * n + i] = sgn * z[i];
-  if (tid == 0) evals[j] = lam[j];
+  const double sgn = bval < 0.0 ? -1.0 : 1.0;
+#pragma unroll
+  for (int m = 0; m < ZL; ++m) {
+    const int i = lane + 32 * m;
+    if (i < n) evecs[(size_t)j * n + i] = sgn * z[m];
+  }
+  if (lane == 0) evals[j] = lam[j];
 }
 
 inline int round_up32(int x) { return (x + 31) & ~31; }
@@ -762,7 +789,7 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
   }
   // 2. bisection
   {
-    const size_t smem = ((size_t)2 * n + 64) * sizeof(double);
+    const size_t smem = ((size_t)4 * n + 64 + 2) * sizeof(double);
     bisect_kernel<<<P, BT, smem, st>>>(w.d, w.e, n, P, w.lam, d_trace);
     AM_LAUNCHED("bisect_kernel");
   }
@@ -787,8 +814,7 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
   }
   // 5. back-transformation
   {
-    const size_t smem = ((size_t)np + 32) * sizeof(double);
-    backtransform_kernel<<<P, KT, smem, st>>>(w.V, w.tau, n, np, w.Y, w.lam, d_evals, d_evecs);
+    backtransform_kernel<<<(P + KT / 32 - 1) / (KT / 32), KT, 0, st>>>(w.V, w.tau, n, np, P, w.Y, w.lam, d_evals, d_evecs);
     AM_LAUNCHED("backtransform_kernel");
   }
   return AM_OK;
