@@ -78,23 +78,43 @@ struct TriOut {
 };
 
 // ------------------------------------------------------------------ 1. tridiagonalisation
+// Step k (LAPACK dsytd2 with the rank-2 update deferred by one step).  x_k = current column k below
+// the diagonal, alpha = x_k[k+1], sigma = |x_k[k+2:]|^2, beta = -sign(alpha) sqrt(alpha^2 + sigma),
+// tau = (beta - alpha)/beta, v_k = (x_k - beta e_{k+1})/(alpha - beta).
+//   B(k)  all warps: fused pass over the CTA's rows >= k — apply the pending update
+//         A -= v_{k-1} w_{k-1}^T + w_{k-1} v_{k-1}^T and accumulate y = A x_k with the UNSCALED column
+//         (A v_k = (y - beta A e_{k+1}) / (alpha - beta), and A e_{k+1} is the column that is gathered
+//         anyway), so the mat-vec does not wait for sigma / sqrt / divisions.  Every row sends
+//         {y_i, A[i][k+1]} to all 16 CTAs with one 16-byte st.async that also counts bytes on the
+//         receiver's mbarrier (data-carrying synchronisation: no cluster barrier in the loop).
+//   S(k)  while the inbox fills: sigma from the per-warp partials, beta, tau, 1/(alpha - beta);
+//         the owner CTA writes v_k, e_k, tau_k for the back-transformation.
+//   C(k)  p = tau (y - beta a)/(alpha - beta), gamma = p.v (one block reduction), w_k = p - tau gamma/2 v,
+//         next column x_{k+1} = a - v w[k+1] - w, per-warp partials of its sigma.
+// The O(D) algebra is replicated in every CTA from identical inputs (bit-identical results).
+__device__ __forceinline__ void st_async_f64x2(uint32_t raddr, double a, double b, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
+               ::"r"(raddr), "l"(__double_as_longlong(a)), "l"(__double_as_longlong(b)), "r"(rbar) : "memory");
+}
+
 __global__ void __cluster_dims__(TC, 1, 1) __launch_bounds__(TT, 1)
 tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriOut out) {
   cg::cluster_group cluster = cg::this_cluster();
   const int c = (int)cluster.block_rank();
   extern __shared__ double sm[];
   double *rows = sm;                          // RL x np
-  double *vb = rows + (size_t)RL * np;        // 2 x np
-  double *wb = vb + 2 * np;                   // 2 x np
-  double *gP = wb + 2 * np;                   // 2 x np  (all-gathered p slices)
-  double *gA = gP + 2 * np;                   // 2 x np  (all-gathered next-column slices)
-  double *red = gA + 2 * np;                  // 4 x TW
+  double *vb = rows + (size_t)RL * np;        // 2 x np   scaled reflectors v_{k-1}, v_k
+  double *wb = vb + 2 * np;                   // 2 x np   w_{k-1}, w_k
+  double *xs = wb + 2 * np;                   // 2 x np   unscaled columns x_k (mat-vec operand)
+  double2 *inbox = reinterpret_cast<double2 *>(xs + 2 * np);  // 2 x np  {y_i, A[i][k+1]}
+  double *red = reinterpret_cast<double *>(inbox + 2 * np);   // 4 x TW rotating reduction slots
+  double *sigp = red + 4 * TW;                // 2 x TW   per-warp partials of sigma
   __shared__ __align__(8) unsigned long long s_mbar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t mbar0 = (uint32_t)__cvta_generic_to_shared(&s_mbar[0]);
-  const uint32_t gP_s = (uint32_t)__cvta_generic_to_shared(gP), gA_s = (uint32_t)__cvta_generic_to_shared(gA);
+  const uint32_t inbox_s = (uint32_t)__cvta_generic_to_shared(inbox);
+  const int i0 = tid, i1 = tid + TT;  // the rows this thread owns in the replicated vector algebra
 
-  // load own rows (symmetrised), zero the vectors
   for (int lr = 0; lr < RL; ++lr) {
     const int i = c + TC * lr;
     for (int j = tid; j < np; j += TT) {
@@ -103,7 +123,7 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
       rows[(size_t)lr * np + j] = a;
     }
   }
-  for (int j = tid; j < 2 * np; j += TT) { vb[j] = 0.0; wb[j] = 0.0; gP[j] = 0.0; gA[j] = 0.0; }
+  for (int j = tid; j < 2 * np; j += TT) { vb[j] = 0.0; wb[j] = 0.0; xs[j] = 0.0; inbox[j] = make_double2(0.0, 0.0); }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8u) : "memory");
@@ -112,71 +132,40 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
   __syncthreads();
   cluster.sync();  // every CTA's buffers and mbarriers exist before any remote store
 
-  // prologue: all-gather column 0 into gA[1]
+  // prologue: all-gather column 0 (inbox slot 1, .y component), form x_0
+  if (tid == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar0 + 8u), "r"((uint32_t)(n - 1) * 16u) : "memory");
   for (int lr = warp; lr < RL; lr += TW) {
     const int i = c + TC * lr;
-    if (i < n && lane < TC) {
-      double *dst = cluster.map_shared_rank(gA + np + i, lane);
-      *dst = rows[(size_t)lr * np + 0];
-    }
+    if (i < n && i >= 1 && lane < TC)
+      st_async_f64x2(mapa_u32(inbox_s + (uint32_t)(np + i) * 16u, lane), 0.0, rows[(size_t)lr * np + 0],
+                     mapa_u32(mbar0 + 8u, lane));
   }
-  cluster.sync();
-  // x (the current column below the diagonal) lives in registers: thread t owns rows t and t + TT
+  mbar_wait_cluster(mbar0 + 8u, 0u);
   double x0 = 0.0, x1 = 0.0;
-  double sig_part = 0.0;
   {
-    const int i0 = tid, i1 = tid + TT;
-    if (i0 >= 1 && i0 < n) x0 = gA[np + i0];
-    if (i1 >= 1 && i1 < n) x1 = gA[np + i1];
-    if (i0 >= 2) sig_part += x0 * x0;
-    sig_part += x1 * x1;
+    if (i0 >= 1 && i0 < n) x0 = inbox[np + i0].y;
+    if (i1 >= 1 && i1 < n) x1 = inbox[np + i1].y;
+    if (i0 < np) xs[i0] = x0;
+    if (i1 < np) xs[i1] = x1;
+    const double sp = warp_sum(((i0 >= 2) ? x0 * x0 : 0.0) + ((i1 >= 2) ? x1 * x1 : 0.0));
+    if (lane == 0) sigp[warp] = sp;
   }
-  int rslot = 0;
-  auto block_sum1 = [&](double v) -> double {
-    // one barrier per reduction: four rotating slots keep successive reductions apart
-    double *r = red + (rslot & 3) * TW;
-    ++rslot;
-    v = warp_sum(v);
-    if (lane == 0) r[warp] = v;
-    __syncthreads();
-    double t = lane < TW ? r[lane] : 0.0;
-    return warp_sum(t);
-  };
-  double sigma = block_sum1(sig_part);
-  double alpha = (n > 1) ? gA[np + 1] : 0.0;  // x[k+1] for k = 0, same value in every thread
+  __syncthreads();
 
+  int rslot = 0;
   long long tA = 0, tB = 0, tS = 0, tC = 0, t0 = clock64(), t1;
 #define AM_TICK(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
   for (int k = 0; k <= n - 3; ++k) {
-    double *vcur = vb + (k & 1) * np, *wcur = wb + (k & 1) * np;
-    const double *vprev = vb + ((k + 1) & 1) * np, *wprev = wb + ((k + 1) & 1) * np;
-    // ---- A. reflector from x (replicated in every CTA)
-    double beta, tau, scale;
-    if (!(sigma > 1e-290)) {
-      beta = alpha; tau = 0.0; scale = 0.0;
-    } else {
-      beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
-      tau = (beta - alpha) / beta;
-      scale = 1.0 / (alpha - beta);
-    }
-    {
-      const int i0 = tid, i1 = tid + TT;
-      const double v0 = (i0 == k + 1) ? 1.0 : ((i0 > k + 1 && i0 < n) ? x0 * scale : 0.0);
-      if (i0 < np) vcur[i0] = v0;
-      if (i1 < np) vcur[i1] = (i1 == k + 1) ? 1.0 : ((i1 > k + 1 && i1 < n) ? x1 * scale : 0.0);
-      if (c == (k % TC)) {
-        if (i0 < np) out.V[(size_t)k * np + i0] = v0;
-        if (i1 < np) out.V[(size_t)k * np + i1] = vcur[i1];
-        if (tid == 0) { out.e[k] = beta; out.tau[k] = tau; }
-      }
-    }
-    // arm this step's inbox: rows k+1..n-1 each deliver p and their entry of the next column
+    const int cur = k & 1, prv = (k + 1) & 1;
+    double *vcur = vb + cur * np, *wcur = wb + cur * np;
+    const double *vprev = vb + prv * np, *wprev = wb + prv * np;
+    const double *xk = xs + cur * np;
+    // arm this step's inbox: rows k+1..n-1 each deliver 16 bytes
     if (tid == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                   ::"r"(mbar0 + 8u * (k & 1)), "r"((uint32_t)(n - k - 1) * 16u) : "memory");
-    __syncthreads();
-    AM_TICK(tA);
-    // ---- B. fused pass over own rows >= k: apply pending update (k-1), p = tau * A v_k
+                   ::"r"(mbar0 + 8u * cur), "r"((uint32_t)(n - k - 1) * 16u) : "memory");
+    // ---- B. fused pass over own rows >= k: pending update (k-1), y = A x_k
     {
       int lrs[MAXRPW];
       double vpi[MAXRPW], wpi[MAXRPW], acc[MAXRPW];
@@ -191,7 +180,7 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
       if (nr > 0) {
 #pragma unroll 2
         for (int j = (k & ~31) + lane; j < np; j += 32) {
-          const double vpj = vprev[j], wpj = wprev[j], vcj = vcur[j];
+          const double vpj = vprev[j], wpj = wprev[j], xj = xk[j];
 #pragma unroll
           for (int r = 0; r < MAXRPW; ++r) {
             if (lrs[r] >= 0) {
@@ -200,57 +189,82 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
               a = fma(-vpi[r], wpj, a);
               a = fma(-wpi[r], vpj, a);
               *ap = a;
-              acc[r] = fma(a, vcj, acc[r]);
+              acc[r] = fma(a, xj, acc[r]);
             }
           }
         }
         __syncwarp();
-        const int buf = k & 1;
-        const uint32_t rbar = mapa_u32(mbar0 + 8u * buf, (uint32_t)(lane & (TC - 1)));
+        const uint32_t rbar = mapa_u32(mbar0 + 8u * cur, (uint32_t)(lane & (TC - 1)));
 #pragma unroll
         for (int r = 0; r < MAXRPW; ++r) {
           if (lrs[r] >= 0) {
             const int i = c + TC * lrs[r];
-            const double p = tau * warp_sum(acc[r]);
+            const double y = warp_sum(acc[r]);
             const double a1 = rows[(size_t)lrs[r] * np + (k + 1)];  // post-update A[i][k+1]
-            if (i >= k + 1) {
-              // data-carrying all-gather: the store itself signals the receiver's mbarrier
-              if (lane < TC) st_async_f64(mapa_u32(gP_s + (uint32_t)(buf * np + i) * 8u, lane), p, rbar);
-              else st_async_f64(mapa_u32(gA_s + (uint32_t)(buf * np + i) * 8u, lane - TC), a1, rbar);
-            }
+            if (i >= k + 1 && lane < TC)
+              st_async_f64x2(mapa_u32(inbox_s + (uint32_t)(cur * np + i) * 16u, lane), y, a1, rbar);
           }
         }
       }
     }
     AM_TICK(tB);
-    mbar_wait_cluster(mbar0 + 8u * (k & 1), (uint32_t)((k >> 1) & 1));  // all slices of step k have landed
-    AM_TICK(tS);
-
-    // ---- C. w_k and the next column x_{k+1} (replicated; two one-barrier reductions)
-    const double *P = gP + (k & 1) * np, *AC = gA + (k & 1) * np;
-    const int i0 = tid, i1 = tid + TT;
-    const bool in0 = (i0 >= k + 1 && i0 < n), in1 = (i1 >= k + 1 && i1 < n);
-    const double p0 = in0 ? P[i0] : 0.0, p1 = in1 ? P[i1] : 0.0;
-    const double v0 = (i0 < np) ? vcur[i0] : 0.0, v1 = (i1 < np) ? vcur[i1] : 0.0;
-    const double gamma = block_sum1(fma(p0, v0, p1 * v1));
-    const double Kc = 0.5 * tau * gamma;
-    const double w0 = in0 ? fma(-Kc, v0, p0) : 0.0, w1 = in1 ? fma(-Kc, v1, p1) : 0.0;
-    if (i0 < np) wcur[i0] = w0;
-    if (i1 < np) wcur[i1] = w1;
-    const double wk1 = P[k + 1] - Kc;  // w_k[k+1]  (v_k[k+1] = 1)
-    x0 = (i0 >= k + 2 && i0 < n) ? AC[i0] - v0 * wk1 - w0 : 0.0;
-    x1 = (i1 >= k + 2 && i1 < n) ? AC[i1] - v1 * wk1 - w1 : 0.0;
-    sig_part = ((i0 >= k + 3) ? x0 * x0 : 0.0) + ((i1 >= k + 3) ? x1 * x1 : 0.0);
-    sigma = block_sum1(sig_part);
-    // alpha of the next step = x_{k+1}[k+2], recomputed by every thread from the gathered vectors
-    if (k + 2 < n) {
-      const double vk2 = vcur[k + 2];
-      alpha = AC[k + 2] - vk2 * wk1 - fma(-Kc, vk2, P[k + 2]);
+    // ---- S. reflector scalars while the inbox fills
+    double sigma = 0.0;
+#pragma unroll
+    for (int w = 0; w < TW; ++w) sigma += sigp[cur * TW + w];
+    const double alpha = xk[k + 1];
+    double beta, tau, scale;
+    if (!(sigma > 1e-290)) {
+      beta = alpha; tau = 0.0; scale = 0.0;
+    } else {
+      beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
+      tau = (beta - alpha) / beta;
+      scale = 1.0 / (alpha - beta);
     }
+    const double v0 = (i0 == k + 1) ? 1.0 : ((i0 > k + 1 && i0 < n) ? x0 * scale : 0.0);
+    const double v1 = (i1 == k + 1) ? 1.0 : ((i1 > k + 1 && i1 < n) ? x1 * scale : 0.0);
+    if (c == (k % TC)) {
+      if (i0 < np) out.V[(size_t)k * np + i0] = v0;
+      if (i1 < np) out.V[(size_t)k * np + i1] = v1;
+      if (tid == 0) { out.e[k] = beta; out.tau[k] = tau; }
+    }
+    AM_TICK(tA);
+    // slot 0 is used by steps 0, 2, ..; slot 1 by the prologue and steps 1, 3, ..
+    mbar_wait_cluster(mbar0 + 8u * cur, (uint32_t)((cur ? ((k + 1) >> 1) : (k >> 1)) & 1));
+    AM_TICK(tS);
+    // ---- C. w_k and the next column (replicated)
+    const double2 *ib = inbox + cur * np;
+    const bool in0 = (i0 >= k + 1 && i0 < n), in1 = (i1 >= k + 1 && i1 < n);
+    const double ts = tau * scale;
+    const double2 g0 = in0 ? ib[i0] : make_double2(0.0, 0.0), g1 = in1 ? ib[i1] : make_double2(0.0, 0.0);
+    const double p0 = in0 ? ts * fma(-beta, g0.y, g0.x) : 0.0, p1 = in1 ? ts * fma(-beta, g1.y, g1.x) : 0.0;
+    double gam = warp_sum(fma(p0, v0, p1 * v1));
+    {
+      double *r = red + (rslot & 3) * TW;
+      ++rslot;
+      if (lane == 0) r[warp] = gam;
+      __syncthreads();
+      gam = 0.0;
+#pragma unroll
+      for (int w = 0; w < TW; ++w) gam += r[w];
+    }
+    const double Kc = 0.5 * tau * gam;
+    const double w0 = in0 ? fma(-Kc, v0, p0) : 0.0, w1 = in1 ? fma(-Kc, v1, p1) : 0.0;
+    if (i0 < np) { vcur[i0] = v0; wcur[i0] = w0; }
+    if (i1 < np) { vcur[i1] = v1; wcur[i1] = w1; }
+    const double2 gk = ib[k + 1];
+    const double wk1 = ts * fma(-beta, gk.y, gk.x) - Kc;  // w_k[k+1]  (v_k[k+1] = 1)
+    x0 = (i0 >= k + 2 && i0 < n) ? g0.y - v0 * wk1 - w0 : 0.0;
+    x1 = (i1 >= k + 2 && i1 < n) ? g1.y - v1 * wk1 - w1 : 0.0;
+    double *xn = xs + prv * np;
+    if (i0 < np) xn[i0] = x0;
+    if (i1 < np) xn[i1] = x1;
+    const double sp = warp_sum(((i0 >= k + 3) ? x0 * x0 : 0.0) + ((i1 >= k + 3) ? x1 * x1 : 0.0));
+    if (lane == 0) sigp[prv * TW + warp] = sp;
+    __syncthreads();
     AM_TICK(tC);
   }
   if (out.dbg && c == 0 && tid == 0) { out.dbg[0] = tA; out.dbg[1] = tB; out.dbg[2] = tS; out.dbg[3] = tC; }
-  __syncthreads();
 
   // epilogue: pending update (n-3) on rows/cols >= n-2, then d and the last e
   {
@@ -768,7 +782,7 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
 
   // 1. tridiagonalisation (one cluster of 16 CTAs)
   {
-    const size_t smem = ((size_t)RL * np + 8 * (size_t)np + 4 * TW) * sizeof(double);
+    const size_t smem = ((size_t)RL * np + 10 * (size_t)np + 6 * TW) * sizeof(double);
     if (smem > 227 * 1024) return am::fail(AM_EINVAL, "am_eigh_topk: matrix does not fit the cluster's shared memory");
     AM_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AM_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
