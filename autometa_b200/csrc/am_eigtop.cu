@@ -29,6 +29,10 @@ constexpr int TC = 16;        // CTAs in the cluster
 constexpr int TT = 512;       // threads per CTA
 constexpr int TW = TT / 32;   // warps per CTA
 constexpr int MAXRPW = 3;     // local rows per warp (RL <= 48)
+constexpr int AW = 4;         // warps that run the replicated O(D) reflector algebra (one per SM sub-partition:
+                              // with all 16 warps doing it redundantly the fp64 chains contend for issue slots)
+constexpr int AT = AW * 32;
+constexpr int NE = (576 + AT - 1) / AT;  // vector elements per algebra thread (rows tid + AT*m)
 constexpr int SMEM_N_MAX = 576;
 constexpr int PMAX = 128;
 
@@ -142,13 +146,19 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
                      mapa_u32(mbar0 + 8u, lane));
   }
   mbar_wait_cluster(mbar0 + 8u, 0u);
-  double x0 = 0.0, x1 = 0.0;
-  {
-    if (i0 >= 1 && i0 < n) x0 = inbox[np + i0].y;
-    if (i1 >= 1 && i1 < n) x1 = inbox[np + i1].y;
-    if (i0 < np) xs[i0] = x0;
-    if (i1 < np) xs[i1] = x1;
-    const double sp = warp_sum(((i0 >= 2) ? x0 * x0 : 0.0) + ((i1 >= 2) ? x1 * x1 : 0.0));
+  double x[NE];
+#pragma unroll
+  for (int m = 0; m < NE; ++m) x[m] = 0.0;
+  if (warp < AW) {
+    double sp = 0.0;
+#pragma unroll
+    for (int m = 0; m < NE; ++m) {
+      const int i = tid + AT * m;
+      if (i >= 1 && i < n) x[m] = inbox[np + i].y;
+      if (i < np) xs[i] = x[m];
+      if (i >= 2) sp = fma(x[m], x[m], sp);
+    }
+    sp = warp_sum(sp);
     if (lane == 0) sigp[warp] = sp;
   }
   __syncthreads();
@@ -208,59 +218,76 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
       }
     }
     AM_TICK(tB);
-    // ---- S. reflector scalars while the inbox fills
-    double sigma = 0.0;
+    // ---- S. reflector scalars while the inbox fills (algebra warps only)
+    double beta = 0.0, tau = 0.0, scale = 0.0;
+    double v[NE];
+    if (warp < AW) {
+      double sigma = 0.0;
 #pragma unroll
-    for (int w = 0; w < TW; ++w) sigma += sigp[cur * TW + w];
-    const double alpha = xk[k + 1];
-    double beta, tau, scale;
-    if (!(sigma > 1e-290)) {
-      beta = alpha; tau = 0.0; scale = 0.0;
-    } else {
-      beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
-      tau = (beta - alpha) / beta;
-      scale = 1.0 / (alpha - beta);
-    }
-    const double v0 = (i0 == k + 1) ? 1.0 : ((i0 > k + 1 && i0 < n) ? x0 * scale : 0.0);
-    const double v1 = (i1 == k + 1) ? 1.0 : ((i1 > k + 1 && i1 < n) ? x1 * scale : 0.0);
-    if (c == (k % TC)) {
-      if (i0 < np) out.V[(size_t)k * np + i0] = v0;
-      if (i1 < np) out.V[(size_t)k * np + i1] = v1;
-      if (tid == 0) { out.e[k] = beta; out.tau[k] = tau; }
+      for (int w = 0; w < AW; ++w) sigma += sigp[cur * AW + w];
+      const double alpha = xk[k + 1];
+      if (!(sigma > 1e-290)) {
+        beta = alpha; tau = 0.0; scale = 0.0;
+      } else {
+        beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+#pragma unroll
+      for (int m = 0; m < NE; ++m) {
+        const int i = tid + AT * m;
+        v[m] = (i == k + 1) ? 1.0 : ((i > k + 1 && i < n) ? x[m] * scale : 0.0);
+        if (c == (k % TC) && i < np) out.V[(size_t)k * np + i] = v[m];
+      }
+      if (c == (k % TC) && tid == 0) { out.e[k] = beta; out.tau[k] = tau; }
     }
     AM_TICK(tA);
     // slot 0 is used by steps 0, 2, ..; slot 1 by the prologue and steps 1, 3, ..
-    mbar_wait_cluster(mbar0 + 8u * cur, (uint32_t)((cur ? ((k + 1) >> 1) : (k >> 1)) & 1));
+    if (warp < AW) mbar_wait_cluster(mbar0 + 8u * cur, (uint32_t)((cur ? ((k + 1) >> 1) : (k >> 1)) & 1));
     AM_TICK(tS);
-    // ---- C. w_k and the next column (replicated)
+    // ---- C. w_k and the next column (algebra warps; the other warps wait at the barriers)
     const double2 *ib = inbox + cur * np;
-    const bool in0 = (i0 >= k + 1 && i0 < n), in1 = (i1 >= k + 1 && i1 < n);
     const double ts = tau * scale;
-    const double2 g0 = in0 ? ib[i0] : make_double2(0.0, 0.0), g1 = in1 ? ib[i1] : make_double2(0.0, 0.0);
-    const double p0 = in0 ? ts * fma(-beta, g0.y, g0.x) : 0.0, p1 = in1 ? ts * fma(-beta, g1.y, g1.x) : 0.0;
-    double gam = warp_sum(fma(p0, v0, p1 * v1));
-    {
-      double *r = red + (rslot & 3) * TW;
-      ++rslot;
-      if (lane == 0) r[warp] = gam;
-      __syncthreads();
-      gam = 0.0;
+    double pv[NE], av[NE];
+    double *r = red + (rslot & 3) * TW;
+    ++rslot;
+    if (warp < AW) {
+      double part = 0.0;
 #pragma unroll
-      for (int w = 0; w < TW; ++w) gam += r[w];
+      for (int m = 0; m < NE; ++m) {
+        const int i = tid + AT * m;
+        const bool in = (i >= k + 1 && i < n);
+        const double2 g = in ? ib[i] : make_double2(0.0, 0.0);
+        pv[m] = in ? ts * fma(-beta, g.y, g.x) : 0.0;
+        av[m] = g.y;
+        part = fma(pv[m], v[m], part);
+      }
+      part = warp_sum(part);
+      if (lane == 0) r[warp] = part;
     }
-    const double Kc = 0.5 * tau * gam;
-    const double w0 = in0 ? fma(-Kc, v0, p0) : 0.0, w1 = in1 ? fma(-Kc, v1, p1) : 0.0;
-    if (i0 < np) { vcur[i0] = v0; wcur[i0] = w0; }
-    if (i1 < np) { vcur[i1] = v1; wcur[i1] = w1; }
-    const double2 gk = ib[k + 1];
-    const double wk1 = ts * fma(-beta, gk.y, gk.x) - Kc;  // w_k[k+1]  (v_k[k+1] = 1)
-    x0 = (i0 >= k + 2 && i0 < n) ? g0.y - v0 * wk1 - w0 : 0.0;
-    x1 = (i1 >= k + 2 && i1 < n) ? g1.y - v1 * wk1 - w1 : 0.0;
-    double *xn = xs + prv * np;
-    if (i0 < np) xn[i0] = x0;
-    if (i1 < np) xn[i1] = x1;
-    const double sp = warp_sum(((i0 >= k + 3) ? x0 * x0 : 0.0) + ((i1 >= k + 3) ? x1 * x1 : 0.0));
-    if (lane == 0) sigp[prv * TW + warp] = sp;
+    __syncthreads();
+    if (warp < AW) {
+      double gam = 0.0;
+#pragma unroll
+      for (int w = 0; w < AW; ++w) gam += r[w];
+      const double Kc = 0.5 * tau * gam;
+      const double2 gk = ib[k + 1];
+      const double wk1 = ts * fma(-beta, gk.y, gk.x) - Kc;  // w_k[k+1]  (v_k[k+1] = 1)
+      double *xn = xs + prv * np;
+      double sp = 0.0;
+#pragma unroll
+      for (int m = 0; m < NE; ++m) {
+        const int i = tid + AT * m;
+        const bool in = (i >= k + 1 && i < n);
+        const double w = in ? fma(-Kc, v[m], pv[m]) : 0.0;
+        if (i < np) { vcur[i] = v[m]; wcur[i] = w; }
+        x[m] = (i >= k + 2 && i < n) ? av[m] - v[m] * wk1 - w : 0.0;
+        if (i < np) xn[i] = x[m];
+        if (i >= k + 3) sp = fma(x[m], x[m], sp);
+      }
+      sp = warp_sum(sp);
+      if (lane == 0) sigp[prv * AW + warp] = sp;
+    }
     __syncthreads();
     AM_TICK(tC);
   }
