@@ -299,6 +299,47 @@ extern "C" int am_colsum(const double *d_X, int64_t n_rows, int D, double *d_col
   return AM_OK;
 }
 
+// mu = colsum / n;  C = (G - n (mu - centre)(mu - centre)^T) / (n - 1), in place on G.  n comes from
+// device memory (it is an all-reduced tensor in the multi-GPU path).  One launch instead of ~8
+// element-wise torch kernels between the Gram and the eigensolve.
+__global__ void cov_finish_kernel(double *__restrict__ G, int D, const double *__restrict__ colsum,
+                                  const double *__restrict__ center, const double *__restrict__ n_ptr,
+                                  double *__restrict__ mu) {
+  const double n = *n_ptr;
+  const int64_t total = (int64_t)D * D;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(q / D), j = (int)(q % D);
+    const double di = colsum[i] / n - (center ? center[i] : colsum[i] / n);
+    const double dj = colsum[j] / n - (center ? center[j] : colsum[j] / n);
+    G[q] = (G[q] - n * (di * dj)) / (n - 1.0);
+    if (i == 0) mu[j] = colsum[j] / n;
+  }
+}
+
+// flags[0] = min over columns of col_present, flags[1] = min over contigs of row_sum (am_clr's
+// "column / row is NA everywhere" tests, kmers.py:369): one launch, read back once per step
+__global__ void count_flags_kernel(const int *__restrict__ present, int ncols, const int *__restrict__ row_sum,
+                                   int64_t n, int *__restrict__ flags) {
+  __shared__ int s_min[32];
+  int m = 0x7fffffff;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = min(m, row_sum[i]);
+  for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? s_min[threadIdx.x] : 0x7fffffff;
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) atomicMin(flags + 1, m);
+  }
+  if (blockIdx.x == 0) {
+    int p = 0x7fffffff;
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) p = min(p, present[c]);
+    for (int o = 16; o > 0; o >>= 1) p = min(p, __shfl_xor_sync(0xffffffffu, p, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(flags + 0, p);
+  }
+}
+
 extern "C" int64_t am_colstats_work_bytes(int D) { return 2 * am_colsum_work_bytes(D); }
 
 extern "C" int am_colstats(const double *d_X, int64_t n_rows, int D, double *d_colsum,
@@ -315,6 +356,29 @@ extern "C" int am_colstats(const double *d_X, int64_t n_rows, int D, double *d_c
   AM_LAUNCHED("colstats_partial_kernel");
   colstats_reduce_kernel<<<(D + 127) / 128, 128, 0, st>>>(psum, pmax, S, D, d_colsum, d_colmaxabs);
   AM_LAUNCHED("colstats_reduce_kernel");
+  return AM_OK;
+}
+
+extern "C" int am_cov_finish(double *d_G, int D, const double *d_colsum, const double *d_center,
+                             const double *d_n, double *d_mu, void *stream) {
+  if (D < 1) return am::fail(AM_EINVAL, "am_cov_finish: bad D");
+  if (!d_G || !d_colsum || !d_n || !d_mu) return am::fail(AM_EINVAL, "am_cov_finish: null pointer");
+  const int64_t total = (int64_t)D * D;
+  cov_finish_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 1024), 256, 0, (cudaStream_t)stream>>>(
+      d_G, D, d_colsum, d_center, d_n, d_mu);
+  AM_LAUNCHED("cov_finish_kernel");
+  return AM_OK;
+}
+
+extern "C" int am_count_flags(const int32_t *d_col_present, int ncols, const int32_t *d_row_sum, int64_t n_contigs,
+                              int32_t *d_flags, void *stream) {
+  if (!d_col_present || !d_flags || ncols < 1 || n_contigs < 0 || (n_contigs > 0 && !d_row_sum))
+    return am::fail(AM_EINVAL, "am_count_flags: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  AM_CUDA(cudaMemsetAsync(d_flags, 0x7f, 2 * sizeof(int32_t), st));
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_contigs + 255) / 256, 296));
+  count_flags_kernel<<<grid, 256, 0, st>>>(d_col_present, ncols, d_row_sum, n_contigs, d_flags);
+  AM_LAUNCHED("count_flags_kernel");
   return AM_OK;
 }
 

@@ -265,6 +265,31 @@ def gram_planes(planes, n: int, D: int, e, out=None, slices: int = GRAM_SLICES):
     return out
 
 
+def cov_finish(G, colsum, center, n_t):
+    """In place: G <- (G - n (mu - center)(mu - center)^T) / (n - 1); returns mu = colsum / n."""
+    import torch
+
+    dev = G.device
+    D = G.shape[0]
+    with torch.cuda.device(dev):
+        mu = torch.empty(D, dtype=torch.float64, device=dev)
+        L.check(L.lib.am_cov_finish(L.t_ptr(G), D, L.t_ptr(colsum), L.t_ptr(center), L.t_ptr(n_t), L.t_ptr(mu),
+                                    L.stream_ptr(dev)))
+    return mu
+
+
+def count_flags(present, row_sum, n: int):
+    """int32[2] on the device: [min(col_present), min(row_sum)]."""
+    import torch
+
+    dev = present.device
+    with torch.cuda.device(dev):
+        flags = torch.empty(2, dtype=torch.int32, device=dev)
+        L.check(L.lib.am_count_flags(L.t_ptr(present), int(present.numel()), L.t_ptr(row_sum), int(n), L.t_ptr(flags),
+                                     L.stream_ptr(dev)))
+    return flags
+
+
 def eigh_desc(A, max_sweeps: int = 30, tol: float = 0.0):
     """All eigenpairs of symmetric A, descending; rows of the returned matrix are
     eigenvectors with sklearn's svd_flip(u_based_decision=False) sign."""

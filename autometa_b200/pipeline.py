@@ -40,7 +40,8 @@ def _fit_project(packed, counts, method, n_components, row_index, col_index, gro
     Dk = D if col_index is None else int(col_index.numel())
     Dout = Dk - 1 if method == "ilr" else Dk
     n_out = counts.shape[0] if row_index is None else int(row_index.numel())
-    cs = torch.zeros(Dout, dtype=torch.float64, device=dev)
+    zbuf = torch.zeros(2 * Dout + D + 2, dtype=torch.float64, device=dev)  # cs | cm | sample sums + count
+    cs = zbuf[:Dout]
     fused = method in ("am_clr", "clr") and D == 512 and col_index is None and n_out > 0
     planes = e = center = None
     if fused:
@@ -51,31 +52,37 @@ def _fit_project(packed, counts, method, n_components, row_index, col_index, gro
         ns = int(sample.numel())
         if row_index is not None:
             sample = row_index[sample]
-        cs_s = torch.zeros(D + 1, dtype=torch.float64, device=dev)
-        cs_s[D] = float(ns)
+        cs_s = zbuf[2 * Dout : 2 * Dout + D + 1]
         _dev.normalize_counts(counts, method, sample, None, colsum=cs_s[:D])
         if distributed:
+            cs_s[D] = float(ns)
             _dist.allreduce_sum_([cs_s], group)
-        center = cs_s[:D] / cs_s[D]
+            center = cs_s[:D] / cs_s[D]
+        else:
+            center = cs_s[:D] * (1.0 / ns)
         if method == "am_clr":
-            bound = float(np.log1p(float(packed.lengths.max()) if packed.n_contigs else 1.0))
+            bound = packed._plans.get("log1p_maxlen")
+            if bound is None:
+                bound = float(np.log1p(float(packed.lengths.max()) if packed.n_contigs else 1.0))
+                packed._plans["log1p_maxlen"] = bound
         else:
             bound = float(2.0 * np.log(D) + 1.0)
         e, sc = _dev.plane_scales(center, None, bound)
         X, planes = _dev.normalize_planes(counts, method, row_index, center, sc, cs)
     elif method == "ilr" or Dout > 1024:
         X = _dev.normalize_counts(counts, method, row_index, col_index)
-        cm = torch.zeros(Dout, dtype=torch.float64, device=dev)
+        cm = zbuf[Dout : 2 * Dout]
         _dev.colstats(X, cs, cm)
     else:
-        cm = torch.zeros(Dout, dtype=torch.float64, device=dev)  # column max|x|: fixed-point scale
+        cm = zbuf[Dout : 2 * Dout]  # column max|x|: fixed-point scale
         X = _dev.normalize_counts(counts, method, row_index, col_index, colsum=cs, colmaxabs=cm)
     mark("normalise")
-    n_t = torch.tensor([float(X.shape[0])], dtype=torch.float64, device=dev)
+    n_t = torch.full((1,), float(X.shape[0]), dtype=torch.float64, device=dev)
     if distributed:
         _dist.allreduce_sum_([cs, n_t], group)
-    mu = cs / n_t
+    mu = None
     if not fused and X.shape[0] > 0:
+        mu = cs / n_t
         # generic route to the same tensor-core kernels: quantise the fp64 matrix about its exact mean
         center = mu
         e, sc = _dev.plane_scales(center, cm)
@@ -84,10 +91,9 @@ def _fit_project(packed, counts, method, n_components, row_index, col_index, gro
         (Dout, Dout), dtype=torch.float64, device=dev)
     if distributed:
         _dist.allreduce_sum_([G], group)
-    if fused:
-        dlt = mu - center
-        G = G - n_t * torch.outer(dlt, dlt)
-    C = G / (n_t - 1.0)
+    # mu and C = (G - n (mu - centre)(mu - centre)^T) / (n - 1) in one launch (in place on G)
+    mu = _dev.cov_finish(G, cs, center if fused else None, n_t)
+    C = G
     mark("gram")
     P = min(n_components, Dout)
     evals, comps, total = _dev.eigh_topk(C, P)
@@ -122,7 +128,7 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
         if distributed:
             _dist.allreduce_max_(present, group)
         if packed.n_contigs:
-            flags = torch.stack([present.min(), row_sum.min()])
+            flags = _dev.count_flags(present, row_sum, packed.n_contigs)
         else:
             flags = torch.ones(2, dtype=torch.int32, device=dev)
         res = None

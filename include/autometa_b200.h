@@ -201,6 +201,15 @@ int am_colsum(const double *d_X, int64_t n_rows, int D, double *d_colsum, void *
 int64_t am_colstats_work_bytes(int D);
 int am_colstats(const double *d_X, int64_t n_rows, int D, double *d_colsum, double *d_colmaxabs,
                 void *d_work, void *stream);
+/* Covariance from the Gram in one launch (_pca.py:604-610): mu[D] = colsum / n and, in place,
+ * G <- (G - n (mu - centre)(mu - centre)^T) / (n - 1); d_center may be NULL when G is already about
+ * the mean; d_n points to the (possibly all-reduced) row count in device memory. */
+int am_cov_finish(double *d_G, int D, const double *d_colsum, const double *d_center,
+                  const double *d_n, double *d_mu, void *stream);
+/* flags[0] = min(col_present), flags[1] = min(row_sum): am_clr's all-NA column / row tests
+ * (kmers.py:369) in one launch. */
+int am_count_flags(const int32_t *d_col_present, int ncols, const int32_t *d_row_sum,
+                   int64_t n_contigs, int32_t *d_flags, void *stream);
 int64_t am_gram_work_bytes(int D);
 int am_gram(const double *d_X, int64_t n_rows, int D, const double *d_mu,
             double *d_G, void *d_work, void *stream);
