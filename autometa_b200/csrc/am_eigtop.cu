@@ -663,7 +663,9 @@ __device__ void orthonormalise_rows(double *Y, double *G, int n, int np, int P, 
 }
 
 __global__ void __launch_bounds__(CT)
-cholqr_kernel(double *__restrict__ Yg, int n, int np, int P, int y_in_smem, int have_m) {
+cholqr_kernel(double *__restrict__ Yg, int n, int np, int P, int y_in_smem, int have_m,
+              const int *__restrict__ mode) {
+  if (mode && mode[0] != 2) return;  // the multi-CTA fast path already handled (or had nothing to do)
   extern __shared__ double sm[];
   double *G = sm;                 // P x P (+ a second P x P buffer when have_m)
   double *Ys = sm + (have_m ? 2 : 1) * P * P;    // P x np when it fits (the 50 x 512 case: 200 KB)
@@ -675,6 +677,81 @@ cholqr_kernel(double *__restrict__ Yg, int n, int np, int P, int y_in_smem, int 
     for (int q = threadIdx.x; q < P * np; q += CT) Yg[q] = Ys[q];
   } else {
     orthonormalise_rows(Yg, G, n, np, P, have_m != 0);
+  }
+}
+
+// ---- multi-CTA fast path of the re-orthonormalisation (the common case: eigenvalues separated
+// well enough that the inverse-iteration vectors are orthogonal to 1e-5).  Three small launches
+// spread over many SMs instead of one CTA: Gram of the P vectors, M = I - E/2 + 3E^2/8 (second-order
+// Loewdin, error O(E^3)), Y <- M Y.  mode[0]: 0 = already orthonormal, 1 = M is valid, 2 = clustered
+// eigenvalues -> the single-CTA CholeskyQR2 kernel takes over.
+__global__ void __launch_bounds__(128)
+ortho_gram_kernel(const double *__restrict__ Y, int n, int np, int P, double *__restrict__ G) {
+  const int a = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = warp; b <= a; b += 4) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = lane; i < n; i += 64) {
+      s0 = fma(__ldg(Y + (size_t)a * np + i), __ldg(Y + (size_t)b * np + i), s0);
+      if (i + 32 < n) s1 = fma(__ldg(Y + (size_t)a * np + i + 32), __ldg(Y + (size_t)b * np + i + 32), s1);
+    }
+    const double s = warp_sum(s0 + s1);
+    if (lane == 0) { G[a * P + b] = s; G[b * P + a] = s; }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+ortho_m_kernel(const double *__restrict__ G, int P, double *__restrict__ M, int *__restrict__ mode) {
+  extern __shared__ double sm[];
+  double *E = sm;  // P x P
+  __shared__ double s_em[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double em = 0.0;
+  for (int q = tid; q < P * P; q += 1024) {
+    const double e = G[q] - ((q / P == q % P) ? 1.0 : 0.0);
+    E[q] = e;
+    em = fmax(em, fabs(e));
+  }
+  for (int o = 16; o > 0; o >>= 1) em = fmax(em, __shfl_xor_sync(FULL, em, o));
+  if (lane == 0) s_em[warp] = em;
+  __syncthreads();
+  em = 0.0;
+  for (int w = 0; w < 32; ++w) em = fmax(em, s_em[w]);
+  const int md = !(em > 4e-16) ? 0 : (em <= 1e-5 ? 1 : 2);
+  if (tid == 0) mode[0] = md;
+  if (md != 1) return;
+  for (int q = tid; q < P * P; q += 1024) {
+    const int a = q / P, b = q % P;
+    double e2 = 0.0;
+    for (int m = 0; m < P; ++m) e2 = fma(E[a * P + m], E[m * P + b], e2);
+    M[q] = (a == b ? 1.0 : 0.0) - 0.5 * E[q] + 0.375 * e2;
+  }
+}
+
+constexpr int OA_COLS = 64;  // element columns per CTA
+__global__ void __launch_bounds__(256)
+ortho_apply_kernel(double *__restrict__ Y, int n, int np, int P, const double *__restrict__ M,
+                   const int *__restrict__ mode) {
+  if (mode[0] != 1) return;
+  extern __shared__ double sm[];
+  double *Ms = sm;                 // P x P
+  double *Yt = sm + P * P;         // P x OA_COLS tile
+  const int i0 = blockIdx.x * OA_COLS, tid = threadIdx.x;
+  for (int q = tid; q < P * P; q += 256) Ms[q] = M[q];
+  for (int q = tid; q < P * OA_COLS; q += 256) {
+    const int b = q / OA_COLS, i = i0 + q % OA_COLS;
+    Yt[q] = (i < n) ? Y[(size_t)b * np + i] : 0.0;
+  }
+  __syncthreads();
+  // thread = one column i and a strided set of rows a
+  const int ci = tid % OA_COLS, a0 = tid / OA_COLS;  // 4 row groups
+  for (int a = a0; a < P; a += 256 / OA_COLS) {
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int b = 0; b + 1 < P; b += 2) {
+      acc0 = fma(Ms[a * P + b], Yt[b * OA_COLS + ci], acc0);
+      acc1 = fma(Ms[a * P + b + 1], Yt[(b + 1) * OA_COLS + ci], acc1);
+    }
+    if (P & 1) acc0 = fma(Ms[a * P + P - 1], Yt[(P - 1) * OA_COLS + ci], acc0);
+    if (i0 + ci < n) Y[(size_t)a * np + i0 + ci] = acc0 + acc1;
   }
 }
 
@@ -716,13 +793,15 @@ backtransform_kernel(const double *__restrict__ V, const double *__restrict__ ta
     for (int m = 0; m < ZL; ++m) { va[m] = na[m]; vb[m] = nb[m]; }
     if (k - 2 >= 0) load_pair(k - 2, na, nb);
     const double ta = __ldg(tau + k), tb = (k >= 1) ? __ldg(tau + k - 1) : 0.0;
-    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    // three interleaved partial sums per dot product: the fp64 FMA chain is the latency here
+    double p1[3] = {0.0, 0.0, 0.0}, p2[3] = {0.0, 0.0, 0.0}, p3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int m = 0; m < ZL; ++m) {
-      s1 = fma(va[m], z[m], s1);
-      s2 = fma(vb[m], z[m], s2);
-      s3 = fma(vb[m], va[m], s3);
+      p1[m % 3] = fma(va[m], z[m], p1[m % 3]);
+      p2[m % 3] = fma(vb[m], z[m], p2[m % 3]);
+      p3[m % 3] = fma(vb[m], va[m], p3[m % 3]);
     }
+    double s1 = (p1[0] + p1[1]) + p1[2], s2 = (p2[0] + p2[1]) + p2[2], s3 = (p3[0] + p3[1]) + p3[2];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       s1 += __shfl_xor_sync(FULL, s1, o);
@@ -763,7 +842,7 @@ backtransform_kernel(const double *__restrict__ V, const double *__restrict__ ta
 inline int round_up32(int x) { return (x + 31) & ~31; }
 
 struct TopWork {
-  double *V, *tau, *d, *e, *lam, *Y, *dbg;
+  double *V, *tau, *d, *e, *lam, *Y, *dbg, *orth;
 };
 
 int64_t carve_top(void *base, int n, int P, TopWork *w) {
@@ -783,6 +862,7 @@ int64_t carve_top(void *base, int n, int P, TopWork *w) {
   t.lam = take((int64_t)PMAX * 8);
   t.Y = take((int64_t)P * np * 8);
   t.dbg = take(64);
+  t.orth = take(((int64_t)2 * P * P + 8) * 8);
   if (w) *w = t;
   return off;
 }
@@ -850,7 +930,23 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
     if (smem + (size_t)P * np * sizeof(double) <= 227 * 1024) { smem += (size_t)P * np * sizeof(double); y_in_smem = 1; }
     if (smem > 48 * 1024)
       AM_CUDA(cudaFuncSetAttribute(cholqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cholqr_kernel<<<1, CT, smem, st>>>(w.Y, n, np, P, y_in_smem, have_m);
+    // fast path over many SMs; the single-CTA CholeskyQR2 only runs for clustered eigenvalues
+    double *Gg = w.orth, *Mg = w.orth + (size_t)P * P;
+    int *mode = (int *)(w.orth + 2 * (size_t)P * P);
+    ortho_gram_kernel<<<P, 128, 0, st>>>(w.Y, n, np, P, Gg);
+    AM_LAUNCHED("ortho_gram_kernel");
+    if ((size_t)P * P * sizeof(double) > 48 * 1024)
+      AM_CUDA(cudaFuncSetAttribute(ortho_m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)P * P * sizeof(double))));
+    ortho_m_kernel<<<1, 1024, (size_t)P * P * sizeof(double), st>>>(Gg, P, Mg, mode);
+    AM_LAUNCHED("ortho_m_kernel");
+    {
+      const size_t sm2 = ((size_t)P * P + (size_t)P * OA_COLS) * sizeof(double);
+      if (sm2 > 48 * 1024)
+        AM_CUDA(cudaFuncSetAttribute(ortho_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+      ortho_apply_kernel<<<(n + OA_COLS - 1) / OA_COLS, 256, sm2, st>>>(w.Y, n, np, P, Mg, mode);
+      AM_LAUNCHED("ortho_apply_kernel");
+    }
+    cholqr_kernel<<<1, CT, smem, st>>>(w.Y, n, np, P, y_in_smem, have_m, mode);
     AM_LAUNCHED("cholqr_kernel");
   }
   // 5. back-transformation
