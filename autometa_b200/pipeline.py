@@ -180,13 +180,57 @@ class HostFeaturiser:
         self.exc_cap = 0
 
     def run(self, group=None, distributed: bool = False):
+        """One assembly, strictly serial: H2D -> pack -> featurise -> D2H (latency path)."""
         import torch
 
         with torch.cuda.device(self.dev):
             self.d_seq[: self.total_bp].copy_(self.h_seq, non_blocking=True)
             self.d_off.copy_(self.h_off, non_blocking=True)
             self.d_starts.copy_(self.h_starts, non_blocking=True)
-            packed = pack_device_arrays(self.d_seq, self.d_off, self.d_starts, self.n, self.total,
+            return self._compute(self.d_seq, self.d_off, self.d_starts, group, distributed)
+
+    def run_many(self, n_steps: int, group=None, distributed: bool = False):
+        """``n_steps`` assemblies back to back with double buffering: the H2D copy of step i+1 runs on
+        a copy stream while step i is packed and featurised.  Every step still copies its input from
+        pinned host memory and reads its scores back; only the PCIe time of the NEXT step is hidden
+        behind the compute of the current one.  Returns the last step's host results."""
+        import torch
+
+        with torch.cuda.device(self.dev):
+            if getattr(self, "d_seq2", None) is None:
+                self.d_seq2 = torch.empty_like(self.d_seq)
+                self.d_off2 = torch.empty_like(self.d_off)
+                self.d_starts2 = torch.empty_like(self.d_starts)
+                self.copy_stream = torch.cuda.Stream(device=self.dev)
+                self.ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+            bufs = [(self.d_seq, self.d_off, self.d_starts), (self.d_seq2, self.d_off2, self.d_starts2)]
+            cur = torch.cuda.current_stream(self.dev)
+
+            def submit(slot):
+                # ALL host->device traffic of a step goes through the copy stream: a small copy queued on
+                # the compute stream would sit behind the next step's 1 GB transfer on the same DMA engine
+                self.copy_stream.wait_stream(cur)  # the buffer's previous consumer has been queued before
+                with torch.cuda.stream(self.copy_stream):
+                    bufs[slot][0][: self.total_bp].copy_(self.h_seq, non_blocking=True)
+                    bufs[slot][1].copy_(self.h_off, non_blocking=True)
+                    bufs[slot][2].copy_(self.h_starts, non_blocking=True)
+                    self.ev_copied[slot].record(self.copy_stream)
+
+            out = None
+            submit(0)
+            for i in range(n_steps):
+                slot = i & 1
+                cur.wait_event(self.ev_copied[slot])
+                if i + 1 < n_steps:
+                    submit((i + 1) & 1)  # buffer (i+1)&1 was last used by step i-1, which has completed
+                out = self._compute(bufs[slot][0], bufs[slot][1], bufs[slot][2], group, distributed)
+            return out
+
+    def _compute(self, d_seq, d_off, d_starts, group, distributed):
+        import torch
+
+        with torch.cuda.device(self.dev):
+            packed = pack_device_arrays(d_seq, d_off, d_starts, self.n, self.total,
                                         self.lengths, self.starts_h, self.total_bp, exc_capacity=self.exc_cap)
             self.exc_cap = max(self.exc_cap, packed.n_exc + 1024)
             if getattr(self, "_plans", None):

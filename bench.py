@@ -385,17 +385,31 @@ def main():
         if distributed:
             dist.barrier()
         e_steps = max(3, min(args.steps, 10))
+        # (a) serial latency of one call; (b) throughput of back-to-back calls with the next step's H2D
+        # copy overlapping the current step's compute (double buffering; every step still copies its
+        # input from pinned host memory and reads its scores back inside the timed region)
         t0 = time.perf_counter()
-        for _ in range(e_steps):
+        for _ in range(3):
             hf.run(distributed=distributed)
+        torch.cuda.synchronize()
+        lat_ms = (time.perf_counter() - t0) / 3 * 1e3
+        hf.run_many(2, distributed=distributed)
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        t0 = time.perf_counter()
+        hf.run_many(e_steps, distributed=distributed)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if distributed:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e_ms = float(dt.item()) / e_steps * 1e3
         e2e = {"value": job_bp / (e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e_ms,
+               "serial_latency_ms": lat_ms, "steps": e_steps,
                "h2d_bytes_per_step": int(hf.h2d_bytes), "d2h_bytes_per_step": int(hf.d2h_bytes),
-               "path": "pinned host ASCII -> H2D -> am_pack_device -> count -> am_clr -> PCA -> D2H scores"}
+               "path": "pinned host ASCII -> H2D -> am_pack_device -> count -> am_clr -> PCA -> D2H scores; "
+                       "back-to-back steps, the H2D copy of step i+1 overlaps the compute of step i "
+                       "(PCIe-bound: 1 byte per bp)"}
 
     if rank == 0:
         hbm, bf16, how = measured_peaks()
