@@ -756,58 +756,65 @@ ortho_apply_kernel(double *__restrict__ Y, int n, int np, int P, const double *_
 }
 
 // ------------------------------------------------------------------ 5. back-transformation + sign + output
-// One WARP per eigenvector (no block barrier in the loop), z in registers (lane owns rows lane + 32 m),
-// and TWO reflectors per reduction round: for H_b H_a z with a = k, b = k-1,
+// One CTA of 4 warps per eigenvector, z in registers (thread owns rows tid + 128 m), one barrier per
+// round, and TWO reflectors per reduction round: for H_b H_a z with a = k, b = k-1,
 //   alpha = v_a.z,  beta = v_b.(z - tau_a alpha v_a) = v_b.z - tau_a alpha (v_b.v_a),
-// so the three dot products v_a.z, v_b.z, v_b.v_a are reduced together (one shuffle tree), then
+// so the three dot products v_a.z, v_b.z, v_b.v_a are reduced together (one shuffle tree + one
+// shared-memory exchange), then
 // z -= tau_a alpha v_a + tau_b beta v_b.  The reflector pair of the next round is prefetched.
-constexpr int KT = 128;            // 4 warps = 4 eigenvectors per CTA
-constexpr int ZL = SMEM_N_MAX / 32;  // rows per lane
+constexpr int KT = 128;              // one CTA (4 warps) per eigenvector
+constexpr int ZL = (SMEM_N_MAX + KT - 1) / KT;  // rows per thread
 __global__ void __launch_bounds__(KT)
 backtransform_kernel(const double *__restrict__ V, const double *__restrict__ tau, int n, int np, int P,
                      const double *__restrict__ Y, const double *__restrict__ lam,
                      double *__restrict__ evals, double *__restrict__ evecs) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j = blockIdx.x * (KT / 32) + warp;
-  if (j >= P) return;
+  __shared__ double red[4][3][KT / 32];  // rotating slots x {v_a.z, v_b.z, v_b.v_a} x warps
+  __shared__ double s_best[KT / 32], s_val[KT / 32];
+  __shared__ int s_idx[KT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = blockIdx.x;
   double z[ZL], va[ZL], vb[ZL], na[ZL], nb[ZL];
 #pragma unroll
   for (int m = 0; m < ZL; ++m) {
-    const int i = lane + 32 * m;
+    const int i = tid + KT * m;
     z[m] = (i < np) ? Y[(size_t)j * np + i] : 0.0;
     na[m] = 0.0; nb[m] = 0.0;
   }
   auto load_pair = [&](int k, double (&xa)[ZL], double (&xb)[ZL]) {
-    // reflectors k and k-1 (k-1 < 0 -> zero vector, tau treated as 0)
 #pragma unroll
     for (int m = 0; m < ZL; ++m) {
-      const int i = lane + 32 * m;
+      const int i = tid + KT * m;
       xa[m] = (i < np && k >= 0) ? __ldg(V + (size_t)k * np + i) : 0.0;
       xb[m] = (i < np && k >= 1) ? __ldg(V + (size_t)(k - 1) * np + i) : 0.0;
     }
   };
-  int k = n - 3;
+  int k = n - 3, slot = 0;
   if (k >= 0) load_pair(k, na, nb);
   for (; k >= 0; k -= 2) {
 #pragma unroll
     for (int m = 0; m < ZL; ++m) { va[m] = na[m]; vb[m] = nb[m]; }
     if (k - 2 >= 0) load_pair(k - 2, na, nb);
     const double ta = __ldg(tau + k), tb = (k >= 1) ? __ldg(tau + k - 1) : 0.0;
-    // three interleaved partial sums per dot product: the fp64 FMA chain is the latency here
-    double p1[3] = {0.0, 0.0, 0.0}, p2[3] = {0.0, 0.0, 0.0}, p3[3] = {0.0, 0.0, 0.0};
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
     for (int m = 0; m < ZL; ++m) {
-      p1[m % 3] = fma(va[m], z[m], p1[m % 3]);
-      p2[m % 3] = fma(vb[m], z[m], p2[m % 3]);
-      p3[m % 3] = fma(vb[m], va[m], p3[m % 3]);
+      s1 = fma(va[m], z[m], s1);
+      s2 = fma(vb[m], z[m], s2);
+      s3 = fma(vb[m], va[m], s3);
     }
-    double s1 = (p1[0] + p1[1]) + p1[2], s2 = (p2[0] + p2[1]) + p2[2], s3 = (p3[0] + p3[1]) + p3[2];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       s1 += __shfl_xor_sync(FULL, s1, o);
       s2 += __shfl_xor_sync(FULL, s2, o);
       s3 += __shfl_xor_sync(FULL, s3, o);
     }
+    double(*r)[KT / 32] = red[slot & 3];
+    ++slot;
+    if (lane == 0) { r[0][warp] = s1; r[1][warp] = s2; r[2][warp] = s3; }
+    __syncthreads();
+    s1 = (r[0][0] + r[0][1]) + (r[0][2] + r[0][3]);
+    s2 = (r[1][0] + r[1][1]) + (r[1][2] + r[1][3]);
+    s3 = (r[2][0] + r[2][1]) + (r[2][2] + r[2][3]);
     const double ca = ta * s1;
     const double cb = tb * fma(-ca, s3, s2);
 #pragma unroll
@@ -818,7 +825,7 @@ backtransform_kernel(const double *__restrict__ V, const double *__restrict__ ta
   int bidx = 0;
 #pragma unroll
   for (int m = 0; m < ZL; ++m) {
-    const int i = lane + 32 * m;
+    const int i = tid + KT * m;
     if (i < n) {
       const double a = fabs(z[m]);
       if (a > best) { best = a; bidx = i; bval = z[m]; }
@@ -830,13 +837,18 @@ backtransform_kernel(const double *__restrict__ V, const double *__restrict__ ta
     const double ov = __shfl_xor_sync(FULL, bval, o);
     if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; bval = ov; }
   }
+  if (lane == 0) { s_best[warp] = best; s_idx[warp] = bidx; s_val[warp] = bval; }
+  __syncthreads();
+  best = s_best[0]; bidx = s_idx[0]; bval = s_val[0];
+  for (int w = 1; w < KT / 32; ++w)
+    if (s_best[w] > best || (s_best[w] == best && s_idx[w] < bidx)) { best = s_best[w]; bidx = s_idx[w]; bval = s_val[w]; }
   const double sgn = bval < 0.0 ? -1.0 : 1.0;
 #pragma unroll
   for (int m = 0; m < ZL; ++m) {
-    const int i = lane + 32 * m;
+    const int i = tid + KT * m;
     if (i < n) evecs[(size_t)j * n + i] = sgn * z[m];
   }
-  if (lane == 0) evals[j] = lam[j];
+  if (tid == 0) evals[j] = lam[j];
 }
 
 inline int round_up32(int x) { return (x + 31) & ~31; }
@@ -951,7 +963,7 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
   }
   // 5. back-transformation
   {
-    backtransform_kernel<<<(P + KT / 32 - 1) / (KT / 32), KT, 0, st>>>(w.V, w.tau, n, np, P, w.Y, w.lam, d_evals, d_evecs);
+    backtransform_kernel<<<P, KT, 0, st>>>(w.V, w.tau, n, np, P, w.Y, w.lam, d_evals, d_evecs);
     AM_LAUNCHED("backtransform_kernel");
   }
   return AM_OK;

@@ -22,7 +22,12 @@ namespace {
 constexpr int PJ_M = 128;   // contigs per tile (TMEM lanes)
 constexpr int PJ_N = 64;    // components per accumulator (padded)
 constexpr int PJ_BK = 64;   // columns (bytes) per stage: two K = 32 MMA steps, 64B swizzle
-constexpr int PJ_S = 6;
+constexpr int PJ_S = 6;     // digit planes stored
+constexpr int PJ_W = 4;     // digit pairs multiplied: s + t <= PJ_W (15 pairs, 5 accumulators).  Scores are
+                            // compared at 1e-8 of their range; the dropped pairs weigh <= 2^-40 of the
+                            // leading one (measured error 1e-11 .. 1e-10 of max|score|), unlike the Gram,
+                            // whose error is amplified by 1/gap in the eigenvectors and keeps every pair.
+constexpr int PJ_NP = PJ_W + 1;  // planes actually staged (0 .. PJ_W)
 constexpr int PJ_THREADS = 192;
 constexpr int PJ_A_BYTES = PJ_M * PJ_BK;  // 8192
 constexpr int PJ_B_BYTES = PJ_N * PJ_BK;  // 4096
@@ -92,7 +97,7 @@ project_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   double *__restrict__ scores) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr uint32_t stage_bytes = PJ_S * (PJ_A_BYTES + PJ_B_BYTES);
+  constexpr uint32_t stage_bytes = PJ_NP * (PJ_A_BYTES + PJ_B_BYTES);
   const uint32_t bars = base + PJ_STAGES * stage_bytes;
   const uint32_t bar_full = bars, bar_empty = bars + 8u * PJ_STAGES, bar_accf = bars + 16u * PJ_STAGES,
                  bar_acce = bar_accf + 8u;
@@ -127,8 +132,8 @@ project_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t fb = bar_full + 8u * stage;
           mbar_expect_tx(fb, stage_bytes);
           const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-          const uint32_t sb = sa + PJ_S * PJ_A_BYTES;
-          for (int s = 0; s < PJ_S; ++s) {
+          const uint32_t sb = sa + PJ_NP * PJ_A_BYTES;
+          for (int s = 0; s < PJ_NP; ++s) {
             tma_load_3d(sa + (uint32_t)s * PJ_A_BYTES, &tmA, ks * PJ_BK, tile * PJ_M, s, fb);
             tma_load_3d(sb + (uint32_t)s * PJ_B_BYTES, &tmB, ks * PJ_BK, 0, s, fb);
           }
@@ -150,7 +155,7 @@ project_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(bar_full + 8u * stage, phase);
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-          const uint32_t sb = sa + PJ_S * PJ_A_BYTES;
+          const uint32_t sb = sa + PJ_NP * PJ_A_BYTES;
           for (int kk = 0; kk < PJ_BK / 32; ++kk) {
             for (int i = 0; i < p.n_ops; ++i) {
               // K-major, 64B swizzle: rows of 64 B, 8-row groups 512 B apart; the second K step
@@ -266,7 +271,7 @@ extern "C" int am_project_planes(const int8_t *d_planes, int64_t n_rows, int D, 
   p.n_tiles = (int)((n_rows + PJ_M - 1) / PJ_M);
   p.n_ksteps = (D + PJ_BK - 1) / PJ_BK;
   {
-    const int Sx = PJ_S, dmax = Sx;  // weights 0..5 plus the square term (3,3) of weight 6
+    const int dmax = PJ_W;  // weights 0 .. PJ_W
     int nops = 0;
     bool seen[8] = {false, false, false, false, false, false, false, false};
     auto add_op = [&](int s, int t0, int nt) {
@@ -277,11 +282,10 @@ extern "C" int am_project_planes(const int8_t *d_planes, int64_t n_rows, int D, 
       p.ofirst[nops] = fl;
       ++nops;
     };
-    for (int s = 0; s < Sx; ++s) {
-      int t0 = 0, left = Sx - s;
+    for (int s = 0; s <= PJ_W; ++s) {
+      int t0 = 0, left = PJ_W + 1 - s;
       while (left > 0) { const int nt = std::min(left, 4); add_op(s, t0, nt); t0 += nt; left -= nt; }
     }
-    add_op(Sx / 2, Sx / 2, 1);
     p.n_ops = nops;
     p.n_acc = dmax + 1;
   }
@@ -302,7 +306,7 @@ extern "C" int am_project_planes(const int8_t *d_planes, int64_t n_rows, int D, 
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return am::fail(AM_ECUDA, "am_project_planes: cuTensorMapEncodeTiled failed");
   }
-  const size_t smem = (size_t)PJ_STAGES * PJ_S * (PJ_A_BYTES + PJ_B_BYTES) + 16 * PJ_STAGES + 64 + 1024;
+  const size_t smem = (size_t)PJ_STAGES * PJ_NP * (PJ_A_BYTES + PJ_B_BYTES) + 16 * PJ_STAGES + 64 + 1024;
   AM_CUDA(cudaFuncSetAttribute(project_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(p.n_tiles, am::num_sms());
   project_i8_kernel<<<grid, PJ_THREADS, smem, st>>>(tmA, tmB, p, f, bconst, d_scores);
