@@ -323,7 +323,8 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
 }
 
 // ------------------------------------------------------------------ 2. bisection
-constexpr int BT = 512;  // shifts per round
+constexpr int BT = 256;  // shifts per round (8 bits of the bracket per round; the Sturm recurrence is bound by
+                         // fp64 throughput at 512 shifts and by the dependent FMA chain at 256)
 
 // Number of eigenvalues of T that are < x, from the sign changes of the leading principal minors
 // u_j = (d_j - x) u_{j-1} - e_{j-1}^2 u_{j-2}  (Sturm sequence).  One FMA on the dependent chain per
@@ -508,7 +509,14 @@ invit_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int n
     dd[n - 1] = dcur;
   }
   __syncwarp();
-  for (int i = lane; i < n; i += 32) rdd[i] = 1.0 / dd[i];
+  // back-substitution coefficients pre-multiplied by 1/d_i so that one FMA per row is on the chain:
+  // x_i = b_i/d_i - (du_i/d_i) x_{i+1} - (du2_i/d_i) x_{i+2}
+  for (int i = lane; i < n; i += 32) {
+    const double r = 1.0 / dd[i];
+    rdd[i] = r;
+    du[i] *= r;
+    du2[i] *= r;
+  }
   __syncwarp();
   // dstein-style: start from a vector of norm ~ eps |T|, stop once the solve has grown it to O(1)
   // (the shift is an eigenvalue to working precision, so one or two solves suffice)
@@ -530,7 +538,8 @@ invit_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int n
       double x1 = cur * rdd[n - 1], x2 = 0.0;
       b[n - 1] = x1;
       for (int i = n - 2; i >= 0; --i) {
-        const double xi = (b[i] - du[i] * x1 - du2[i] * x2) * rdd[i];
+        const double t = fma(-du2[i], x2, b[i] * rdd[i]);  // x2 is one step old: off the chain
+        const double xi = fma(-du[i], x1, t);
         b[i] = xi;
         x2 = x1;
         x1 = xi;
