@@ -308,6 +308,7 @@ def eigh_desc(A, max_sweeps: int = 30, tol: float = 0.0):
     return evals, evecs
 
 
+_topk_state: Dict[str, bool] = {}
 TOPK_MAX_D = 576
 TOPK_MAX_P = 128
 
@@ -321,7 +322,7 @@ def eigh_topk(A, P: int):
 
     dev = A.device
     D = A.shape[0]
-    if not (3 <= D <= TOPK_MAX_D and 1 <= P <= min(D, TOPK_MAX_P)):
+    if _topk_state.get("disabled") or not (3 <= D <= TOPK_MAX_D and 1 <= P <= min(D, TOPK_MAX_P)):
         evals, evecs = eigh_desc(A)
         return evals[:P].contiguous(), evecs[:P].contiguous(), torch.clamp(evals, min=0.0).sum().reshape(1)
     with torch.cuda.device(dev):
@@ -329,10 +330,21 @@ def eigh_topk(A, P: int):
         evecs = torch.empty((P, D), dtype=torch.float64, device=dev)
         trace = torch.empty(1, dtype=torch.float64, device=dev)
         work = _work(dev, L.lib.am_eigh_topk_work_bytes(D, P), "eigtop")
-        L.check(
-            L.lib.am_eigh_topk(L.t_ptr(A), D, P, L.t_ptr(evals), L.t_ptr(evecs), L.t_ptr(trace),
-                               L.t_ptr(work), L.stream_ptr(dev))
-        )
+        rc = L.lib.am_eigh_topk(L.t_ptr(A), D, P, L.t_ptr(evals), L.t_ptr(evecs), L.t_ptr(trace),
+                                L.t_ptr(work), L.stream_ptr(dev))
+        if rc == L.AM_ECUDA and not _topk_state.get("disabled"):
+            # e.g. a 16-CTA cluster cannot be scheduled on this part: use the device Jacobi solver
+            # from now on (still a CUDA path; there is no CPU fallback)
+            import warnings
+
+            warnings.warn("am_eigh_topk unavailable (%s); using am_eigh" % L.lib.am_last_error().decode(errors="replace"))
+            _topk_state["disabled"] = True
+        elif rc != L.AM_OK:
+            L.check(rc)
+        if _topk_state.get("disabled"):
+            evals_all, evecs_all = eigh_desc(A)
+            return (evals_all[:P].contiguous(), evecs_all[:P].contiguous(),
+                    torch.clamp(evals_all, min=0.0).sum().reshape(1))
     return evals, evecs, trace
 
 

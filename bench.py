@@ -287,6 +287,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--norm", default="am_clr", choices=["am_clr", "clr", "ilr"],
+                    help="normalisation (BASELINE.json configs[4] = ilr with --contigs 1000000 --bp 5000000000 on 8 GPUs "
+                         "under --scaling strong)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -326,7 +329,7 @@ def main():
     stages = ["count", "normalise", "gram", "eigh", "project"]
 
     def run_step(marks=None):
-        return pipeline.featurise(packed, K, "am_clr", NCOMP, distributed=distributed, keep=False, marks=marks)
+        return pipeline.featurise(packed, K, args.norm, NCOMP, distributed=distributed, keep=False, marks=marks)
 
     # clocks are sampled from the first warm-up step to the end of the timed region (nvidia-smi needs
     # ~0.3 s to start and samples every 100 ms, so a short timed region alone could fall between samples)
@@ -378,7 +381,7 @@ def main():
     # ---- end to end from host buffers
     e2e = None
     if not args.no_e2e:
-        hf = pipeline.HostFeaturiser(asm, device=dev, k=K, method="am_clr", n_components=NCOMP)
+        hf = pipeline.HostFeaturiser(asm, device=dev, k=K, method=args.norm, n_components=NCOMP)
         for _ in range(2):
             hf.run(distributed=distributed)
         torch.cuda.synchronize()
@@ -475,9 +478,9 @@ def main():
             "scaling": args.scaling, "vs_baseline": None, "dtype": DTYPE,
             "data": "synthetic",
             "config": {
-                "workload": f"C2: 5-mer count + am_clr + PCA(50), {shard_n} contigs / {shard_bp / 1e9:.3f} Gbp per GPU "
+                "workload": f"C2: 5-mer count + {args.norm} + PCA(50), {shard_n} contigs / {shard_bp / 1e9:.3f} Gbp per GPU "
                             f"({job_bp / 1e9:.3f} Gbp job), seeded synthetic assembly",
-                "k": K, "norm": "am_clr", "pca_dimensions": NCOMP,
+                "k": K, "norm": args.norm, "pca_dimensions": NCOMP,
                 "parallelism": f"contigs sharded by bp over {world} GPU(s); NCCL all-reduce of column presence, "
                                "column sums and the 512x512 Gram only",
                 "l2": "inputs larger than L2 (0.25 GB codes, 0.41 GB counts, 0.82 GB features per step); no flush",
