@@ -60,12 +60,14 @@ __global__ void bucket_scatter_kernel(const double *__restrict__ X, int n, int F
                                       const unsigned *__restrict__ bucket_of,
                                       const unsigned *__restrict__ bucket_start,
                                       unsigned *__restrict__ fill, int *__restrict__ sorted_idx,
-                                      double *__restrict__ sorted_x) {
+                                      double *__restrict__ sorted_x, const int *__restrict__ parent,
+                                      int *__restrict__ sorted_root) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned b = bucket_of[i];
   const unsigned pos = bucket_start[b] + atomicAdd(fill + b, 1u);
   sorted_idx[pos] = i;
+  sorted_root[pos] = parent[i];  // root at the start of the step (the forest is flat between steps)
   for (int d = 0; d < F; ++d) sorted_x[(int64_t)d * n + pos] = __ldg(X + (int64_t)i * F + d);
 }
 
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(128)
 eps_union_kernel(int n, GridParams gp, double eps2, const unsigned *__restrict__ bucket_start,
                  const int *__restrict__ sorted_idx, const double *__restrict__ sorted_x,
                  const int *__restrict__ rmin_inv, const int *__restrict__ rmax,
-                 int *__restrict__ parent) {
+                 const int *__restrict__ sorted_root, int *__restrict__ parent) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= n) return;
   const int F = gp.F;
@@ -140,6 +142,9 @@ eps_union_kernel(int n, GridParams gp, double eps2, const unsigned *__restrict__
     if (__ldg(rmax + b) == myroot0 && 0x7fffffff - __ldg(rmin_inv + b) == myroot0) continue;  // nothing to merge
     const unsigned beg = bucket_start[b], end = bucket_start[b + 1];
     for (unsigned j = beg; j < end; ++j) {
+      // already in my component when the step began: nothing to merge, skip the distance test
+      // (4 sequential bytes instead of 24 + the arithmetic; most candidates at large eps)
+      if (__ldg(sorted_root + j) == myroot0) continue;
       const int other = sorted_idx[j];
       if (other >= me) continue;  // each unordered pair once, from its larger row
       double dist = 0.0;
@@ -216,6 +221,7 @@ struct Work {
   int *root_of_label;      // n
   int *rmin_inv;           // nb
   int *rmax;               // nb
+  int *sorted_root;        // n
   unsigned *scan_tmp;      // scan_tmp_words(max(n, nb))
 };
 
@@ -242,6 +248,7 @@ int64_t carve(void *base, int64_t n, Work *w) {
   t.root_of_label = (int *)take(n * 4);
   t.rmin_inv = (int *)take((int64_t)nb * 4);
   t.rmax = (int *)take((int64_t)nb * 4);
+  t.sorted_root = (int *)take(n * 4);
   t.scan_tmp = (unsigned *)take(am::scan_tmp_words(std::max<int64_t>(n + 1, nb + 1)) * 4);
   if (w) *w = t;
   return off;
@@ -296,14 +303,14 @@ extern "C" int am_eps_union(const double *d_X, int64_t n_points, int F, double e
   am::g_launches.fetch_add(am::exclusive_scan(w.counts, w.bucket_start, (int)nb, w.scan_tmp, st) - 1);
   AM_LAUNCHED("exclusive_scan");
   bucket_scatter_kernel<<<blocks, 256, 0, st>>>(d_X, n, F, w.bucket_of, w.bucket_start, w.fill,
-                                                w.sorted_idx, w.sorted_x);
+                                                w.sorted_idx, w.sorted_x, d_parent, w.sorted_root);
   AM_LAUNCHED("bucket_scatter_kernel");
   AM_CUDA(cudaMemsetAsync(w.rmin_inv, 0, (size_t)nb * 4, st));
   AM_CUDA(cudaMemsetAsync(w.rmax, 0xFF, (size_t)nb * 4, st));
   bucket_roots_kernel<<<blocks, 256, 0, st>>>(n, w.bucket_of, d_parent, w.rmin_inv, w.rmax);
   AM_LAUNCHED("bucket_roots_kernel");
   eps_union_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, gp, eps * eps, w.bucket_start, w.sorted_idx,
-                                                    w.sorted_x, w.rmin_inv, w.rmax, d_parent);
+                                                    w.sorted_x, w.rmin_inv, w.rmax, w.sorted_root, d_parent);
   AM_LAUNCHED("eps_union_kernel");
   return AM_OK;
 }
