@@ -59,6 +59,7 @@ class PackedAssembly:
     starts: "torch.Tensor"  # int64 [N] device
     n_exc: int = 0
     ids: Optional[List[str]] = None
+    gc_content: Optional["torch.Tensor"] = None  # fp64 [N] percent, when packed with gc=True
     _plans: dict = field(default_factory=dict)
 
     @property
@@ -66,15 +67,31 @@ class PackedAssembly:
         return self.codes.device
 
 
-def read_fasta(path: str) -> HostAssembly:
-    """Parse a (optionally gzipped) FASTA file; ids = first token of each header,
-    sequences concatenated with case preserved (kmers.py:143-148 semantics)."""
+def read_raw(path: str) -> bytes:
     if not os.path.exists(path):
         raise FileNotFoundError(path)
     opener = gzip.open if path.endswith(".gz") else open
     with opener(path, "rb") as fh:
-        raw = fh.read()
-    return parse_fasta_bytes(raw)
+        return fh.read()
+
+
+def read_fasta(path: str) -> HostAssembly:
+    """Parse a (optionally gzipped) FASTA file; ids = first token of each header,
+    sequences concatenated with case preserved (kmers.py:143-148 semantics)."""
+    return parse_fasta_bytes(read_raw(path))
+
+
+def record_titles(raw: bytes) -> List[bytes]:
+    """Header lines without '>' and trailing whitespace, CR/LF inside replaced by blanks:
+    what Bio.SeqIO's FastaWriter prints for a record that came from its FASTA parser."""
+    buf = np.frombuffer(raw, dtype=np.uint8)
+    gt = np.flatnonzero(buf == ord(">"))
+    gt = gt[(gt == 0) | (buf[np.maximum(gt, 1) - 1] == ord("\n"))]
+    titles = []
+    for p in gt:
+        e = raw.find(b"\n", int(p))
+        titles.append(raw[int(p) + 1 : e if e >= 0 else len(raw)].rstrip().replace(b"\r", b" "))
+    return titles
 
 
 def parse_fasta_bytes(raw: bytes) -> HostAssembly:
@@ -148,7 +165,8 @@ def _as_i32(a: np.ndarray):
     return a.view(np.int32)
 
 
-def pack_to_device(asm: HostAssembly, device=None, threads: int = 0, on_device: bool = False) -> PackedAssembly:
+def pack_to_device(asm: HostAssembly, device=None, threads: int = 0, on_device: bool = False,
+                   gc: bool = False) -> PackedAssembly:
     """Pack ``asm`` and place it in HBM.
 
     ``on_device=False``: 2-bit packing on host threads, then one H2D copy of the
@@ -159,6 +177,8 @@ def pack_to_device(asm: HostAssembly, device=None, threads: int = 0, on_device: 
 
     device = L.require_cuda(device)
     n = asm.n_contigs
+    if gc:
+        on_device = True  # GC% is a by-product of the device packer's pass over the ASCII bytes
     if not on_device:
         starts, lengths, total, codes, bitmap, rank, masks = pack_host_arrays(asm, threads)
         with torch.cuda.device(device):
@@ -182,12 +202,13 @@ def pack_to_device(asm: HostAssembly, device=None, threads: int = 0, on_device: 
         d_seq[:nbytes].copy_(seq_h, non_blocking=True)
         d_off = torch.from_numpy(offsets - base).to(device)
         d_starts = torch.from_numpy(starts if n else np.zeros(1, np.int64)).to(device)
-        return pack_device_arrays(d_seq, d_off, d_starts, n, total, lengths, starts, asm.total_bp, asm.ids)
+        return pack_device_arrays(d_seq, d_off, d_starts, n, total, lengths, starts, asm.total_bp, asm.ids, gc=gc)
 
 
 def pack_device_arrays(d_seq, d_off, d_starts, n, total, lengths, starts_host, total_bp, ids=None,
-                       exc_capacity: int = 0) -> PackedAssembly:
-    """Run ``am_pack_device`` on ASCII bytes that already live in HBM."""
+                       exc_capacity: int = 0, gc: bool = False) -> PackedAssembly:
+    """Run ``am_pack_device`` on ASCII bytes that already live in HBM; ``gc=True`` also
+    returns ``Metagenome.gc_content``'s percentage per contig (metagenome.py:303-320)."""
     import torch
 
     device = d_seq.device
@@ -199,24 +220,30 @@ def pack_device_arrays(d_seq, d_off, d_starts, n, total, lengths, starts_host, t
         rank = torch.empty(nbw, dtype=torch.int32, device=device)
         work = torch.empty(nbw, dtype=torch.int32, device=device)
         n_exc = torch.zeros(1, dtype=torch.int64, device=device)
+        gc_at = torch.empty((max(n, 1), 2), dtype=torch.int32, device=device) if gc else None
         cap = exc_capacity if exc_capacity > 0 else max(1024, total // 64 // 16)
         while True:
             masks = torch.empty(cap, dtype=torch.int64, device=device)
             L.check(
-                L.lib.am_pack_device(
+                L.lib.am_pack_device_gc(
                     L.t_ptr(d_seq), L.t_ptr(d_off), L.t_ptr(d_starts), n, total, L.t_ptr(codes),
                     L.t_ptr(bitmap), L.t_ptr(rank), L.t_ptr(masks), cap, L.t_ptr(n_exc),
-                    L.t_ptr(work), L.stream_ptr(device),
+                    L.t_ptr(gc_at) if gc else None, L.t_ptr(work), L.stream_ptr(device),
                 )
             )
             found = int(n_exc.item())
             if found <= cap:
                 break
             cap = found
+        gc_content = None
+        if gc:
+            gc_content = torch.empty(max(n, 1), dtype=torch.float64, device=device)
+            L.check(L.lib.am_gc_finish(L.t_ptr(gc_at), n, L.t_ptr(gc_content), L.stream_ptr(device)))
+            gc_content = gc_content[:n]
         return PackedAssembly(
             n_contigs=n, total_bp=total_bp, total_packed_bases=total, lengths=lengths,
             starts_host=starts_host, codes=codes, exc_bitmap=bitmap, exc_rank=rank, exc_mask=masks,
-            starts=d_starts, n_exc=found, ids=ids,
+            starts=d_starts, n_exc=found, ids=ids, gc_content=gc_content,
         )
 
 

@@ -32,13 +32,17 @@ __device__ __forceinline__ void conv4(uint32_t w, uint32_t &code8, uint32_t &bad
   bad4 = (((~ok) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu;
 }
 
+// GC: also count the bases Biopython's gc_fraction(seq, "remove") counts, case-insensitively:
+// gc = #{G,C,S}, at = #{A,T,W,U} (autometa/common/metagenome.py:303-320 -> Bio.SeqUtils.gc_fraction)
+template <bool GC>
 __device__ __forceinline__ void pack_group(const uint8_t *__restrict__ seq, int64_t src, int nbases,
-                                           uint32_t (&codes)[4], uint64_t &bad) {
+                                           uint32_t (&codes)[4], uint64_t &bad, uint32_t &gc, uint32_t &at) {
   // read 17 aligned words covering [src, src+64)
   const uint32_t *base = reinterpret_cast<const uint32_t *>(seq + (src & ~(int64_t)3));
   const int sh = (int)(src & 3) * 8;
   uint32_t prev = __ldg(base);
   bad = 0;
+  uint32_t gcb = 0, atb = 0;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint32_t c32 = 0;
@@ -52,9 +56,21 @@ __device__ __forceinline__ void pack_group(const uint8_t *__restrict__ seq, int6
       conv4(w, c8, b4);
       c32 |= c8 << (8 * r);
       bad |= (uint64_t)b4 << (4 * wi);
+      if (GC) {
+        const uint32_t u = w & 0xDFDFDFDFu;  // fold case: only b and b^0x20 map to a letter
+        const uint32_t mg = __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x53535353u);
+        const uint32_t ma = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x54545454u) |
+                            __vcmpeq4(u, 0x57575757u) | __vcmpeq4(u, 0x55555555u);
+        const int nb = nbases - 4 * wi;
+        const uint32_t keep = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+        gcb += __popc(mg & keep);
+        atb += __popc(ma & keep);
+      }
     }
     codes[q] = c32;
   }
+  gc = gcb >> 3;
+  at = atb >> 3;
   if (nbases < 64) {
     // bytes past the contig end belong to the next record: clear them
     const uint64_t keep = nbases <= 0 ? 0ull : ((1ull << nbases) - 1ull);
@@ -68,26 +84,44 @@ __device__ __forceinline__ void pack_group(const uint8_t *__restrict__ seq, int6
   }
 }
 
+template <bool GC>
 __global__ void __launch_bounds__(256)
 pack_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ offsets,
             const int64_t *__restrict__ starts, int64_t n_contigs, int64_t n_groups,
-            uint4 *__restrict__ codes4, uint32_t *__restrict__ bitmap, uint32_t *__restrict__ pop) {
+            uint4 *__restrict__ codes4, uint32_t *__restrict__ bitmap, uint32_t *__restrict__ pop,
+            uint32_t *__restrict__ gc_at) {
   // n_groups is padded by the launcher to a multiple of 32 so every warp writes one bitmap word
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t c[4] = {0, 0, 0, 0};
   uint64_t bad = 0;
+  uint32_t gc = 0, at = 0;
+  int i = -1;
   if (g < n_groups && n_contigs > 0) {
     const int64_t pos = g * AM_GROUP_BASES;
-    const int i = find_contig(starts, n_contigs, pos);
+    i = find_contig(starts, n_contigs, pos);
     const int64_t off = __ldg(offsets + i);
     const int64_t L = __ldg(offsets + i + 1) - off;
     const int64_t local = pos - __ldg(starts + i);
     if (local < L) {
       const int64_t rem = L - local;
-      pack_group(seq, off + local, rem > 64 ? 64 : (int)rem, c, bad);
+      pack_group<GC>(seq, off + local, rem > 64 ? 64 : (int)rem, c, bad, gc, at);
     }
   }
   if (g < n_groups) codes4[g] = make_uint4(c[0], c[1], c[2], c[3]);
+  if (GC) {
+    // one atomic pair per (warp, contig): 32 consecutive groups mostly share a contig
+    const unsigned peers = __match_any_sync(0xffffffffu, i);
+    uint32_t sg = 0, sa = 0;
+    for (unsigned m = peers; m; m &= m - 1) {
+      const int src = __ffs(m) - 1;
+      sg += __shfl_sync(peers, gc, src);
+      sa += __shfl_sync(peers, at, src);
+    }
+    if (i >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+      if (sg) atomicAdd(gc_at + 2 * (int64_t)i, sg);
+      if (sa) atomicAdd(gc_at + 2 * (int64_t)i + 1, sa);
+    }
+  }
   const uint32_t ball = __ballot_sync(0xffffffffu, bad != 0);
   if ((threadIdx.x & 31) == 0) {
     const int64_t w = g >> 5;
@@ -114,19 +148,46 @@ pack_mask_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ of
   const int64_t off = __ldg(offsets + i);
   const int64_t L = __ldg(offsets + i + 1) - off;
   const int64_t local = pos - __ldg(starts + i);
-  uint32_t c[4];
+  uint32_t c[4], gc, at;
   uint64_t bad = 0;
   const int64_t rem = L - local;
-  pack_group(seq, off + local, rem > 64 ? 64 : (int)rem, c, bad);
+  pack_group<false>(seq, off + local, rem > 64 ? 64 : (int)rem, c, bad, gc, at);
   exc_mask[r] = bad;
 }
 
+__global__ void gc_finish_kernel(const uint32_t *__restrict__ gc_at, int64_t n, double *__restrict__ gc_content) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double g = (double)gc_at[2 * i], len = g + (double)gc_at[2 * i + 1];
+  // gc_fraction(...) * 100 in Python floats; a record without countable bases gives 0
+  gc_content[i] = len > 0.0 ? __dmul_rn(__ddiv_rn(g, len), 100.0) : 0.0;
+}
+
 }  // namespace
+
+extern "C" int am_gc_finish(const uint32_t *d_gc_at, int64_t n_contigs, double *d_gc_content, void *stream) {
+  if (n_contigs < 0 || (n_contigs && (!d_gc_at || !d_gc_content)))
+    return am::fail(AM_EINVAL, "am_gc_finish: bad args");
+  if (!n_contigs) return AM_OK;
+  gc_finish_kernel<<<(unsigned)((n_contigs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_gc_at, n_contigs,
+                                                                                       d_gc_content);
+  AM_LAUNCHED("gc_finish_kernel");
+  return AM_OK;
+}
 
 extern "C" int am_pack_device(const uint8_t *d_seq, const int64_t *d_offsets, const int64_t *d_starts,
                               int64_t n_contigs, int64_t total_packed_bases, uint32_t *d_codes,
                               uint32_t *d_exc_bitmap, uint32_t *d_exc_rank, uint64_t *d_exc_mask,
                               int64_t exc_capacity, int64_t *d_n_exc, void *d_work, void *stream) {
+  return am_pack_device_gc(d_seq, d_offsets, d_starts, n_contigs, total_packed_bases, d_codes, d_exc_bitmap,
+                           d_exc_rank, d_exc_mask, exc_capacity, d_n_exc, nullptr, d_work, stream);
+}
+
+extern "C" int am_pack_device_gc(const uint8_t *d_seq, const int64_t *d_offsets, const int64_t *d_starts,
+                                 int64_t n_contigs, int64_t total_packed_bases, uint32_t *d_codes,
+                                 uint32_t *d_exc_bitmap, uint32_t *d_exc_rank, uint64_t *d_exc_mask,
+                                 int64_t exc_capacity, int64_t *d_n_exc, uint32_t *d_gc_at, void *d_work,
+                                 void *stream) {
   if (n_contigs < 0 || total_packed_bases < 0 || total_packed_bases % AM_GROUP_BASES)
     return am::fail(AM_EINVAL, "am_pack_device: bad sizes");
   if (!d_seq || !d_offsets || !d_starts || !d_codes || !d_exc_bitmap || !d_exc_rank || !d_n_exc || !d_work)
@@ -143,9 +204,14 @@ extern "C" int am_pack_device(const uint8_t *d_seq, const int64_t *d_offsets, co
   AM_CUDA(cudaMemsetAsync(pop, 0, (size_t)n_words * 4, st));
   const int64_t threads = (n_groups + 31) / 32 * 32;
   const unsigned blocks = (unsigned)((threads + 255) / 256);
+  if (d_gc_at && n_contigs) AM_CUDA(cudaMemsetAsync(d_gc_at, 0, (size_t)n_contigs * 8, st));
   if (blocks) {
-    pack_kernel<<<blocks, 256, 0, st>>>(d_seq, d_offsets, d_starts, n_contigs, n_groups,
-                                        reinterpret_cast<uint4 *>(d_codes), d_exc_bitmap, pop);
+    if (d_gc_at)
+      pack_kernel<true><<<blocks, 256, 0, st>>>(d_seq, d_offsets, d_starts, n_contigs, n_groups,
+                                                reinterpret_cast<uint4 *>(d_codes), d_exc_bitmap, pop, d_gc_at);
+    else
+      pack_kernel<false><<<blocks, 256, 0, st>>>(d_seq, d_offsets, d_starts, n_contigs, n_groups,
+                                                 reinterpret_cast<uint4 *>(d_codes), d_exc_bitmap, pop, nullptr);
     AM_LAUNCHED("pack_kernel");
   }
   // rank[w] = flagged groups before bitmap word w; rank needs n_words + 1 slots

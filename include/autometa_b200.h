@@ -117,6 +117,24 @@ int am_pack_device(const uint8_t *d_seq, const int64_t *d_offsets,
                    uint64_t *d_exc_mask, int64_t exc_capacity, int64_t *d_n_exc,
                    void *d_work, void *stream);
 
+/* FASTA-ingest by-products.  am_pack_device_gc is am_pack_device
+ * that also counts, per contig and case-insensitively, the bases
+ * Bio.SeqUtils.gc_fraction(seq, "remove") counts: d_gc_at[2i] = #{G,C,S},
+ * d_gc_at[2i+1] = #{A,T,W,U} (uint32 [n_contigs x 2], zeroed by the call; NULL =
+ * plain am_pack_device).  am_gc_finish turns the counts into
+ * Metagenome.gc_content's column, autometa/common/metagenome.py:303-320:
+ * gc_content[i] = gc / (gc + at) * 100 in IEEE double (0 when gc + at == 0).
+ * Contig lengths are the offsets' differences (am_pack_plan). */
+int am_pack_device_gc(const uint8_t *d_seq, const int64_t *d_offsets,
+                      const int64_t *d_starts, int64_t n_contigs,
+                      int64_t total_packed_bases, uint32_t *d_codes,
+                      uint32_t *d_exc_bitmap, uint32_t *d_exc_rank,
+                      uint64_t *d_exc_mask, int64_t exc_capacity,
+                      int64_t *d_n_exc, uint32_t *d_gc_at, void *d_work,
+                      void *stream);
+int am_gc_finish(const uint32_t *d_gc_at, int64_t n_contigs,
+                 double *d_gc_content, void *stream);
+
 /* ---------------------------------------------------------------------------
  * Work list for the count kernel: contigs are cut into items of at most
  * `max_item_bases` windows (a multiple of AM_TILE_BASES) so that a multi-Mbp

@@ -376,3 +376,43 @@ def cluster_metrics(labels, markers, coverage, gc, n_ref_markers):
         present_marker_count=present,
         single_copy_marker_count=single,
     )
+
+
+# --------------------------------------------------------------------------- #
+# FASTA-ingest by-products                                      #
+# --------------------------------------------------------------------------- #
+def gc_fraction_remove(seq: bytes) -> float:
+    """``Bio.SeqUtils.gc_fraction(seq)`` with its default ``ambiguous="remove"`` as used by
+    autometa/common/metagenome.py:139,314.  Biopython (>=1.82 per autometa-env.yml:9) is
+    not installed in the build container, so this restates its published definition:
+    gc = count of the letters "CGScgs", length = gc + count of "ATWUatwu", 0 for length 0,
+    else gc / length.  PARITY UNPINNED against a live Biopython; checked only against the
+    values its docstring documents (ACTG -> 0.5, ACTGN -> 0.5, ACTGSSSS -> 0.75)."""
+    gc = sum(seq.count(x) for x in b"CGScgs")
+    length = gc + sum(seq.count(x) for x in b"ATWUatwu")
+    if length == 0:
+        return 0
+    return gc / length
+
+
+def gc_content_table(seqs: List[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    """(gc_content %, length) per record: Metagenome.gc_content, metagenome.py:303-320."""
+    gc = np.array([gc_fraction_remove(s) * 100 for s in seqs], dtype=np.float64)
+    return gc, np.array([len(s) for s in seqs], dtype=np.int64)
+
+
+def length_weighted_gc(seqs: List[bytes]) -> float:
+    """Metagenome.length_weighted_gc, metagenome.py:124-144."""
+    size = sum(len(s) for s in seqs)
+    weights = [len(s) / size for s in seqs]
+    return float(np.average(a=[gc_fraction_remove(s) * 100 for s in seqs], weights=weights))
+
+
+def fragmentation_metric(lengths, quality_measure: float = 0.5):
+    """Metagenome.fragmentation_metric, metagenome.py:177-208."""
+    target = sum(lengths) * quality_measure
+    total = 0
+    for length in sorted(lengths, reverse=True):
+        total += length
+        if total >= target:
+            return length

@@ -479,3 +479,46 @@ def test_digit_planes_fused_equals_generic_quantiser(torch_cuda):
     scale = np.sqrt(np.outer(np.diag(G64), np.diag(G64)))
     assert np.max(np.abs(G8 - G64) / scale) <= 5e-12
     assert np.array_equal(G8, G8.T)
+
+
+# ----------------------------------------------------------------------------- FASTA-ingest by-products (8f-2)
+def test_gc_content_matches_oracle(torch_cuda, small_fna, tmp_path):
+    from autometa_b200.common.metagenome import Metagenome
+
+    ids, seqs = O.read_fasta(small_fna)
+    gc, length = O.gc_content_table(seqs)
+    mg = Metagenome(small_fna)
+    df = mg.gc_content()
+    assert df.index.name == "contig" and list(df.columns) == ["gc_content", "length"]
+    assert df.index.tolist() == ids
+    assert np.array_equal(df["length"].to_numpy(), length)
+    assert np.array_equal(df["gc_content"].to_numpy(), gc)  # bit-exact: integer counts, one division
+    assert mg.length_weighted_gc == O.length_weighted_gc(seqs)
+    d = mg.describe()
+    assert d.index.name == "assembly" and d["nseqs"].iloc[0] == len(seqs)
+    assert d["length_weighted_gc_content (%)"].iloc[0] == O.length_weighted_gc(seqs)
+    # ragged lengths around the 64-base group size, every byte class, empty and header-only records
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTacgtNnSsWwUuRYKMBDHV-*.", dtype=np.uint8)
+    recs = []
+    for L in [0, 1, 3, 4, 5, 63, 64, 65, 127, 128, 129, 255, 4096, 70001] + list(rng.integers(1, 3000, 200)):
+        p = np.full(len(alphabet), 0.2 / (len(alphabet) - 8))
+        p[:8] = 0.1
+        recs.append(alphabet[rng.choice(len(alphabet), size=int(L), p=p / p.sum())].tobytes())
+    fa = tmp_path / "r.fa"
+    with open(fa, "wb") as fh:
+        for i, s in enumerate(recs):
+            fh.write(b">r%d d\n" % i + b"\n".join(s[j : j + 70] for j in range(0, len(s), 70)) + b"\n")
+    _, seqs2 = O.read_fasta(str(fa))
+    assert seqs2 == recs
+    gc2, len2 = O.gc_content_table(recs)
+    df2 = Metagenome(str(fa)).gc_content()
+    assert np.array_equal(df2["length"].to_numpy(), len2)
+    assert np.array_equal(df2["gc_content"].to_numpy(), gc2)
+    # the packed codes of the GC pass are the ones the plain packer writes
+    from autometa_b200 import assembly as A
+
+    h = A.read_fasta(str(fa))
+    a, b = A.pack_to_device(h, on_device=True), A.pack_to_device(h, gc=True)
+    assert torch_cuda.equal(a.codes, b.codes) and torch_cuda.equal(a.exc_bitmap, b.exc_bitmap)
+    assert a.gc_content is None and b.gc_content.shape[0] == len(recs)

@@ -226,3 +226,52 @@ def test_shard_ranges_balance_and_cover():
         assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
         bp = np.array([lens[a:b].sum() for a, b in r])
         assert bp.max() - bp.min() <= 2 * lens.max()
+
+
+# ------------------------------------------------------------------ metagenome (8f-2)
+def test_gc_fraction_oracle_known_answers():
+    # the values Bio.SeqUtils.gc_fraction documents for ambiguous="remove"
+    assert O.gc_fraction_remove(b"ACTG") == 0.5
+    assert O.gc_fraction_remove(b"ACTGN") == 0.5
+    assert O.gc_fraction_remove(b"ACTGSSSS") == 0.75
+    assert O.gc_fraction_remove(b"GGAUCUUCGGAUCU") == 0.5
+    assert O.gc_fraction_remove(b"NNNN") == 0 and O.gc_fraction_remove(b"") == 0
+    assert O.gc_fraction_remove(b"acgtWwSsUu") == 0.4
+
+
+def test_metagenome_host_members(small_fna, tmp_path):
+    from autometa_b200.common.metagenome import Metagenome
+
+    ids, seqs = O.read_fasta(small_fna)
+    lengths = [len(s) for s in seqs]
+    mg = Metagenome(small_fna)
+    assert str(mg) == os.path.realpath(small_fna)
+    assert mg.nseqs == len(seqs) and mg.size == sum(lengths)
+    assert mg.sequences == [s.decode() for s in seqs]
+    assert mg.largest_seq == ids[lengths.index(max(lengths))]
+    for q in (0.1, 0.5, 0.9):
+        m = mg.fragmentation_metric(q)
+        assert isinstance(m, int) and m == O.fragmentation_metric(lengths, q)
+    with pytest.raises(ValueError):
+        mg.fragmentation_metric(1.4)
+    # length_filter: argument checks, force semantics, 60-column FASTA out, original kept when nothing passes
+    out = tmp_path / "f.fna"
+    with pytest.raises(ValueError):
+        mg.length_filter(out=str(out), cutoff=-6)
+    with pytest.raises(TypeError):
+        mg.length_filter(out=str(out), cutoff="12324")
+    with pytest.raises(FileExistsError):
+        mg.length_filter(out=small_fna, cutoff=10)
+    cutoff = sorted(lengths)[len(lengths) // 2]
+    f = mg.length_filter(out=str(out), cutoff=cutoff)
+    want = [(i, s) for i, s in zip(ids, seqs) if len(s) >= cutoff]
+    assert f.nseqs == len(want) and f.ids == [i for i, _ in want]
+    assert f.sequences == [s.decode() for _, s in want]
+    lines = open(out).read().split("\n")
+    assert max(len(l) for l in lines if not l.startswith(">")) == 60
+    assert mg.length_filter(out=str(tmp_path / "g.fna"), cutoff=10 ** 9) is mg
+    # header description survives the rewrite the way SeqIO.write keeps it
+    p = tmp_path / "d.fa"
+    p.write_bytes(b">c1 some description \r\nACGT\nAC\n>c2\nA\n")
+    g = Metagenome(str(p)).length_filter(out=str(tmp_path / "d2.fa"), cutoff=2)
+    assert open(g.assembly, "rb").read() == b">c1 some description\nACGTAC\n"
