@@ -7,6 +7,11 @@ schedule, tie rule and termination; the clustering itself runs on the GPU
 ``DBSCAN(min_samples=1)``: every point is a core point, there are no border or
 noise points, and each eps is the connected components of the eps-graph — so the
 sweep keeps ONE union-find forest on the device and only adds merges as eps grows.
+
+The callers of the sweep are mirrored on top of it: ``get_clusters``
+(:440-545, re-sweeps the leftovers until nothing more is recovered) and
+``taxon_guided_binning`` (:548-705, the same per taxon from superkingdom down to
+species).  Only ``method="dbscan"`` is on the device; HDBSCAN is out of scope.
 """
 from __future__ import annotations
 
@@ -18,7 +23,7 @@ import pandas as pd
 
 from .. import _lib as L
 from .. import device as _dev
-from ..common.exceptions import TableFormatError
+from ..common.exceptions import BinningError, TableFormatError
 from .utilities import (
     METRICS,
     add_metrics,
@@ -26,7 +31,12 @@ from .utilities import (
     cluster_metrics_arrays,
     markers_coo,
     passing_mask,
+    reindex_bin_names,
+    zero_pad_bin_names,
 )
+
+#: autometa/taxonomy/database.py:65-74
+CANONICAL_RANKS = ["species", "genus", "family", "order", "class", "phylum", "superkingdom", "root"]
 
 logger = logging.getLogger(__name__)
 
@@ -209,3 +219,113 @@ def _recursive_dbscan_frames(table, markers_df, completeness_cutoff, purity_cuto
     )
     unclustered_df = best_df.loc[~best_df.index.isin(clustered_df.index)]
     return clustered_df, unclustered_df
+
+
+def get_clusters(
+    main: pd.DataFrame,
+    markers_df: pd.DataFrame,
+    completeness: float,
+    purity: float,
+    coverage_stddev: float,
+    gc_content_stddev: float,
+    method: str,
+    n_jobs: int = -1,
+    verbose: bool = False,
+    device=None,
+) -> pd.DataFrame:
+    """Sweep, keep the passing clusters, sweep the leftovers again ... until a round recovers
+    nothing or nothing is left (reference recursive_dbscan.py:440-545).  Returns ``main`` with
+    ``cluster`` (``bin_NN`` / ``pd.NA``) and the four metric columns."""
+    if method not in ("dbscan", "hdbscan"):
+        raise ValueError(f"Method: {method} not a choice. choose between dict_keys(['dbscan', 'hdbscan'])")
+    if method != "dbscan":
+        raise NotImplementedError("only method='dbscan' runs on the device; HDBSCAN is out of scope (DESIGN.md 9)")
+    n_bins = 0
+    rounds = []
+    while True:
+        clustered_df, unclustered_df = recursive_dbscan(
+            table=main,
+            markers_df=markers_df,
+            completeness_cutoff=completeness,
+            purity_cutoff=purity,
+            coverage_stddev_cutoff=coverage_stddev,
+            gc_content_stddev_cutoff=gc_content_stddev,
+            verbose=verbose,
+            n_jobs=n_jobs,
+            device=device,
+        )
+        if clustered_df.empty:  # nothing recovered: the rest stays unbinned
+            rounds.append(unclustered_df.assign(cluster=pd.NA))
+            break
+        clustered_df = reindex_bin_names(df=clustered_df, initial_index=n_bins)
+        rounds.append(clustered_df)
+        if unclustered_df.empty:
+            break
+        n_bins += clustered_df.cluster.nunique()
+        main = unclustered_df
+    df = pd.concat(rounds, axis="index", sort=True)
+    for metric in ["purity", "completeness", "coverage_stddev", "gc_content_stddev"]:
+        if metric not in df.columns:  # no cluster at all in the first round
+            df[metric] = pd.NA
+    return zero_pad_bin_names(df)
+
+
+def taxon_guided_binning(
+    main: pd.DataFrame,
+    markers: pd.DataFrame,
+    completeness: float = 20.0,
+    purity: float = 95.0,
+    coverage_stddev: float = 25.0,
+    gc_content_stddev: float = 5.0,
+    starting_rank: str = "superkingdom",
+    method: str = "dbscan",
+    reverse_ranks: bool = False,
+    n_jobs: int = -1,
+    verbose: bool = False,
+    device=None,
+) -> pd.DataFrame:
+    """``get_clusters`` per taxon, rank by rank, on the contigs not binned yet
+    (reference recursive_dbscan.py:548-705).  ``main`` carries the canonical-rank columns."""
+    if main.loc[main.index.isin(markers.index)].empty:
+        raise TableFormatError("No markers for contigs in table. Unable to assess binning quality")
+    if main.shape[0] <= 1:
+        raise BinningError("Not enough contigs in table for binning")
+    logger.info(f"Using {method} clustering method")
+    ranks = [r for r in (CANONICAL_RANKS if reverse_ranks else reversed(CANONICAL_RANKS)) if r != "root"]
+    ranks = ranks[ranks.index(starting_rank):]
+    logger.debug(f"Using ranks: {', '.join(ranks)}")
+    binned = set()
+    n_bins = 0
+    found = []
+    for rank in ranks:
+        by_taxon = main.loc[main[rank] != "unclassified"].groupby(rank)
+        sizes = by_taxon[rank].count()
+        logger.info(f"Examining {rank}: {sizes.index.nunique():,} unique taxa ({sizes.sum():,} contigs)")
+        for taxon, members in by_taxon:
+            if members.empty:
+                continue
+            todo = members.loc[members["cluster"].isna()] if "cluster" in members.columns else members
+            if binned:
+                todo = todo.loc[~todo.index.isin(binned)]
+            if todo.empty:
+                continue
+            logger.debug(f"Examining taxonomy: {rank} : {taxon} : {todo.shape}")
+            clusters_df = get_clusters(
+                main=todo, markers_df=markers, completeness=completeness, purity=purity,
+                coverage_stddev=coverage_stddev, gc_content_stddev=gc_content_stddev, method=method,
+                n_jobs=n_jobs, verbose=verbose, device=device,
+            )
+            clustered = clusters_df.loc[clusters_df["cluster"].notnull()]
+            if clustered.empty:
+                continue
+            binned.update(clustered.index)
+            names = {c: f"bin_{1 + i + n_bins:04d}" for i, c in enumerate(clustered.cluster.unique())}
+            clustered.cluster = clustered.cluster.map(names.__getitem__)
+            n_bins += clustered.cluster.nunique()
+            found.append(clustered)
+    if not found:
+        raise BinningError("Failed to recover any clusters from dataset")
+    clustered_df = pd.concat(found, sort=True)
+    unclustered_df = main.loc[~main.index.isin(clustered_df.index)]
+    unclustered_df["cluster"] = pd.NA
+    return pd.concat([clustered_df, unclustered_df], sort=True)

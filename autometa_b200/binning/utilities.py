@@ -135,3 +135,23 @@ def apply_binning_metrics_filter(
         & df.coverage_stddev.le(coverage_stddev_cutoff)
         & df.gc_content_stddev.le(gc_content_stddev_cutoff)
     ]
+
+
+def reindex_bin_names(df: pd.DataFrame, cluster_col: str = "cluster", initial_index: int = 0) -> pd.DataFrame:
+    """Rename the clusters of ``df`` to ``bin_<initial_index+1>``, ``bin_<initial_index+2>``, ... in
+    order of first appearance; rows without a cluster stay null (reference utilities.py:265-325).
+    Modifies and returns ``df``."""
+    assigned = df[cluster_col].dropna()
+    names = {old: f"bin_{initial_index + 1 + rank}" for rank, old in enumerate(assigned.unique())}
+    df[cluster_col] = assigned.map(names.__getitem__)
+    return df
+
+
+def zero_pad_bin_names(df: pd.DataFrame, cluster_col: str = "cluster") -> pd.DataFrame:
+    """Renumber the clusters ``bin_001`` ... in order of first appearance, zero-padded to the
+    number of digits of the cluster count (reference utilities.py:328-363).  Modifies and returns ``df``."""
+    assigned = df[cluster_col].dropna()
+    width = len(str(assigned.nunique()))
+    names = {old: "bin_" + str(rank + 1).zfill(width) for rank, old in enumerate(assigned.unique())}
+    df[cluster_col] = assigned.map(names.__getitem__)
+    return df

@@ -149,3 +149,22 @@ def make_sweep_input(n_points: int = 200_000, n_clusters: int = 400, n_markers: 
         columns=[f"PF{m:05d}" for m in range(n_markers)],
     )
     return table, markers_df
+
+
+def add_taxonomy(table, seed: int = 3):
+    """Deterministic canonical-rank columns for ``taxon_guided_binning`` inputs: taxa are bands of the
+    embedding plane (so that contigs of a taxon are spatially coherent), a few contigs "unclassified"."""
+    rng = np.random.default_rng(seed)
+    x, y = table["x_1"].to_numpy(), table["x_2"].to_numpy()
+    out = table.copy()
+    out["superkingdom"] = np.where(x < 0, "Bacteria", "Archaea")
+    out["phylum"] = ["p_%d" % v for v in (np.floor(x / 50).astype(int) * 10 + np.floor(y / 100).astype(int))]
+    out["class"] = ["c_%d" % v for v in (np.floor(x / 25).astype(int) * 100 + np.floor(y / 50).astype(int))]
+    for rank in ("order", "family", "genus", "species"):
+        out[rank] = "unclassified"
+    drop = rng.random(len(out)) < 0.05
+    for rank in ("superkingdom", "phylum", "class"):
+        col = out[rank].to_numpy(dtype=object)
+        col[drop] = "unclassified"
+        out[rank] = col
+    return out

@@ -56,5 +56,10 @@ def golden_dbscan():
 
 
 @pytest.fixture(scope="session")
+def golden_binning():
+    return np.load(os.path.join(GOLDEN, "binning_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def small_fna():
     return os.path.join(GOLDEN, "small.fna")

@@ -63,7 +63,39 @@ def make_small_fasta(path):
     return recs
 
 
+def _frame_to_npz(prefix, df, res):
+    res[f"{prefix}_index"] = np.array(df.index.tolist())
+    res[f"{prefix}_columns"] = np.array(df.columns.tolist())
+    res[f"{prefix}_cluster"] = np.array(["" if pd.isna(c) else str(c) for c in df["cluster"]])
+    for m in ["completeness", "purity", "coverage_stddev", "gc_content_stddev"]:
+        res[f"{prefix}_{m}"] = pd.to_numeric(df[m], errors="coerce").to_numpy(dtype=np.float64, na_value=np.nan)
+
+
+def make_binning_golden():
+    """The sweep's callers through the reference: get_clusters and taxon_guided_binning."""
+    from autometa_b200 import synth
+
+    res = {}
+    table, markers = synth.make_sweep_input(n_points=1500, n_clusters=9, n_markers=40, seed=21)
+    df = rdb.get_clusters(table.copy(), markers, 20.0, 90.0, 25.0, 5.0, method="dbscan", n_jobs=1)
+    _frame_to_npz("get_clusters", df, res)
+    # a table where nothing passes: every contig stays unclustered with NA metrics
+    df0 = rdb.get_clusters(table.iloc[:40].copy(), markers, 99.0, 99.0, 0.001, 0.001, method="dbscan", n_jobs=1)
+    _frame_to_npz("get_clusters_none", df0, res)
+    tax = synth.add_taxonomy(table, seed=3)
+    dft = rdb.taxon_guided_binning(tax.copy(), markers, 20.0, 90.0, 25.0, 5.0, method="dbscan", n_jobs=1)
+    _frame_to_npz("taxon", dft, res)
+    dfr = rdb.taxon_guided_binning(tax.copy(), markers, 20.0, 90.0, 25.0, 5.0, starting_rank="phylum",
+                                   method="dbscan", reverse_ranks=True, n_jobs=1)
+    _frame_to_npz("taxon_rev", dfr, res)
+    np.savez_compressed(os.path.join(HERE, "binning_golden.npz"), **res)
+    print("binning golden:", {k: v.shape for k, v in res.items() if k.endswith("_cluster")},
+          "bins:", sorted(set(res["get_clusters_cluster"]))[:6], sorted(set(res["taxon_cluster"]))[:6])
+
+
 def main():
+    if "binning" in sys.argv[1:]:
+        return make_binning_golden()
     fna = os.path.join(HERE, "small.fna")
     make_small_fasta(fna)
     out = {}
@@ -146,6 +178,7 @@ def main():
         res[f"metrics_{m}"] = mdf[m].to_numpy(dtype=np.float64)
         res[f"contig_{m}"] = cdf[m].to_numpy(dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, "dbscan_golden.npz"), **res)
+    make_binning_golden()
     print("golden vectors written:", sorted(os.listdir(HERE)))
 
 

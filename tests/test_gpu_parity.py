@@ -522,3 +522,45 @@ def test_gc_content_matches_oracle(torch_cuda, small_fna, tmp_path):
     a, b = A.pack_to_device(h, on_device=True), A.pack_to_device(h, gc=True)
     assert torch_cuda.equal(a.codes, b.codes) and torch_cuda.equal(a.exc_bitmap, b.exc_bitmap)
     assert a.gc_content is None and b.gc_content.shape[0] == len(recs)
+
+
+# ----------------------------------------------------------------------------- callers of the sweep (8f-3)
+def _check_binning_frame(df, g, prefix):
+    assert df.index.tolist() == g[f"{prefix}_index"].tolist()
+    assert df.columns.tolist() == g[f"{prefix}_columns"].tolist()
+    got = np.array(["" if pd.isna(c) else str(c) for c in df["cluster"]])
+    assert np.array_equal(got, g[f"{prefix}_cluster"])
+    for m in ["completeness", "purity", "coverage_stddev", "gc_content_stddev"]:
+        a = pd.to_numeric(df[m], errors="coerce").to_numpy(dtype=np.float64, na_value=np.nan)
+        assert np.allclose(a, g[f"{prefix}_{m}"], rtol=1e-12, atol=0, equal_nan=True), m
+
+
+def test_get_clusters_matches_reference_golden(torch_cuda, golden_binning):
+    from autometa_b200 import synth
+    from autometa_b200.binning import recursive_dbscan as R
+
+    table, markers = synth.make_sweep_input(n_points=1500, n_clusters=9, n_markers=40, seed=21)
+    df = R.get_clusters(table.copy(), markers, 20.0, 90.0, 25.0, 5.0, method="dbscan")
+    _check_binning_frame(df, golden_binning, "get_clusters")
+    df0 = R.get_clusters(table.iloc[:40].copy(), markers, 99.0, 99.0, 0.001, 0.001, method="dbscan")
+    _check_binning_frame(df0, golden_binning, "get_clusters_none")
+    with pytest.raises(ValueError):
+        R.get_clusters(table.copy(), markers, 20.0, 90.0, 25.0, 5.0, method="kmeans")
+
+
+def test_taxon_guided_binning_matches_reference_golden(torch_cuda, golden_binning):
+    from autometa_b200 import synth
+    from autometa_b200.binning import recursive_dbscan as R
+    from autometa_b200.common.exceptions import BinningError, TableFormatError
+
+    table, markers = synth.make_sweep_input(n_points=1500, n_clusters=9, n_markers=40, seed=21)
+    tax = synth.add_taxonomy(table, seed=3)
+    df = R.taxon_guided_binning(tax.copy(), markers, 20.0, 90.0, 25.0, 5.0, method="dbscan")
+    _check_binning_frame(df, golden_binning, "taxon")
+    dfr = R.taxon_guided_binning(tax.copy(), markers, 20.0, 90.0, 25.0, 5.0, starting_rank="phylum",
+                                 method="dbscan", reverse_ranks=True)
+    _check_binning_frame(dfr, golden_binning, "taxon_rev")
+    with pytest.raises(TableFormatError):
+        R.taxon_guided_binning(tax.copy(), markers.iloc[:0], method="dbscan")
+    with pytest.raises(BinningError):
+        R.taxon_guided_binning(tax.loc[[markers.index[0]]].copy(), markers, method="dbscan")

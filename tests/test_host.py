@@ -275,3 +275,15 @@ def test_metagenome_host_members(small_fna, tmp_path):
     p.write_bytes(b">c1 some description \r\nACGT\nAC\n>c2\nA\n")
     g = Metagenome(str(p)).length_filter(out=str(tmp_path / "d2.fa"), cutoff=2)
     assert open(g.assembly, "rb").read() == b">c1 some description\nACGTAC\n"
+
+
+def test_bin_name_helpers():
+    from autometa_b200.binning.utilities import reindex_bin_names, zero_pad_bin_names
+
+    df = pd.DataFrame({"cluster": [7, 3, 7, pd.NA, 11, 3]}, index=list("abcdef"))
+    r = reindex_bin_names(df.copy(), initial_index=4)
+    assert r["cluster"].tolist()[:3] == ["bin_5", "bin_6", "bin_5"] and pd.isna(r["cluster"].iloc[3])
+    assert r["cluster"].tolist()[4:] == ["bin_7", "bin_6"]
+    many = pd.DataFrame({"cluster": [f"bin_{i}" for i in range(1, 13)] + [pd.NA]})
+    z = zero_pad_bin_names(many)
+    assert z["cluster"].tolist()[:12] == [f"bin_{i:02d}" for i in range(1, 13)] and pd.isna(z["cluster"].iloc[12])
