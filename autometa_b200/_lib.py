@@ -54,6 +54,10 @@ _SIGS = {
     "am_pack_device": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "am_pack_device_gc": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "am_gc_finish": (C.c_int, [_p, _i64, _p, _p]),
+    "am_tsv_write_f64": (C.c_int, [C.c_char_p, _p, _i64, _p, _p, _i64, _i64, _p, _i32]),
+    "am_tsv_write_i32": (C.c_int, [C.c_char_p, _p, _i64, _p, _p, _i64, _i64, _p, _i32]),
+    "am_tsv_shape": (C.c_int, [_p, _i64, _p, _p]),
+    "am_tsv_parse_f64": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i32]),
     "am_count_plan": (C.c_int, [_p, _i64, _i32, _i32, _p, _i64, _p, _p, _i64, _p]),
     "am_count_kmers": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p]),
     "am_normalize_work_bytes": (_i64, [_i32]),

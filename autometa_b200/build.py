@@ -15,6 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libautometa_b200.so")
 SOURCES = [
     "am_host.cpp",
+    "am_tsv.cpp",
     "am_pack.cu",
     "am_count.cu",
     "am_normalize.cu",

@@ -30,6 +30,7 @@ import pandas as pd
 from .. import _lib as L
 from .. import assembly as _asm
 from .. import device as _dev
+from .. import tsv as _tsv
 from .exceptions import TableFormatError
 
 logger = logging.getLogger(__name__)
@@ -55,7 +56,7 @@ def load(kmers_fpath: str) -> pd.DataFrame:
     if not os.path.exists(kmers_fpath) or not os.path.getsize(kmers_fpath):
         raise FileNotFoundError(kmers_fpath)
     try:
-        df = pd.read_csv(kmers_fpath, sep="\t", index_col="contig")
+        df = _tsv.read_table(kmers_fpath, index_col="contig")
     except (ValueError, TypeError):
         raise TableFormatError(f"contig column not found in {kmers_fpath}!")
     return df
@@ -107,7 +108,7 @@ def count(
     out_exists = os.path.exists(out) if out else False
     if out_specified and out_exists and not force:
         logger.warning(f"counts already exist: {out} force to overwrite. [retrieving]")
-        df = pd.read_csv(out, sep="\t", index_col="contig")
+        df = _tsv.read_table(out, index_col="contig")
     else:
         if not isinstance(size, int) or isinstance(size, bool):
             raise TypeError(f"size must be an int! Given: {type(size)}")
@@ -122,8 +123,12 @@ def count(
         for cid, ln in zip(np.asarray(host.ids, dtype=object)[~countable], lengths[~countable]):
             logger.warning(f"{cid} can not be counted! k-mer size exceeds length. {ln}")
         df = _counts_frame(host.ids, counts, countable, names)
+        if out and df.shape[0] == len(host.ids):  # no duplicate ids: write straight from the count matrix
+            _tsv.write_counts(out, host.ids, names, counts)
+            logger.debug(f"Wrote {df.shape[0]} contigs {size}-mers frequencies to {out}.")
+            return df
     if out:
-        df.to_csv(out, sep="\t", index=True, header=True)
+        _tsv.write_frame(df, out)
         logger.debug(f"Wrote {df.shape[0]} contigs {size}-mers frequencies to {out}.")
     return df
 
@@ -186,7 +191,7 @@ def normalize(
     out_exists = os.path.exists(out) if out else False
     if out_specified and out_exists and not force:
         logger.debug(f"{out} already exists. Use force to overwrite. retrieving...")
-        return pd.read_csv(out, sep="\t", index_col="contig")
+        return _tsv.read_table(out, index_col="contig")
     logger.debug(f"Transforming k-mer counts using {method}")
     choices = {"ilr", "clr", "am_clr"}
     if method == "am_clr":
@@ -198,7 +203,7 @@ def normalize(
     else:
         raise ValueError(f"Normalize Method not available! {method}. choices: {', '.join(choices)}")
     if out_specified and (force or not out_exists):
-        norm_df.to_csv(out, sep="\t", index=True, header=True)
+        _tsv.write_frame(norm_df, out)
     return norm_df
 
 
@@ -293,7 +298,7 @@ def embed(
     """
     if isinstance(kmers, str) and os.path.exists(kmers) and os.path.getsize(kmers):
         try:
-            df = pd.read_csv(kmers, sep="\t", index_col="contig")
+            df = _tsv.read_table(kmers, index_col="contig")
         except ValueError:
             raise TableFormatError(f"contig column not found in {kmers}")
     elif isinstance(kmers, pd.DataFrame):
@@ -303,7 +308,7 @@ def embed(
     if out and os.path.exists(out) and os.path.getsize(out) and not force:
         logger.debug(f"k-mers frequency embedding already exists {out}")
         try:
-            return pd.read_csv(out, sep="\t", index_col="contig")
+            return _tsv.read_table(out, index_col="contig")
         except ValueError:
             raise TableFormatError(f"contig column not found in {out}")
     if df.empty:
@@ -378,6 +383,6 @@ def embed(
     else:
         embedded_df = pd.DataFrame(X, index=df.index, columns=embed_cols)
     if out:
-        embedded_df.to_csv(out, sep="\t", index=True, header=True)
+        _tsv.write_frame(embedded_df, out)
         logger.debug(f"embedded.shape {embedded_df.shape} : Written {out}")
     return embedded_df

@@ -1,0 +1,143 @@
+"""Fast TSV I/O for the k-mer tables.
+
+``write_frame`` / ``write_counts`` / ``read_table`` replace
+``df.to_csv(out, sep="\\t", index=True, header=True)`` and
+``pd.read_csv(path, sep="\\t", index_col="contig")`` of the reference
+(autometa/common/kmers.py:116,328,431,704) with the multi-threaded C routines
+``am_tsv_*``: byte-identical files, identical frames.  Anything outside the fast
+path (mixed dtypes, quoted labels, compressed files ...) goes through pandas, so the
+result is the same either way.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+from . import _lib as L
+
+_NEEDS_QUOTE = ("\t", '"', "\r", "\n")
+#: spellings pandas turns into NaN when it parses an index column
+_NA_LABELS = {"", "#N/A", "#N/A N/A", "#NA", "-1.#IND", "-1.#QNAN", "-NaN", "-nan", "1.#IND", "1.#QNAN", "<NA>",
+              "N/A", "NA", "NULL", "NaN", "None", "n/a", "nan", "null"}
+
+
+def _threads() -> int:
+    return max(1, min(64, os.cpu_count() or 1))
+
+
+def _cell(label) -> str:
+    s = str(label)
+    if any(ch in s for ch in _NEEDS_QUOTE):  # csv.QUOTE_MINIMAL with quotechar '"'
+        return '"' + s.replace('"', '""') + '"'
+    return s
+
+
+def _labels_blob(labels: Sequence):
+    cells = [_cell(x) for x in labels]
+    blob = "".join(cells).encode("utf-8")
+    lens = np.fromiter((len(c.encode("utf-8")) if not c.isascii() else len(c) for c in cells), dtype=np.int64,
+                       count=len(cells))
+    offsets = np.zeros(len(cells) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    return np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, np.uint8), offsets
+
+
+def _header(index_name, columns) -> bytes:
+    first = "" if index_name is None else _cell(index_name)
+    return ("\t".join([first] + [_cell(c) for c in columns]) + "\n").encode("utf-8")
+
+
+def write_counts(path: str, ids: Sequence[str], names: Sequence[str], counts: np.ndarray,
+                 index_name: str = "contig") -> None:
+    """Write an int32 count matrix (0 = not observed = empty cell) as ``count`` would."""
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    n, d = counts.shape
+    blob, offsets = _labels_blob(ids)
+    hdr = _header(index_name, names)
+    L.check(L.lib.am_tsv_write_i32(os.fsencode(path), hdr, len(hdr), L.np_ptr(blob), L.np_ptr(offsets), n, d,
+                                   L.np_ptr(counts) if counts.size else None, _threads()))
+
+
+def write_frame(df: pd.DataFrame, path: str) -> None:
+    """``df.to_csv(path, sep="\\t", index=True, header=True)``; the fast writer when every column is float64."""
+    simple = (
+        isinstance(path, (str, os.PathLike)) and not str(path).endswith((".gz", ".bz2", ".zip", ".xz", ".zst"))
+        and df.index.nlevels == 1 and df.columns.nlevels == 1 and df.shape[1] > 0
+        and all(dt == np.float64 for dt in df.dtypes)
+        and (df.index.dtype == object or pd.api.types.is_string_dtype(df.index.dtype))
+        and not df.index.hasnans
+    )
+    if not simple:
+        df.to_csv(path, sep="\t", index=True, header=True)
+        return
+    values = np.ascontiguousarray(df.to_numpy(dtype=np.float64))
+    blob, offsets = _labels_blob(df.index)
+    hdr = _header(df.index.name, df.columns)
+    L.check(L.lib.am_tsv_write_f64(os.fsencode(str(path)), hdr, len(hdr), L.np_ptr(blob), L.np_ptr(offsets),
+                                   values.shape[0], values.shape[1], L.np_ptr(values) if values.size else None,
+                                   _threads()))
+
+
+def _looks_numeric(label: str) -> bool:
+    try:
+        float(label)
+        return True
+    except ValueError:
+        return False
+
+
+def read_table(path: str, index_col: str = "contig") -> pd.DataFrame:
+    """``pd.read_csv(path, sep="\\t", index_col=index_col)`` for a table of numbers."""
+    fast = isinstance(path, (str, os.PathLike)) and not str(path).endswith((".gz", ".bz2", ".zip", ".xz", ".zst"))
+    df = _read_fast(str(path), index_col) if fast else None
+    if df is None:
+        df = pd.read_csv(path, sep="\t", index_col=index_col)
+    return df
+
+
+def _read_fast(path: str, index_col: str) -> Optional[pd.DataFrame]:
+    buf = np.fromfile(path, dtype=np.uint8)
+    if buf.size == 0:
+        return None
+    end = int(np.argmax(buf == 10)) if (buf == 10).any() else buf.size
+    try:
+        head = buf[:end].tobytes().decode("utf-8")
+    except UnicodeDecodeError:
+        return None
+    head = head[:-1] if head.endswith("\r") else head
+    fields = head.split("\t")
+    if '"' in head or fields[0] != index_col or len(set(fields)) != len(fields) or len(fields) < 2:
+        return None  # index column elsewhere, mangled duplicate names, quoting: pandas' job
+    if any(f == "" or f.startswith("Unnamed") for f in fields):
+        return None
+    n_rows = np.zeros(1, np.int64)
+    n_fields = np.zeros(1, np.int64)
+    L.check(L.lib.am_tsv_shape(L.np_ptr(buf), buf.size, L.np_ptr(n_rows), L.np_ptr(n_fields)))
+    n, f = int(n_rows[0]), int(n_fields[0])
+    if n == 0 or f != len(fields):
+        return None
+    idb = np.empty(n, np.int64)
+    ide = np.empty(n, np.int64)
+    values = np.empty((n, f - 1), np.float64)
+    all_int = np.zeros(f - 1, np.uint8)
+    rc = L.lib.am_tsv_parse_f64(L.np_ptr(buf), buf.size, n, f, L.np_ptr(idb), L.np_ptr(ide), L.np_ptr(values),
+                                L.np_ptr(all_int), _threads())
+    if rc != 0:
+        return None
+    raw = buf.tobytes()
+    try:
+        ids = [raw[b:e].decode("utf-8") for b, e in zip(idb.tolist(), ide.tolist())]
+    except UnicodeDecodeError:
+        return None
+    # pandas would convert an all-numeric / NA-spelled index column; leave those tables to it
+    if _looks_numeric(ids[0]) or not _NA_LABELS.isdisjoint(ids) or any(i != i.strip(" ") for i in ids[:1]):
+        return None
+    index = pd.Index(ids, name=index_col)
+    cols = fields[1:]
+    if not all_int.any():
+        return pd.DataFrame(values, index=index, columns=cols)
+    data = {c: (values[:, j].astype(np.int64) if all_int[j] else values[:, j]) for j, c in enumerate(cols)}
+    return pd.DataFrame(data, index=index, columns=cols)

@@ -321,6 +321,28 @@ int am_cluster_metrics(const int64_t *d_labels, int64_t n_points, const int32_t 
                        double *d_cov_std, double *d_gc_std, int32_t *d_present, int32_t *d_single,
                        double *d_summary, void *d_work, void *stream);
 
+/* ---------------------------------------------------------------------------
+ * Host-side TSV I/O of the k-mer tables, all host threads.
+ * Replaces `df.to_csv(out, sep="\t", index=True, header=True)` and
+ * `pd.read_csv(fpath, sep="\t", index_col="contig")` at
+ * autometa/common/kmers.py:116,328,431,704.  `header` = the complete header line
+ * including its '\n'; `ids`/`id_offsets[n_rows+1]` = the (already quoted where the
+ * CSV dialect requires it) index labels.  Floats are written as Python repr,
+ * NaN / count 0 as empty cells: the files are byte-identical to pandas'.  The
+ * parser reproduces pandas' default C-engine float conversion bit for bit and
+ * returns AM_EINVAL for tables outside its fast path (quoted labels, ragged rows,
+ * non-numeric cells). */
+int am_tsv_write_f64(const char *path, const uint8_t *header, int64_t header_len,
+                     const uint8_t *ids, const int64_t *id_offsets, int64_t n_rows,
+                     int64_t n_cols, const double *values, int n_threads);
+int am_tsv_write_i32(const char *path, const uint8_t *header, int64_t header_len,
+                     const uint8_t *ids, const int64_t *id_offsets, int64_t n_rows,
+                     int64_t n_cols, const int32_t *counts, int n_threads);
+int am_tsv_shape(const uint8_t *buf, int64_t len, int64_t *n_rows, int64_t *n_fields);
+int am_tsv_parse_f64(const uint8_t *buf, int64_t len, int64_t n_rows, int64_t n_fields,
+                     int64_t *id_begin, int64_t *id_end, double *values,
+                     uint8_t *col_all_int, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

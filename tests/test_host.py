@@ -287,3 +287,87 @@ def test_bin_name_helpers():
     many = pd.DataFrame({"cluster": [f"bin_{i}" for i in range(1, 13)] + [pd.NA]})
     z = zero_pad_bin_names(many)
     assert z["cluster"].tolist()[:12] == [f"bin_{i:02d}" for i in range(1, 13)] and pd.isna(z["cluster"].iloc[12])
+
+
+# ------------------------------------------------------------------ TSV I/O (8f-4)
+def _bits_equal(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return bool(np.all((a.view(np.int64) == b.view(np.int64)) | (np.isnan(a) & np.isnan(b))))
+
+
+def test_tsv_writer_is_byte_identical_to_pandas(tmp_path):
+    from autometa_b200 import tsv
+
+    rng = np.random.default_rng(0)
+    n, d = 3000, 64
+    X = rng.normal(size=(n, d))
+    X[:200] = np.frombuffer(rng.bytes(200 * d * 8), dtype=np.float64).reshape(200, d)  # every exponent, subnormals
+    X[200:400] *= 10.0 ** rng.integers(-25, 25, size=(200, d))
+    X[400:600] = np.round(X[400:600] * 1000)  # integral values -> "123.0"
+    X[600, :12] = [0.0, -0.0, np.inf, -np.inf, np.nan, 1e16, 1e-5, 123456.0, 1e15, 9999999999999998.0, 1e-4, 5e-324]
+    ids = [f"NODE_{i}_length_{i * 7}_cov_{i / 3:.3f}" for i in range(n)]
+    ids[7] = 'odd"name'
+    for cols in ([f"k{j}" for j in range(d)], list(range(d))):
+        df = pd.DataFrame(X, index=pd.Index(ids, name="contig"), columns=cols)
+        tsv.write_frame(df, str(tmp_path / "fast.tsv"))
+        df.to_csv(tmp_path / "pd.tsv", sep="\t", index=True, header=True)
+        assert (tmp_path / "fast.tsv").read_bytes() == (tmp_path / "pd.tsv").read_bytes()
+    # count tables: 0 == pd.NA == empty cell
+    C = rng.integers(0, 5, size=(500, 32)).astype(np.int32)
+    C[3] = 0
+    names = [f"K{j}" for j in range(32)]
+    tsv.write_counts(str(tmp_path / "c.tsv"), ids[:500], names, C)
+    cols = {nm: pd.arrays.IntegerArray(np.ascontiguousarray(C[:, j]), np.ascontiguousarray(C[:, j] == 0))
+            for j, nm in enumerate(names)}
+    pd.DataFrame(cols, index=pd.Index(ids[:500], name="contig")).to_csv(tmp_path / "c_pd.tsv", sep="\t")
+    assert (tmp_path / "c.tsv").read_bytes() == (tmp_path / "c_pd.tsv").read_bytes()
+    # frames outside the fast path go through pandas and still come out right
+    mixed = pd.DataFrame({"a": [1, 2], "b": [0.5, np.nan]}, index=pd.Index(["x", "y"], name="contig"))
+    tsv.write_frame(mixed, str(tmp_path / "m.tsv"))
+    assert (tmp_path / "m.tsv").read_text() == mixed.to_csv(sep="\t")
+
+
+def test_tsv_reader_equals_pandas_bit_for_bit(tmp_path):
+    from autometa_b200 import tsv
+
+    rng = np.random.default_rng(1)
+    n, d = 4000, 48
+    X = rng.normal(size=(n, d))
+    X[:300] = np.frombuffer(rng.bytes(300 * d * 8), dtype=np.float64).reshape(300, d)
+    X[300:600] *= 10.0 ** rng.integers(-25, 25, size=(300, d))
+    X[600:900] = np.round(X[600:900] * 50)
+    X[rng.random(X.shape) < 0.05] = np.nan
+    X[901, :4] = [np.inf, -np.inf, 0.0, -0.0]
+    ids = [f"c{i}" for i in range(n)]
+    df = pd.DataFrame(X, index=pd.Index(ids, name="contig"), columns=[f"k{j}" for j in range(d)])
+    p = tmp_path / "t.tsv"
+    df.to_csv(p, sep="\t")
+    a, b = tsv.read_table(str(p)), pd.read_csv(p, sep="\t", index_col="contig")
+    pd.testing.assert_frame_equal(a, b, check_exact=True)
+    assert _bits_equal(a.to_numpy(), b.to_numpy())
+    # digits beyond the 17 pandas keeps, exponents, signs, blanks, CRLF, blank lines, integer columns
+    text = ("contig\ti\tf\tg\r\n"
+            "a\t12\t0.000123456789012345678901\t1e-320\r\n"
+            "\r\n"
+            "b\t-7\t123456789012345678901234567890\t+1.5E+10\r\n"
+            "c\t+3\t\t-0.1e-5\r\n"
+            "d\t0\t9007199254740993\tnan\r\n")
+    p2 = tmp_path / "u.tsv"
+    p2.write_bytes(text.encode())
+    a, b = tsv.read_table(str(p2)), pd.read_csv(p2, sep="\t", index_col="contig")
+    pd.testing.assert_frame_equal(a, b, check_exact=True)
+    assert a["i"].dtype == np.int64 and _bits_equal(a["f"], b["f"]) and _bits_equal(a["g"], b["g"])
+    # tables the fast path declines: same answer through pandas (numeric ids, quoted ids, index not first, gz)
+    for body in ("contig\tx\n1\t2.5\n2\t3.5\n", 'contig\tx\n"a\tb"\t1.0\n', "x\tcontig\n1.0\tq\n", "contig\tx\nNA\t1.0\n",
+                 "contig\tx\nq\ttrue\n"):
+        p3 = tmp_path / "v.tsv"
+        p3.write_text(body)
+        pd.testing.assert_frame_equal(tsv.read_table(str(p3)), pd.read_csv(p3, sep="\t", index_col="contig"))
+    df.iloc[:50].to_csv(tmp_path / "z.tsv.gz", sep="\t")
+    pd.testing.assert_frame_equal(tsv.read_table(str(tmp_path / "z.tsv.gz")),
+                                  pd.read_csv(tmp_path / "z.tsv.gz", sep="\t", index_col="contig"), check_exact=True)
+    # pandas' default converter is not correctly rounded (17 digits, one scaling): the fast reader
+    # reproduces its values, which differ from the written doubles in the last bit for some cells
+    (tmp_path / "w.tsv").write_text("id\tx\nq\t1.0\n")
+    with pytest.raises(ValueError):
+        tsv.read_table(str(tmp_path / "w.tsv"))
