@@ -265,12 +265,12 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
+template <int NS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_THREADS, 1)
 gram_i8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  GramI8Params p, double *__restrict__ part) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr int NS = G2_STAGES;
   const uint32_t bars = base + (uint32_t)NS * G2_STAGE_BYTES;
   const uint32_t bar_full = bars, bar_empty = bars + 8u * NS, bar_accf = bars + 16u * NS, bar_acce = bar_accf + 8u;
   __shared__ uint32_t s_tmem;
@@ -311,6 +311,11 @@ gram_i8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int r = row0; r < row1; r += GI_K) {
           mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
           const uint32_t lfb = mapa_shared(bar_full + 8u * stage, 0);
+          if (p.dbg_mode & 2) {  // timing probe: no loads, MMAs run on whatever is in shared memory
+            if (rank == 0) mbar_arrive(bar_full + 8u * stage);
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           if (rank == 0) mbar_expect_tx(bar_full + 8u * stage, 2u * G2_STAGE_BYTES);
           const uint32_t sa = base + (uint32_t)stage * G2_STAGE_BYTES;
           const uint32_t sb = sa + 3u * GI_A_BYTES;
@@ -346,10 +351,12 @@ gram_i8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                          a2 = make_desc(sa + 2u * GI_A_BYTES, GI_K * 128, 1024, 2);
           const uint64_t b0 = make_desc(sb, GI_B_BYTES, 512, 4), b2 = make_desc(sb + 2u * GI_B_BYTES, GI_B_BYTES, 512, 4),
                          b3 = make_desc(sb + 3u * GI_B_BYTES, GI_B_BYTES, 512, 4);
+          if (!(p.dbg_mode & 1)) {
           umma_i8_2sm(tmem + 0u * GI_N, a0, b0, id256, acc);   // planes (0|1) x B(0,1 | 2,3)   -> idx 0..3
           umma_i8_2sm(tmem + 4u * GI_N, a0, b2, id128, acc);   // planes (0|1) x B(4 | 5)       -> idx 4,5
           umma_i8_2sm(tmem + 2u * GI_N, a1, b0, id256, 1u);    // planes (2|3) x B(0,1 | 2,3)   -> idx 2..5
           umma_i8_2sm(tmem + 4u * GI_N, a2, b3, id128, 1u);    // planes (4|5) x B(0 | 1)       -> idx 4,5
+          }
           acc = 1u;
           umma_commit_2sm(bar_empty + 8u * stage);
           if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -369,7 +376,7 @@ gram_i8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int chunk = item / p.n_tiles, tile = item % p.n_tiles;
       const size_t pidx = ((size_t)(chunk + (int)rank * p.n_chunks) * p.n_tiles + tile);
       double *out = part + (pidx * GI_M + (size_t)(q * 32 + lane)) * GI_N;
-      for (int c = 0; c < GI_N / 16; ++c) {
+      for (int c = 0; c < ((p.dbg_mode & 4) ? 0 : GI_N / 16); ++c) {
         double g[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) g[j] = 0.0;
@@ -600,14 +607,24 @@ extern "C" int am_gram_planes(const int8_t *d_planes, int64_t n_rows, int D, int
   }
   int n_parts = p.n_chunks;
   const char *pm = getenv("AM_GRAM_PAIR");
-  const bool use_pair = (S == 6) && !(pm && pm[0] == '0') && p.dbg_mode == 0;
+  const bool use_pair = (S == 6) && !(pm && pm[0] == '0');
   if (use_pair) {
     // CTA pairs (cta_group::2): one cluster of 2 per work item
-    const size_t smem = (size_t)G2_STAGES * G2_STAGE_BYTES + 16 * (size_t)G2_STAGES + 64 + 1024;
-    AM_CUDA(cudaFuncSetAttribute(gram_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const char *sv = getenv("AM_GRAM_STAGES");
+    const int ns = sv ? atoi(sv) : G2_STAGES;
+    const size_t smem = (size_t)ns * G2_STAGE_BYTES + 16 * (size_t)ns + 64 + 1024;
     const int n_items = p.n_chunks * p.n_tiles;
     const int pairs = std::max(1, std::min(n_items, am::num_sms() / 2));
-    gram_i8x2_kernel<<<2 * pairs, GI_THREADS, smem, st>>>(tmA, tmB, p, part);
+    if (ns == 5) {
+      AM_CUDA(cudaFuncSetAttribute(gram_i8x2_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gram_i8x2_kernel<5><<<2 * pairs, GI_THREADS, smem, st>>>(tmA, tmB, p, part);
+    } else if (ns == 11) {
+      AM_CUDA(cudaFuncSetAttribute(gram_i8x2_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gram_i8x2_kernel<11><<<2 * pairs, GI_THREADS, smem, st>>>(tmA, tmB, p, part);
+    } else {
+      AM_CUDA(cudaFuncSetAttribute(gram_i8x2_kernel<G2_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gram_i8x2_kernel<G2_STAGES><<<2 * pairs, GI_THREADS, smem, st>>>(tmA, tmB, p, part);
+    }
     AM_LAUNCHED("gram_i8x2_kernel");
     n_parts = 2 * p.n_chunks;
   } else {
