@@ -467,10 +467,10 @@ def main():
             "frac": round(sum(a["bytes"] for a in acct.values()) / (ms_per_step * 1e-3) / 1e9 / hbm, 4),
         }
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported once, on rank 0 at N=1
             cpu = cpu_baseline(asm, os.cpu_count() or 1)
         sweep = None
-        if not args.no_sweep:
+        if not args.no_sweep and world == 1:  # the 200k-point sweep fits one GPU: replicas only
             sweep = sweep_bench(dev, torch, cpu=not args.no_cpu_baseline)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
