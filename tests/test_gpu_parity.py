@@ -564,3 +564,57 @@ def test_taxon_guided_binning_matches_reference_golden(torch_cuda, golden_binnin
         R.taxon_guided_binning(tax.copy(), markers.iloc[:0], method="dbscan")
     with pytest.raises(BinningError):
         R.taxon_guided_binning(tax.loc[[markers.index[0]]].copy(), markers, method="dbscan")
+
+
+# ----------------------------------------------------------------------------- full-size featurise properties
+@pytest.mark.parametrize("case", ["C2_am_clr", "C5_shard_ilr"])
+def test_featurise_full_size_properties(torch_cuda, case):
+    """BASELINE.json sizes through size-independent properties: C2 (200k contigs / 1 Gbp, am_clr, fused
+    tensor-core path) and one GPU's share of C5 (125k contigs / 625 Mbp, ilr, generic path).  Checked:
+    the normalised rows of a contig sample against the oracle, ilr's isometry with clr, orthonormal
+    components with sklearn's sign rule, column variances of the scores == explained_variance_ (the
+    defining property of PCA scores), explained_variance_ratio_ == EV / trace, and the scores of a row
+    sample recomputed in float64 from the returned mean-free rows and components."""
+    import torch
+
+    from autometa_b200 import assembly as A, pipeline, synth
+
+    n, bp, method = (200_000, 1_000_000_000, "am_clr") if case == "C2_am_clr" else (125_000, 625_000_000, "ilr")
+    asm = synth.make_assembly(n, bp, seed=20261019 + (2 if method == "am_clr" else 5))
+    packed = A.pack_to_device(asm, device="cuda:0", on_device=True)
+    res = pipeline.featurise(packed, 5, method, 50)
+    X, S = res["normalized"], res["scores"]
+    D = 512 if method == "am_clr" else 511
+    assert tuple(X.shape) == (n, D) and tuple(S.shape) == (n, 50)
+    sample = np.random.default_rng(1).choice(n, size=200, replace=False)
+    seqs = [asm.seq[int(asm.offsets[i]): int(asm.offsets[i + 1])].tobytes() for i in sample]
+    ref_counts, _ = O.count_sequences(seqs, 5)
+    assert np.array_equal(res["counts"][torch.from_numpy(sample).cuda()].cpu().numpy(), ref_counts)
+    Xs = X[torch.from_numpy(sample).cuda()].cpu().numpy()
+    if method == "am_clr":
+        refX = O.am_clr(ref_counts.astype(np.float64))[0]  # no column is absent at this size
+    else:
+        refX = O.ilr(ref_counts.astype(np.float64))
+        clr_rows = O.clr(ref_counts.astype(np.float64))
+        assert np.allclose((Xs ** 2).sum(1), (clr_rows ** 2).sum(1), rtol=1e-11, atol=0)  # ilr is an isometry
+    assert np.max(np.abs(Xs - refX) / np.max(np.abs(refX), axis=1, keepdims=True)) <= 1e-12
+    V = res["components"].cpu().numpy()
+    ev, evr = res["explained_variance"].cpu().numpy(), res["explained_variance_ratio"].cpu().numpy()
+    assert np.max(np.abs(V @ V.T - np.eye(50))) < 1e-11
+    j = np.argmax(np.abs(V), axis=1)
+    assert np.all(V[np.arange(50), j] > 0)  # svd_flip(u_based_decision=False)
+    assert np.all(np.diff(ev) <= 0) and ev[-1] > 0
+    mean = X.mean(dim=0, dtype=torch.float64)
+    var_scores = ((S - S.mean(dim=0)) ** 2).sum(dim=0) / (n - 1)
+    assert np.allclose(var_scores.cpu().numpy(), ev, rtol=1e-9, atol=0)
+    assert float(S.mean(dim=0).abs().max()) < 1e-9 * float(S.abs().max())
+    trace = float((((X - mean) ** 2).sum(dim=0) / (n - 1)).sum())
+    assert np.allclose(evr, ev / trace, rtol=1e-9, atol=0)
+    s_ref = (Xs - mean.cpu().numpy()) @ V.T
+    s_got = S[torch.from_numpy(sample).cuda()].cpu().numpy()
+    assert np.max(np.abs(s_got - s_ref)) <= 1e-8 * float(S.abs().max())
+    # C V^T = V^T diag(ev): the components are eigenvectors of the sample covariance
+    Xc = X - mean
+    CV = (Xc.T @ (Xc @ res["components"].T)) / (n - 1)
+    resid = (CV - res["components"].T * res["explained_variance"]).abs().max()
+    assert float(resid) <= 1e-9 * float(ev[0])
