@@ -224,8 +224,11 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // with 4 MMAs per K step (N = 256, 128, 256, 128) instead of 10, and each CTA stages only 3 A planes
 // and 4 B planes (20 KB per stage instead of 36 KB).  CTA1 also forms the weight-6 pairs (1,5), (3,3),
 // (5,1): more of the exact product, not less.  Both CTAs write a partial tile; the reduce kernel sums.
-constexpr int G2_STAGES = 8;
-constexpr uint32_t G2_STAGE_BYTES = 3u * GI_A_BYTES + 4u * GI_B_BYTES;  // 20480
+constexpr int G2_KS = 2;          // K steps (GI_K = 32 rows each) per pipeline stage: one box load covers 64 rows
+constexpr int G2_STAGES = 5;
+constexpr int G2_THREADS = 256;  // warp 0: TMA (A planes), 1: MMA issuer, 2-5: epilogue, 6, 7: TMA (B planes)
+constexpr uint32_t G2_A_BYTES = G2_KS * GI_A_BYTES, G2_B_BYTES = G2_KS * GI_B_BYTES;  // per plane per stage
+constexpr uint32_t G2_STAGE_BYTES = 3u * G2_A_BYTES + 4u * G2_B_BYTES;  // 40960
 
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -265,8 +268,10 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
-template <int NS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_THREADS, 1)
+// PROBE = true compiles in the AM_GRAM_DBG switch-off flags (timing probes); the production
+// instance has none of those branches (they cost 9 % in the MMA-issuing thread).
+template <int NS, bool PROBE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gram_i8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  GramI8Params p, double *__restrict__ part) {
   extern __shared__ uint8_t smem_raw[];
@@ -296,9 +301,12 @@ gram_i8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = s_tmem;
 
-  if (warp == 0) {
-    // ===== TMA producer (both CTAs; every load signals the LEADER's full barrier) =====
+  if (warp == 0 || warp >= 6) {
+    // ===== TMA producers (both CTAs; every load signals the LEADER's full barrier).  Issuing the 7 box
+    // loads of a stage from one thread costs more than its MMAs take, so three warps share them:
+    // warp 0 arms the barrier and loads the 3 A planes, warps 6 and 7 load 2 B planes each. =====
     if (lane == 0) {
+      const bool do_a = warp == 0;
       int stage = 0;
       uint32_t phase = 0;
       const int bplane[2][4] = {{0, 1, 4, 0}, {2, 3, 5, 1}};
@@ -308,21 +316,26 @@ gram_i8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         decode_tile(tile, p.TJ, I, Jb);
         const int row0 = chunk * p.rows_per_chunk;
         const int row1 = min(p.n_rows, row0 + p.rows_per_chunk);
-        for (int r = row0; r < row1; r += GI_K) {
+        for (int r = row0; r < row1; r += G2_KS * GI_K) {
           mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
           const uint32_t lfb = mapa_shared(bar_full + 8u * stage, 0);
-          if (p.dbg_mode & 2) {  // timing probe: no loads, MMAs run on whatever is in shared memory
-            if (rank == 0) mbar_arrive(bar_full + 8u * stage);
+          if (PROBE && (p.dbg_mode & 2)) {  // timing probe: no loads, MMAs run on whatever is in shared memory
+            if (rank == 0 && do_a) mbar_arrive(bar_full + 8u * stage);
             if (++stage == NS) { stage = 0; phase ^= 1u; }
             continue;
           }
-          if (rank == 0) mbar_expect_tx(bar_full + 8u * stage, 2u * G2_STAGE_BYTES);
           const uint32_t sa = base + (uint32_t)stage * G2_STAGE_BYTES;
-          const uint32_t sb = sa + 3u * GI_A_BYTES;
+          const uint32_t sb = sa + 3u * G2_A_BYTES;
+          if (do_a) {
+            if (rank == 0) mbar_expect_tx(bar_full + 8u * stage, 2u * G2_STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < 3; ++k) tma_load_3d_2sm(sa + (uint32_t)k * GI_A_BYTES, &tmA, I * GI_M, r, 2 * k + (int)rank, lfb);
+            for (int k = 0; k < 3; ++k) tma_load_3d_2sm(sa + (uint32_t)k * G2_A_BYTES, &tmA, I * GI_M, r, 2 * k + (int)rank, lfb);
+          } else {
+            const int q0 = 2 * (warp - 6);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) tma_load_3d_2sm(sb + (uint32_t)q * GI_B_BYTES, &tmB, Jb * GI_N, r, bplane[rank][q], lfb);
+            for (int q = 0; q < 2; ++q)
+              tma_load_3d_2sm(sb + (uint32_t)(q0 + q) * G2_B_BYTES, &tmB, Jb * GI_N, r, bplane[rank][q0 + q], lfb);
+          }
           if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
       }
@@ -335,6 +348,13 @@ gram_i8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t id256 = idesc0 | ((uint32_t)(256 >> 3) << 17), id128 = idesc0 | ((uint32_t)(128 >> 3) << 17);
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
+      // A plane of a stage: 64 rows x 128 B (SW128 atoms of 8 rows); B plane: 64 rows x 64 B (SW64), planes
+      // G2_B_BYTES apart (= the stride between the N atoms of one MMA); K step h starts 32 rows further in
+      const uint32_t sb0 = base + 3u * G2_A_BYTES;
+      const uint64_t dA0 = make_desc(base, GI_K * 128, 1024, 2), dA1 = make_desc(base + G2_A_BYTES, GI_K * 128, 1024, 2),
+                     dA2 = make_desc(base + 2u * G2_A_BYTES, GI_K * 128, 1024, 2);
+      const uint64_t dB0 = make_desc(sb0, G2_B_BYTES, 512, 4), dB2 = make_desc(sb0 + 2u * G2_B_BYTES, G2_B_BYTES, 512, 4),
+                     dB3 = make_desc(sb0 + 3u * G2_B_BYTES, G2_B_BYTES, 512, 4);
       for (int item = pair; item < n_items; item += n_pairs) {
         const int chunk = item / p.n_tiles;
         const int row0 = chunk * p.rows_per_chunk;
@@ -342,22 +362,24 @@ gram_i8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(bar_acce, acc_phase ^ 1u);
         tc_fence_after();
         uint32_t acc = 0u;
-        for (int r = row0; r < row1; r += GI_K) {
+        for (int r = row0; r < row1; r += G2_KS * GI_K) {
           mbar_wait(bar_full + 8u * stage, phase);
           tc_fence_after();
-          const uint32_t sa = base + (uint32_t)stage * G2_STAGE_BYTES;
-          const uint32_t sb = sa + 3u * GI_A_BYTES;
-          const uint64_t a0 = make_desc(sa, GI_K * 128, 1024, 2), a1 = make_desc(sa + GI_A_BYTES, GI_K * 128, 1024, 2),
-                         a2 = make_desc(sa + 2u * GI_A_BYTES, GI_K * 128, 1024, 2);
-          const uint64_t b0 = make_desc(sb, GI_B_BYTES, 512, 4), b2 = make_desc(sb + 2u * GI_B_BYTES, GI_B_BYTES, 512, 4),
-                         b3 = make_desc(sb + 3u * GI_B_BYTES, GI_B_BYTES, 512, 4);
-          if (!(p.dbg_mode & 1)) {
-          umma_i8_2sm(tmem + 0u * GI_N, a0, b0, id256, acc);   // planes (0|1) x B(0,1 | 2,3)   -> idx 0..3
-          umma_i8_2sm(tmem + 4u * GI_N, a0, b2, id128, acc);   // planes (0|1) x B(4 | 5)       -> idx 4,5
-          umma_i8_2sm(tmem + 2u * GI_N, a1, b0, id256, 1u);    // planes (2|3) x B(0,1 | 2,3)   -> idx 2..5
-          umma_i8_2sm(tmem + 4u * GI_N, a2, b3, id128, 1u);    // planes (4|5) x B(0 | 1)       -> idx 4,5
+          // descriptors of this stage = stage-0 descriptors + stage offset (address field, 16-byte units)
+          const uint64_t so = (uint64_t)((uint32_t)stage * (G2_STAGE_BYTES >> 4));
+#pragma unroll
+          for (int h = 0; h < G2_KS; ++h) {
+            if (r + h * GI_K >= row1) break;  // chunks end on multiples of 32 rows, not of 64
+            const uint64_t oa = so + (uint64_t)(h * (GI_A_BYTES >> 4)), ob = so + (uint64_t)(h * (GI_B_BYTES >> 4));
+            const uint64_t a0 = dA0 + oa, a1 = dA1 + oa, a2 = dA2 + oa, b0 = dB0 + ob, b2 = dB2 + ob, b3 = dB3 + ob;
+            if (!(PROBE && (p.dbg_mode & 1))) {
+              umma_i8_2sm(tmem + 0u * GI_N, a0, b0, id256, acc);   // planes (0|1) x B(0,1 | 2,3)   -> idx 0..3
+              umma_i8_2sm(tmem + 4u * GI_N, a0, b2, id128, acc);   // planes (0|1) x B(4 | 5)       -> idx 4,5
+              umma_i8_2sm(tmem + 2u * GI_N, a1, b0, id256, 1u);    // planes (2|3) x B(0,1 | 2,3)   -> idx 2..5
+              umma_i8_2sm(tmem + 4u * GI_N, a2, b3, id128, 1u);    // planes (4|5) x B(0 | 1)       -> idx 4,5
+            }
+            acc = 1u;
           }
-          acc = 1u;
           umma_commit_2sm(bar_empty + 8u * stage);
           if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
@@ -376,7 +398,7 @@ gram_i8x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int chunk = item / p.n_tiles, tile = item % p.n_tiles;
       const size_t pidx = ((size_t)(chunk + (int)rank * p.n_chunks) * p.n_tiles + tile);
       double *out = part + (pidx * GI_M + (size_t)(q * 32 + lane)) * GI_N;
-      for (int c = 0; c < ((p.dbg_mode & 4) ? 0 : GI_N / 16); ++c) {
+      for (int c = 0; c < ((PROBE && (p.dbg_mode & 4)) ? 0 : GI_N / 16); ++c) {
         double g[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) g[j] = 0.0;
@@ -608,22 +630,39 @@ extern "C" int am_gram_planes(const int8_t *d_planes, int64_t n_rows, int D, int
   int n_parts = p.n_chunks;
   const char *pm = getenv("AM_GRAM_PAIR");
   const bool use_pair = (S == 6) && !(pm && pm[0] == '0');
+  CUtensorMap tmA2, tmB2;  // the pair kernel loads 64-row boxes
   if (use_pair) {
     // CTA pairs (cta_group::2): one cluster of 2 per work item
+    {
+      cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)n_rows, (cuuint64_t)S};
+      cuuint64_t gstr[2] = {(cuuint64_t)Dp, (cuuint64_t)Dp * (cuuint64_t)n_rows};
+      cuuint32_t estr[3] = {1, 1, 1};
+      cuuint32_t boxA[3] = {GI_M, G2_KS * GI_K, 1};
+      cuuint32_t boxB[3] = {GI_N, G2_KS * GI_K, 1};
+      CUresult r1 = encode(&tmA2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)d_planes, gdim, gstr, boxA, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CUresult r2 = encode(&tmB2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)d_planes, gdim, gstr, boxB, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return am::fail(AM_ECUDA, "am_gram_planes: cuTensorMapEncodeTiled failed");
+    }
     const char *sv = getenv("AM_GRAM_STAGES");
     const int ns = sv ? atoi(sv) : G2_STAGES;
     const size_t smem = (size_t)ns * G2_STAGE_BYTES + 16 * (size_t)ns + 64 + 1024;
     const int n_items = p.n_chunks * p.n_tiles;
     const int pairs = std::max(1, std::min(n_items, am::num_sms() / 2));
-    if (ns == 5) {
-      AM_CUDA(cudaFuncSetAttribute(gram_i8x2_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gram_i8x2_kernel<5><<<2 * pairs, GI_THREADS, smem, st>>>(tmA, tmB, p, part);
-    } else if (ns == 11) {
-      AM_CUDA(cudaFuncSetAttribute(gram_i8x2_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gram_i8x2_kernel<11><<<2 * pairs, GI_THREADS, smem, st>>>(tmA, tmB, p, part);
+    auto launch = [&](auto kern) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      kern<<<2 * pairs, G2_THREADS, smem, st>>>(tmA2, tmB2, p, part);
+      return cudaGetLastError();
+    };
+    if (p.dbg_mode || sv) {  // probes: AM_GRAM_DBG bit flags, AM_GRAM_STAGES in {3, 5}
+      if (ns == 3) AM_CUDA(launch(gram_i8x2_kernel<3, true>));
+      else AM_CUDA(launch(gram_i8x2_kernel<G2_STAGES, true>));
     } else {
-      AM_CUDA(cudaFuncSetAttribute(gram_i8x2_kernel<G2_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gram_i8x2_kernel<G2_STAGES><<<2 * pairs, GI_THREADS, smem, st>>>(tmA, tmB, p, part);
+      AM_CUDA(launch(gram_i8x2_kernel<G2_STAGES, false>));
     }
     AM_LAUNCHED("gram_i8x2_kernel");
     n_parts = 2 * p.n_chunks;

@@ -240,7 +240,7 @@ __device__ __forceinline__ void digits6(double v, int (&a)[6]) {
 // corrected by n (mu - centre)(mu - centre)^T afterwards).  Lane owns columns 128 m + 4 lane + e:
 // 16-byte count loads, 4-byte digit stores (128 contiguous bytes per warp instruction).
 template <int METHOD>
-__global__ void __launch_bounds__(NWARPS * 32)
+__global__ void __launch_bounds__(NWARPS * 32, 2)  // two CTAs per SM: the pass is latency-bound at 8 warps
 normalize512_planes_kernel(const int32_t *__restrict__ counts, int64_t n_out,
                            const int64_t *__restrict__ row_index, double *__restrict__ out,
                            double *__restrict__ psum, const double *__restrict__ center,
@@ -251,13 +251,21 @@ normalize512_planes_kernel(const int32_t *__restrict__ counts, int64_t n_out,
   double *cen = sm + LOGT;        // [16][32] permuted: value i of lane l at i*32 + l
   double *scl = cen + D;          // same layout
   double *red = scl + D;          // NWARPS * D
+  double *coef = red + NWARPS * D;  // ilr only: sqrt(c / (c + 1)) and 1 / c, same permuted layout
+  double *rcp = coef + D;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < LOGT; i += blockDim.x) logt[i] = log((double)(i + 1));
   for (int q = threadIdx.x; q < D; q += blockDim.x) {
     const int i = q >> 5, l = q & 31;
     const int col = 128 * (i >> 2) + 4 * l + (i & 3);
-    cen[q] = center[col];
-    scl[q] = sc[col];
+    // ilr has D - 1 output columns; the pad column is written as exact zeros
+    const bool pad = METHOD == 2 && col == D - 1;
+    cen[q] = pad ? 0.0 : center[col];
+    scl[q] = pad ? 0.0 : sc[col];
+    if (METHOD == 2) {
+      coef[q] = col ? sqrt((double)col / (double)(col + 1)) : 0.0;
+      rcp[q] = col ? 1.0 / (double)col : 0.0;
+    }
   }
   __syncthreads();
   double csum[16];
@@ -292,18 +300,56 @@ normalize512_planes_kernel(const int32_t *__restrict__ counts, int64_t n_out,
       for (int o2 = 16; o2 > 0; o2 >>= 1) z += __shfl_xor_sync(FULL, z, o2);
       const double delta = (1.0 / (double)D) * (1.0 / (double)D);
       const double scale = 1.0 - (double)z * delta;
+      // closure of the replaced row: q = x / S * scale; one reciprocal per row instead of 512
+      // divisions (differs from x / S in the last bit at most, 1e-16 of the 1e-12 budget)
+      const double sS = scale / S;
       double Q = 0.0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) Q += xv[i] == 0 ? delta : scale * ((double)xv[i] / S);
+      for (int i = 0; i < 16; ++i) Q += xv[i] == 0 ? delta : sS * (double)xv[i];
       Q = warp_sum(Q);
       const double lzero = log(delta / Q);
       const double lscale = log(scale / S / Q);
       double sl = 0.0;
 #pragma unroll
       for (int i = 0; i < 16; ++i) { l[i] = xv[i] == 0 ? lzero : (log_int(logt, xv[i]) + lscale); sl += l[i]; }
-      const double mean = warp_sum(sl) / (double)D;
+      if (METHOD == 1) {
+        const double mean = warp_sum(sl) / (double)D;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) l[i] -= mean;
+        for (int i = 0; i < 16; ++i) l[i] -= mean;
+      } else {
+        // ilr: out_{c-1} = sqrt(c/(c+1)) (mean(l[0:c]) - l[c]) (centring cancels).  Exclusive prefix
+        // sums in column order c = 128 m + 4 lane + e: lane-local, then a warp scan per 128-column block.
+        double v[16];
+        double carry = 0.0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const double s4 = (l[4 * m] + l[4 * m + 1]) + (l[4 * m + 2] + l[4 * m + 3]);
+          double incl = s4;
+#pragma unroll
+          for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            const double t = __shfl_up_sync(FULL, incl, o2);
+            if (lane >= o2) incl += t;
+          }
+          double pre = carry + (incl - s4);
+          carry += __shfl_sync(FULL, incl, 31);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = 4 * m + e;
+            v[i] = coef[i * 32 + lane] * (pre * rcp[i * 32 + lane] - l[i]);
+            pre += l[i];
+          }
+        }
+        // shift by one column so that lane/slot (m, e) holds output column 128 m + 4 lane + e
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const double nxt = __shfl_sync(FULL, v[4 * m], (lane + 1) & 31);
+          const double wrap = m < 3 ? __shfl_sync(FULL, v[m < 3 ? 4 * (m + 1) : 0], 0) : 0.0;
+          l[4 * m] = v[4 * m + 1];
+          l[4 * m + 1] = v[4 * m + 2];
+          l[4 * m + 2] = v[4 * m + 3];
+          l[4 * m + 3] = lane == 31 ? wrap : nxt;
+        }
+      }
     }
     double2 *o2p = reinterpret_cast<double2 *>(out + r * D) + 2 * lane;
     uint32_t *pl = reinterpret_cast<uint32_t *>(planes + (size_t)r * D) + lane;
@@ -521,17 +567,22 @@ extern "C" int am_normalize_planes(const int32_t *d_counts, int64_t n_rows_out, 
                                    double *d_colsum, const double *d_center, const double *d_sc, int S,
                                    int8_t *d_planes, void *d_work, void *stream) {
   if (D != 512 || S != 6) return am::fail(AM_EINVAL, "am_normalize_planes: only D = 512 (k = 5) and S = 6");
-  if (method != AM_NORM_AM_CLR && method != AM_NORM_CLR) return am::fail(AM_EINVAL, "am_normalize_planes: am_clr or clr");
+  if (method != AM_NORM_AM_CLR && method != AM_NORM_CLR && method != AM_NORM_ILR)
+    return am::fail(AM_EINVAL, "am_normalize_planes: unknown method");
   if (n_rows_out == 0) return AM_OK;
   if (!d_counts || !d_out || !d_colsum || !d_center || !d_sc || !d_planes || !d_work || n_rows_out < 0)
     return am::fail(AM_EINVAL, "am_normalize_planes: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = norm_grid(n_rows_out);
   double *partials = (double *)d_work;
-  const size_t smem = (size_t)(LOGT + 2 * 512 + NWARPS * 512) * sizeof(double);
+  const size_t smem = (size_t)(LOGT + 4 * 512 + NWARPS * 512) * sizeof(double);
   if (method == AM_NORM_AM_CLR) {
     AM_CUDA(cudaFuncSetAttribute(normalize512_planes_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     normalize512_planes_kernel<0><<<grid, NWARPS * 32, smem, st>>>(d_counts, n_rows_out, d_row_index, d_out, partials,
+                                                                   d_center, d_sc, d_planes);
+  } else if (method == AM_NORM_ILR) {
+    AM_CUDA(cudaFuncSetAttribute(normalize512_planes_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    normalize512_planes_kernel<2><<<grid, NWARPS * 32, smem, st>>>(d_counts, n_rows_out, d_row_index, d_out, partials,
                                                                    d_center, d_sc, d_planes);
   } else {
     AM_CUDA(cudaFuncSetAttribute(normalize512_planes_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -217,7 +217,8 @@ def alloc_planes(n: int, D: int, dev, slices: int = GRAM_SLICES):
 def normalize_planes(counts, method: str, row_index, center, sc, colsum, out=None, planes=None,
                      slices: int = GRAM_SLICES):
     """Fused kernel 2 + quantisation (D = 512): fp64 rows, column sums and the int8 digit planes of
-    ``round((x - center) * sc)`` in one pass."""
+    ``round((x - center) * sc)`` in one pass.  ``center``/``sc``/``colsum`` have 512 entries; for ilr
+    the returned matrix is the 511-column view of a pitch-512 buffer (last column zero)."""
     import torch
 
     dev = counts.device
@@ -235,7 +236,7 @@ def normalize_planes(counts, method: str, row_index, center, sc, colsum, out=Non
                                       L.t_ptr(colsum), L.t_ptr(center), L.t_ptr(sc), slices, L.t_ptr(planes),
                                       L.t_ptr(work), L.stream_ptr(dev))
         )
-    return out, planes
+    return (out[:, : D - 1] if method == "ilr" else out), planes
 
 
 def quantize_planes(X, center, sc, planes=None, slices: int = GRAM_SLICES):

@@ -40,20 +40,23 @@ def _fit_project(packed, counts, method, n_components, row_index, col_index, gro
     Dk = D if col_index is None else int(col_index.numel())
     Dout = Dk - 1 if method == "ilr" else Dk
     n_out = counts.shape[0] if row_index is None else int(row_index.numel())
-    zbuf = torch.zeros(2 * Dout + D + 2, dtype=torch.float64, device=dev)  # cs | cm | sample sums + count
+    zbuf = torch.zeros(2 * D + D + 2, dtype=torch.float64, device=dev)  # cs | cm | sample sums + count
     cs = zbuf[:Dout]
-    fused = method in ("am_clr", "clr") and D == 512 and col_index is None and n_out > 0
+    fused = method in ("am_clr", "clr", "ilr") and D == 512 and col_index is None and n_out > 0
     planes = e = center = None
     if fused:
         # provisional centre from a strided row sample (the exact mean needs the full pass);
         # fixed-point range from the hard bound of the transform: |am_clr| <= log1p(longest
-        # contig), |clr| <= log(D^2) + 1
+        # contig), |clr|, |ilr| <= log(max(D^2, longest contig)) + 1
         sample = _sample_rows(n_out, dev, packed._plans)
         ns = int(sample.numel())
         if row_index is not None:
             sample = row_index[sample]
-        cs_s = zbuf[2 * Dout : 2 * Dout + D + 1]
-        _dev.normalize_counts(counts, method, sample, None, colsum=cs_s[:D])
+        cs_s = zbuf[2 * D : 2 * D + D + 1]
+        if method == "ilr":  # the generic ilr kernel has no fused column sums; 2048 x 511 is tiny
+            cs_s[:Dout] = _dev.normalize_counts(counts, method, sample, None).sum(dim=0)
+        else:
+            _dev.normalize_counts(counts, method, sample, None, colsum=cs_s[:D])
         if distributed:
             cs_s[D] = float(ns)
             _dist.allreduce_sum_([cs_s], group)
@@ -66,9 +69,15 @@ def _fit_project(packed, counts, method, n_components, row_index, col_index, gro
                 bound = float(np.log1p(float(packed.lengths.max()) if packed.n_contigs else 1.0))
                 packed._plans["log1p_maxlen"] = bound
         else:
-            bound = float(2.0 * np.log(D) + 1.0)
+            # |clr|, |ilr| <= max log q - min log q <= log(1 / min q), min q >= min(1/D^2, 1/(row sum))
+            bound = packed._plans.get("log_range")
+            if bound is None:
+                longest = float(packed.lengths.max()) if packed.n_contigs else 1.0
+                bound = float(max(2.0 * np.log(D), np.log(max(longest, 1.0))) + 1.0)
+                packed._plans["log_range"] = bound
         e, sc = _dev.plane_scales(center, None, bound)
-        X, planes = _dev.normalize_planes(counts, method, row_index, center, sc, cs)
+        X, planes = _dev.normalize_planes(counts, method, row_index, center, sc, zbuf[:D])
+        center = center[:Dout]
     elif method == "ilr" or Dout > 1024:
         X = _dev.normalize_counts(counts, method, row_index, col_index)
         cm = zbuf[Dout : 2 * Dout]

@@ -188,11 +188,13 @@ int am_normalize(const int32_t *d_counts, int64_t n_rows_out, int D,
                  int method, double *d_out, double *d_colsum, double *d_colmaxabs, void *d_work,
                  void *stream);
 
-/* Fused normalise + quantise for the k = 5 table (D = 512, S = 6, am_clr or clr): one pass writes
- * the fp64 rows, adds the column sums and writes the int8 digit planes of
+/* Fused normalise + quantise for the k = 5 table (D = 512, S = 6; am_clr, clr or ilr): one pass
+ * writes the fp64 rows, adds the column sums and writes the int8 digit planes of
  * round((out - centre_j) sc_j) (layout of am_quantize_planes) that am_gram_planes and
  * am_project_planes consume.  d_center[512] is a provisional centre (e.g. the column means of a
- * row sample normalised first); d_sc from am_plane_scales. */
+ * row sample normalised first); d_sc from am_plane_scales.  ilr has 511 output columns: d_out,
+ * d_colsum and the planes keep a pitch of 512 with an all-zero last column (entry 511 of
+ * d_center / d_sc is ignored). */
 int am_normalize_planes(const int32_t *d_counts, int64_t n_rows_out, int D,
                         const int64_t *d_row_index, int method, double *d_out, double *d_colsum,
                         const double *d_center, const double *d_sc, int S, int8_t *d_planes,

@@ -74,6 +74,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) probe2(int rota
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_base;
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar2;
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const uint32_t sa = (smem_u32(smem) + 1023u) & ~1023u;
@@ -81,7 +82,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) probe2(int rota
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x == 0) mbar_init(smem_u32(&bar), 1);
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -93,8 +94,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) probe2(int rota
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
       const uint32_t o = rotate ? (uint32_t)(r & 3) * 16384u : 0u;
-      const uint32_t tcol = rotate >= 2 ? 0u : (uint32_t)((r & 1) * 256);  // rotate 2: every MMA accumulates into the same columns
+      const uint32_t tcol = rotate == 2 ? 0u : (uint32_t)((r & 1) * 256);  // rotate 2: every MMA accumulates into the same columns
       umma_i8_2sm(td + tcol, make_desc(sa + o, 32 * 128, 1024, 2), make_desc(sa + o + 4096u, 2048, 512, 4), idm, 1u);
+      // rotate 3 / 4: a tcgen05.commit (to a scratch barrier nobody waits on) after every 4th / 8th MMA
+      if ((rotate == 3 && (r & 3) == 3) || (rotate == 4 && (r & 7) == 7))
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&bar2)), "h"((uint16_t)3) : "memory");
     }
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(&bar)), "h"((uint16_t)1) : "memory");
@@ -114,7 +119,7 @@ int main() {
   cudaFuncSetAttribute(probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const char *names[] = {"i8  MN-major", "i8  K-major ", "bf16 K-major", "i8  MN rotating operands"};
   for (int N : {256, 128})
-    for (int rot = 1; rot < 3; ++rot) {
+    for (int rot = 1; rot < 5; ++rot) {
       const int reps = 4000;
       for (int it = 0; it < 2; ++it) probe2<<<148, 128, 100 * 1024>>>(rot, reps, N, d);
       cudaError_t e = cudaDeviceSynchronize();
