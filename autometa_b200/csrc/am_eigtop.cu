@@ -322,6 +322,292 @@ tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriO
   cluster.sync();  // no CTA exits while a peer may still address its shared memory
 }
 
+// Register-resident variant for np <= 512 (the k = 5 table): the smem pass over the trailing matrix (16 B
+// of shared-memory traffic per element and step) was the longest phase of a step; with 8 warps x 4 rows
+// x 16 columns per lane the CTA's 32 x 512 block lives in 128 registers per thread and only the three
+// operand vectors are read from shared memory.
+constexpr int RT = 256;       // threads per CTA
+constexpr int RW = RT / 32;   // warps
+constexpr int RR = 4;         // local rows per warp (RL <= 32)
+constexpr int NB = 16;        // 32-column blocks per row (np <= 512)
+constexpr int JG = 4;         // column blocks per branch in the update pass
+
+// PROBE = true: per-phase cycle counters (scripts/dev_eig_once.py, AM_TRIDIAG_PROBE=1); off in production
+template <bool PROBE>
+__global__ void __cluster_dims__(TC, 1, 1) __launch_bounds__(RT, 1)
+tridiag_reg_kernel(const double *__restrict__ A, int n, int np, int RL, TriOut out) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int c = (int)cluster.block_rank();
+  extern __shared__ double sm[];
+  double *rows = sm;                          // RL x np
+  double *vb = rows + (size_t)RL * np;        // 2 x np   scaled reflectors v_{k-1}, v_k
+  double *wb = vb + 2 * np;                   // 2 x np   w_{k-1}, w_k
+  double *xs = wb + 2 * np;                   // 2 x np   unscaled columns x_k (mat-vec operand)
+  double2 *inbox = reinterpret_cast<double2 *>(xs + 2 * np);  // 2 x np  {y_i, A[i][k+1]}
+  double *red = reinterpret_cast<double *>(inbox + 2 * np);   // 4 x TW rotating reduction slots
+  double *sigp = red + 4 * TW;                // 2 x TW   per-warp partials of sigma (layout shared with the other kernel)
+  __shared__ __align__(8) unsigned long long s_mbar[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t mbar0 = (uint32_t)__cvta_generic_to_shared(&s_mbar[0]);
+  const uint32_t inbox_s = (uint32_t)__cvta_generic_to_shared(inbox);
+  
+  for (int lr = 0; lr < RL; ++lr) {
+    const int i = c + TC * lr;
+    for (int j = tid; j < np; j += RT) {
+      double a = 0.0;
+      if (i < n && j < n) a = 0.5 * (__ldg(A + (size_t)i * n + j) + __ldg(A + (size_t)j * n + i));
+      rows[(size_t)lr * np + j] = a;
+    }
+  }
+  for (int j = tid; j < 2 * np; j += RT) { vb[j] = 0.0; wb[j] = 0.0; xs[j] = 0.0; inbox[j] = make_double2(0.0, 0.0); }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster.sync();  // every CTA's buffers and mbarriers exist before any remote store
+
+  // prologue: all-gather column 0 (inbox slot 1, .y component), form x_0
+  if (tid == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar0 + 8u), "r"((uint32_t)(n - 1) * 16u) : "memory");
+  for (int lr = warp; lr < RL; lr += RW) {
+    const int i = c + TC * lr;
+    if (i < n && i >= 1 && lane < TC)
+      st_async_f64x2(mapa_u32(inbox_s + (uint32_t)(np + i) * 16u, lane), 0.0, rows[(size_t)lr * np + 0],
+                     mapa_u32(mbar0 + 8u, lane));
+  }
+  mbar_wait_cluster(mbar0 + 8u, 0u);
+  double x[NE];
+#pragma unroll
+  for (int m = 0; m < NE; ++m) x[m] = 0.0;
+  if (warp < AW) {
+    double sp = 0.0;
+#pragma unroll
+    for (int m = 0; m < NE; ++m) {
+      const int i = tid + AT * m;
+      if (i >= 1 && i < n) x[m] = inbox[np + i].y;
+      if (i < np) xs[i] = x[m];
+      if (i >= 2) sp = fma(x[m], x[m], sp);
+    }
+    sp = warp_sum(sp);
+    if (lane == 0) sigp[warp] = sp;
+  }
+  __syncthreads();
+
+  // the CTA's rows move into registers: warp w owns local rows w + 8 r, lane l the columns l + 32 jj
+  double am[RR][NB];
+#pragma unroll
+  for (int r = 0; r < RR; ++r) {
+    const int lr = warp + RW * r;
+#pragma unroll
+    for (int jj = 0; jj < NB; ++jj) {
+      const int j = 32 * jj + lane;
+      am[r][jj] = (lr < RL && j < np) ? rows[(size_t)lr * np + j] : 0.0;
+    }
+  }
+  int rslot = 0;
+  long long tA = 0, tB = 0, tS = 0, tC = 0, tB1 = 0, tB2 = 0, t0 = PROBE ? clock64() : 0, t1 = 0;
+long long tprev = 0;
+#define AM_TICK(acc) do { if (PROBE) { t1 = clock64(); acc += t1 - t0; tprev = t0; t0 = t1; } } while (0)
+  for (int k = 0; k <= n - 3; ++k) {
+    const int cur = k & 1, prv = (k + 1) & 1;
+    double *vcur = vb + cur * np, *wcur = wb + cur * np;
+    const double *vprev = vb + prv * np, *wprev = wb + prv * np;
+    const double *xk = xs + cur * np;
+    // arm this step's inbox: rows k+1..n-1 each deliver 16 bytes
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                   ::"r"(mbar0 + 8u * cur), "r"((uint32_t)(n - k - 1) * 16u) : "memory");
+    // ---- B. fused pass over own rows >= k, matrix in registers: pending update (k-1), y = A x_k
+    {
+      const int kb = k >> 5, jb1 = (k + 1) >> 5, l1 = (k + 1) & 31;
+      bool act[RR];
+      double vpi[RR], wpi[RR], acc[RR], a1v[RR];
+      bool any = false;
+#pragma unroll
+      for (int r = 0; r < RR; ++r) {
+        const int lr = warp + RW * r;
+        const int i = c + TC * lr;
+        act[r] = lr < RL && i < n && i >= k;
+        vpi[r] = act[r] ? vprev[i] : 0.0;
+        wpi[r] = act[r] ? wprev[i] : 0.0;
+        acc[r] = 0.0;
+        a1v[r] = 0.0;
+        any |= act[r];
+      }
+      if (any) {
+        // column blocks in groups of JG: one (warp-uniform) branch per group, so that the loads and the
+        // 3-deep fp64 chains of JG x RR elements are scheduled together (a branch per block serialises
+        // load latency + chain latency 16 times per step)
+#pragma unroll
+        for (int g = 0; g < NB / JG; ++g) {
+          if (JG * g + JG - 1 >= kb && 32 * JG * g < np) {
+            double vpj[JG], wpj[JG], xj[JG];
+#pragma unroll
+            for (int q = 0; q < JG; ++q) {
+              const int j = 32 * (JG * g + q) + lane;
+              const bool ok = j < np;
+              vpj[q] = ok ? vprev[j] : 0.0;
+              wpj[q] = ok ? wprev[j] : 0.0;
+              xj[q] = ok ? xk[j] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < JG; ++q) {
+              const int jj = JG * g + q;
+#pragma unroll
+              for (int r = 0; r < RR; ++r) {
+                if (act[r]) {
+                  double a = am[r][jj];
+                  a = fma(-vpi[r], wpj[q], a);
+                  a = fma(-wpi[r], vpj[q], a);
+                  am[r][jj] = a;
+                  acc[r] = fma(a, xj[q], acc[r]);
+                }
+              }
+            }
+          }
+        }
+        // post-update A[i][k+1] lives in column block jb1 of lane l1 (picked up outside the update code:
+        // a test per block inside it splits the block into branches)
+#define AM_PICK(JJ) case JJ: a1v[0] = am[0][JJ]; a1v[1] = am[1][JJ]; a1v[2] = am[2][JJ]; a1v[3] = am[3][JJ]; break;
+        switch (jb1) {
+          AM_PICK(0) AM_PICK(1) AM_PICK(2) AM_PICK(3) AM_PICK(4) AM_PICK(5) AM_PICK(6) AM_PICK(7)
+          AM_PICK(8) AM_PICK(9) AM_PICK(10) AM_PICK(11) AM_PICK(12) AM_PICK(13) AM_PICK(14) AM_PICK(15)
+          default: break;
+        }
+#undef AM_PICK
+        AM_TICK(tB1);
+        if (PROBE && out.dbg && c == 0 && tid == 0 && (k & 63) == 0 && (k >> 6) < 8) out.dbg[8 + (k >> 6)] = t1 - tprev;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int r = 0; r < RR; ++r) acc[r] += __shfl_xor_sync(FULL, acc[r], o);
+        }
+        AM_TICK(tB2);
+        const uint32_t rbar = mapa_u32(mbar0 + 8u * cur, (uint32_t)(lane & (TC - 1)));
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+          const double a1 = __shfl_sync(FULL, a1v[r], l1);  // post-update A[i][k+1]
+          const int i = c + TC * (warp + RW * r);
+          if (act[r] && i >= k + 1 && lane < TC)
+            st_async_f64x2(mapa_u32(inbox_s + (uint32_t)(cur * np + i) * 16u, lane), acc[r], a1, rbar);
+        }
+      }
+    }
+    AM_TICK(tB);
+    // ---- S. reflector scalars while the inbox fills (algebra warps only)
+    double beta = 0.0, tau = 0.0, scale = 0.0;
+    double v[NE];
+    if (warp < AW) {
+      double sigma = 0.0;
+#pragma unroll
+      for (int w = 0; w < AW; ++w) sigma += sigp[cur * AW + w];
+      const double alpha = xk[k + 1];
+      if (!(sigma > 1e-290)) {
+        beta = alpha; tau = 0.0; scale = 0.0;
+      } else {
+        beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+#pragma unroll
+      for (int m = 0; m < NE; ++m) {
+        const int i = tid + AT * m;
+        v[m] = (i == k + 1) ? 1.0 : ((i > k + 1 && i < n) ? x[m] * scale : 0.0);
+        if (c == (k % TC) && i < np) out.V[(size_t)k * np + i] = v[m];
+      }
+      if (c == (k % TC) && tid == 0) { out.e[k] = beta; out.tau[k] = tau; }
+    }
+    AM_TICK(tA);
+    // slot 0 is used by steps 0, 2, ..; slot 1 by the prologue and steps 1, 3, ..
+    if (warp < AW) mbar_wait_cluster(mbar0 + 8u * cur, (uint32_t)((cur ? ((k + 1) >> 1) : (k >> 1)) & 1));
+    AM_TICK(tS);
+    // ---- C. w_k and the next column (algebra warps; the other warps wait at the barriers)
+    const double2 *ib = inbox + cur * np;
+    const double ts = tau * scale;
+    double pv[NE], av[NE];
+    double *r = red + (rslot & 3) * TW;
+    ++rslot;
+    if (warp < AW) {
+      double part = 0.0;
+#pragma unroll
+      for (int m = 0; m < NE; ++m) {
+        const int i = tid + AT * m;
+        const bool in = (i >= k + 1 && i < n);
+        const double2 g = in ? ib[i] : make_double2(0.0, 0.0);
+        pv[m] = in ? ts * fma(-beta, g.y, g.x) : 0.0;
+        av[m] = g.y;
+        part = fma(pv[m], v[m], part);
+      }
+      part = warp_sum(part);
+      if (lane == 0) r[warp] = part;
+    }
+    __syncthreads();
+    if (warp < AW) {
+      double gam = 0.0;
+#pragma unroll
+      for (int w = 0; w < AW; ++w) gam += r[w];
+      const double Kc = 0.5 * tau * gam;
+      const double2 gk = ib[k + 1];
+      const double wk1 = ts * fma(-beta, gk.y, gk.x) - Kc;  // w_k[k+1]  (v_k[k+1] = 1)
+      double *xn = xs + prv * np;
+      double sp = 0.0;
+#pragma unroll
+      for (int m = 0; m < NE; ++m) {
+        const int i = tid + AT * m;
+        const bool in = (i >= k + 1 && i < n);
+        const double w = in ? fma(-Kc, v[m], pv[m]) : 0.0;
+        if (i < np) { vcur[i] = v[m]; wcur[i] = w; }
+        x[m] = (i >= k + 2 && i < n) ? av[m] - v[m] * wk1 - w : 0.0;
+        if (i < np) xn[i] = x[m];
+        if (i >= k + 3) sp = fma(x[m], x[m], sp);
+      }
+      sp = warp_sum(sp);
+      if (lane == 0) sigp[prv * AW + warp] = sp;
+    }
+    __syncthreads();
+    AM_TICK(tC);
+  }
+  if (PROBE && out.dbg && c == 0 && tid == 0) { out.dbg[0] = tA; out.dbg[1] = tB; out.dbg[2] = tS; out.dbg[3] = tC; out.dbg[4] = tB1; out.dbg[5] = tB2; }
+
+  // epilogue: pending update (n-3) on rows/cols >= n-2 (in registers), back to shared memory, then d and the last e
+  {
+    const int k = n - 2, kb = k >> 5;
+    const double *vprev = vb + ((k + 1) & 1) * np, *wprev = wb + ((k + 1) & 1) * np;
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+      const int lr = warp + RW * r;
+      const int i = c + TC * lr;
+      if (lr < RL && i < n) {
+        const bool upd = i >= k;
+        const double vi = upd ? vprev[i] : 0.0, wi = upd ? wprev[i] : 0.0;
+#pragma unroll
+        for (int jj = 0; jj < NB; ++jj) {
+          const int j = 32 * jj + lane;
+          if (j < np) {
+            double a = am[r][jj];
+            if (upd && jj >= kb) {
+              a = fma(-vi, wprev[j], a);
+              a = fma(-wi, vprev[j], a);
+            }
+            rows[(size_t)lr * np + j] = a;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int lr = tid; lr < RL; lr += RT) {
+      const int i = c + TC * lr;
+      if (i < n) {
+        out.d[i] = rows[(size_t)lr * np + i];
+        if (i == n - 1) { out.e[n - 2] = rows[(size_t)lr * np + (n - 2)]; out.e[n - 1] = 0.0; out.tau[n - 2] = 0.0; out.tau[n - 1] = 0.0; }
+      }
+    }
+  }
+  cluster.sync();  // no CTA exits while a peer may still address its shared memory
+}
+
 // ------------------------------------------------------------------ 2. bisection
 constexpr int BT = 256;  // shifts per round (8 bits of the bracket per round; the Sturm recurrence is bound by
                          // fp64 throughput at 512 shifts and by the dependent FMA chain at 256)
@@ -882,7 +1168,7 @@ int64_t carve_top(void *base, int n, int P, TopWork *w) {
   t.e = take((int64_t)np * 8);
   t.lam = take((int64_t)PMAX * 8);
   t.Y = take((int64_t)P * np * 8);
-  t.dbg = take(64);
+  t.dbg = take(256);
   t.orth = take(((int64_t)2 * P * P + 8) * 8);
   if (w) *w = t;
   return off;
@@ -912,11 +1198,15 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
   {
     const size_t smem = ((size_t)RL * np + 10 * (size_t)np + 6 * TW) * sizeof(double);
     if (smem > 227 * 1024) return am::fail(AM_EINVAL, "am_eigh_topk: matrix does not fit the cluster's shared memory");
-    AM_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AM_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    const char *tv = getenv("AM_TRIDIAG_SMEM");
+    const bool reg = np <= 32 * NB && RL <= RR * RW && !(tv && tv[0] == '1');
+    const bool probe = getenv("AM_TRIDIAG_PROBE") != nullptr;
+    auto kern = reg ? (probe ? tridiag_reg_kernel<true> : tridiag_reg_kernel<false>) : tridiag_cluster_kernel;
+    AM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(TC);
-    cfg.blockDim = dim3(TT);
+    cfg.blockDim = dim3(reg ? RT : TT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -926,7 +1216,7 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AM_CUDA(cudaLaunchKernelEx(&cfg, tridiag_cluster_kernel, d_A, n, np, RL, out));
+    AM_CUDA(cudaLaunchKernelEx(&cfg, kern, d_A, n, np, RL, out));
     AM_LAUNCHED("tridiag_cluster_kernel");
   }
   // 2. bisection
