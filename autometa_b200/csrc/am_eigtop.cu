@@ -331,6 +331,9 @@ constexpr int RW = RT / 32;   // warps
 constexpr int RR = 4;         // local rows per warp (RL <= 32)
 constexpr int NB = 16;        // 32-column blocks per row (np <= 512)
 constexpr int JG = 4;         // column blocks per branch in the update pass
+constexpr int RAW = RW;       // all 8 warps run the replicated reflector algebra: 2 vector entries per thread
+constexpr int RAT = RAW * 32;
+constexpr int RNE = (32 * NB + RAT - 1) / RAT;
 
 // PROBE = true: per-phase cycle counters (scripts/dev_eig_once.py, AM_TRIDIAG_PROBE=1); off in production
 template <bool PROBE>
@@ -378,14 +381,14 @@ tridiag_reg_kernel(const double *__restrict__ A, int n, int np, int RL, TriOut o
                      mapa_u32(mbar0 + 8u, lane));
   }
   mbar_wait_cluster(mbar0 + 8u, 0u);
-  double x[NE];
+  double x[RNE];
 #pragma unroll
-  for (int m = 0; m < NE; ++m) x[m] = 0.0;
-  if (warp < AW) {
+  for (int m = 0; m < RNE; ++m) x[m] = 0.0;
+  if (warp < RAW) {
     double sp = 0.0;
 #pragma unroll
-    for (int m = 0; m < NE; ++m) {
-      const int i = tid + AT * m;
+    for (int m = 0; m < RNE; ++m) {
+      const int i = tid + RAT * m;
       if (i >= 1 && i < n) x[m] = inbox[np + i].y;
       if (i < np) xs[i] = x[m];
       if (i >= 2) sp = fma(x[m], x[m], sp);
@@ -498,11 +501,11 @@ long long tprev = 0;
     AM_TICK(tB);
     // ---- S. reflector scalars while the inbox fills (algebra warps only)
     double beta = 0.0, tau = 0.0, scale = 0.0;
-    double v[NE];
-    if (warp < AW) {
+    double v[RNE];
+    if (warp < RAW) {
       double sigma = 0.0;
 #pragma unroll
-      for (int w = 0; w < AW; ++w) sigma += sigp[cur * AW + w];
+      for (int w = 0; w < RAW; ++w) sigma += sigp[cur * RAW + w];
       const double alpha = xk[k + 1];
       if (!(sigma > 1e-290)) {
         beta = alpha; tau = 0.0; scale = 0.0;
@@ -512,8 +515,8 @@ long long tprev = 0;
         scale = 1.0 / (alpha - beta);
       }
 #pragma unroll
-      for (int m = 0; m < NE; ++m) {
-        const int i = tid + AT * m;
+      for (int m = 0; m < RNE; ++m) {
+        const int i = tid + RAT * m;
         v[m] = (i == k + 1) ? 1.0 : ((i > k + 1 && i < n) ? x[m] * scale : 0.0);
         if (c == (k % TC) && i < np) out.V[(size_t)k * np + i] = v[m];
       }
@@ -521,19 +524,19 @@ long long tprev = 0;
     }
     AM_TICK(tA);
     // slot 0 is used by steps 0, 2, ..; slot 1 by the prologue and steps 1, 3, ..
-    if (warp < AW) mbar_wait_cluster(mbar0 + 8u * cur, (uint32_t)((cur ? ((k + 1) >> 1) : (k >> 1)) & 1));
+    if (warp < RAW) mbar_wait_cluster(mbar0 + 8u * cur, (uint32_t)((cur ? ((k + 1) >> 1) : (k >> 1)) & 1));
     AM_TICK(tS);
     // ---- C. w_k and the next column (algebra warps; the other warps wait at the barriers)
     const double2 *ib = inbox + cur * np;
     const double ts = tau * scale;
-    double pv[NE], av[NE];
+    double pv[RNE], av[RNE];
     double *r = red + (rslot & 3) * TW;
     ++rslot;
-    if (warp < AW) {
+    if (warp < RAW) {
       double part = 0.0;
 #pragma unroll
-      for (int m = 0; m < NE; ++m) {
-        const int i = tid + AT * m;
+      for (int m = 0; m < RNE; ++m) {
+        const int i = tid + RAT * m;
         const bool in = (i >= k + 1 && i < n);
         const double2 g = in ? ib[i] : make_double2(0.0, 0.0);
         pv[m] = in ? ts * fma(-beta, g.y, g.x) : 0.0;
@@ -544,18 +547,18 @@ long long tprev = 0;
       if (lane == 0) r[warp] = part;
     }
     __syncthreads();
-    if (warp < AW) {
+    if (warp < RAW) {
       double gam = 0.0;
 #pragma unroll
-      for (int w = 0; w < AW; ++w) gam += r[w];
+      for (int w = 0; w < RAW; ++w) gam += r[w];
       const double Kc = 0.5 * tau * gam;
       const double2 gk = ib[k + 1];
       const double wk1 = ts * fma(-beta, gk.y, gk.x) - Kc;  // w_k[k+1]  (v_k[k+1] = 1)
       double *xn = xs + prv * np;
       double sp = 0.0;
 #pragma unroll
-      for (int m = 0; m < NE; ++m) {
-        const int i = tid + AT * m;
+      for (int m = 0; m < RNE; ++m) {
+        const int i = tid + RAT * m;
         const bool in = (i >= k + 1 && i < n);
         const double w = in ? fma(-Kc, v[m], pv[m]) : 0.0;
         if (i < np) { vcur[i] = v[m]; wcur[i] = w; }
@@ -564,7 +567,7 @@ long long tprev = 0;
         if (i >= k + 3) sp = fma(x[m], x[m], sp);
       }
       sp = warp_sum(sp);
-      if (lane == 0) sigp[prv * AW + warp] = sp;
+      if (lane == 0) sigp[prv * RAW + warp] = sp;
     }
     __syncthreads();
     AM_TICK(tC);
