@@ -1149,10 +1149,199 @@ backtransform_kernel(const double *__restrict__ V, const double *__restrict__ ta
   if (tid == 0) evals[j] = lam[j];
 }
 
+// ------------------------------------------------------------------ 5b. blocked back-transformation
+// z = H_0 H_1 ... H_{n-3} y with the reflectors grouped WB at a time in compact WY form (LAPACK dlarft,
+// forward / columnwise):  H_{k0} ... H_{k0+m-1} = I - V T V^T,  T upper triangular,
+//   T[j][j] = tau_j,  T[0:j, j] = -tau_j T[0:j, 0:j] (V[:, 0:j]^T v_j).
+// Applying a block costs 4 barriers instead of one per pair of reflectors (255 -> 128 barriers with a
+// quarter of the dependent reductions per barrier); the T factors are shared by all P eigenvectors.
+constexpr int WB = 16;    // reflectors per block
+constexpr int WT = 256;   // threads
+constexpr int WZ = (SMEM_N_MAX + WT - 1) / WT;  // vector entries per thread
+
+__global__ void __launch_bounds__(WT)
+wy_factor_kernel(const double *__restrict__ V, const double *__restrict__ tau, int n, int np,
+                 double *__restrict__ Tf) {
+  extern __shared__ double sm[];
+  const int pitch = np + 1;  // rows of the tile start in different banks
+  double *Vt = sm;                 // WB x pitch
+  double *G = Vt + WB * pitch;     // WB x (WB + 1)
+  double *T = G + WB * (WB + 1);   // WB x (WB + 1)
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int k0 = blockIdx.x * WB;
+  const int m = min(WB, (n - 2) - k0);  // reflectors k0 .. k0+m-1 (k <= n-3)
+  for (int q = tid; q < WB * np; q += WT) {
+    const int r = q / np, i = q - r * np;
+    Vt[r * pitch + i] = (r < m) ? __ldg(V + (size_t)(k0 + r) * np + i) : 0.0;
+  }
+  for (int q = tid; q < WB * (WB + 1); q += WT) T[q] = 0.0;
+  __syncthreads();
+  {
+    const int a = tid & (WB - 1), c = tid >> 4;  // WT = WB * WB pairs
+    double s = 0.0;
+    if (a <= c)
+      for (int i = k0; i < np; ++i) s = fma(Vt[a * pitch + i], Vt[c * pitch + i], s);  // v_k is zero up to k
+    G[a * (WB + 1) + c] = s;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int a = lane;
+    if (a < m) T[a * (WB + 1) + a] = __ldg(tau + k0 + a);
+    __syncwarp();
+    for (int j = 1; j < m; ++j) {
+      const double tj = __ldg(tau + k0 + j);
+      const double tmp = (a < j) ? -tj * G[a * (WB + 1) + j] : 0.0;
+      double acc = 0.0;
+      for (int c = 0; c < j; ++c) {
+        const double tc = __shfl_sync(FULL, tmp, c);
+        if (a < j && c >= a) acc = fma(T[a * (WB + 1) + c], tc, acc);
+      }
+      if (a < j) T[a * (WB + 1) + j] = acc;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int q = tid; q < WB * WB; q += WT) Tf[(size_t)blockIdx.x * WB * WB + q] = T[(q / WB) * (WB + 1) + (q % WB)];
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(WT)
+backtransform_wy_kernel(const double *__restrict__ V, const double *__restrict__ Tf, int n, int np, int P,
+                        const double *__restrict__ Y, const double *__restrict__ lam,
+                        double *__restrict__ evals, double *__restrict__ evecs) {
+  extern __shared__ double sm[];
+  double *Vt = sm;                    // 2 x WB x np   (double-buffered reflector tiles)
+  double *Tt = Vt + 2 * WB * np;      // 2 x WB x WB   (their T factors)
+  double *zs = Tt + 2 * WB * WB;      // np
+  double *us = zs + np;               // WB
+  double *ws = us + WB;               // WB
+  __shared__ double s_best[WT / 32], s_val[WT / 32];
+  __shared__ int s_idx[WT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = blockIdx.x;
+  double z[WZ];
+#pragma unroll
+  for (int q = 0; q < WZ; ++q) {
+    const int i = tid + WT * q;
+    z[q] = (i < np) ? Y[(size_t)j * np + i] : 0.0;
+    if (i < np) zs[i] = z[q];
+  }
+  const int nblk = (n - 2 + WB - 1) / WB;
+  const int per_row = np / 2;
+  // tile b (rows k0 .. k0+WB-1 of V; rows past n-3 are zero) and T_b -> buffer b & 1, asynchronously
+  auto prefetch = [&](int b) {
+    const int k0 = b * WB;
+    const int m = min(WB, (n - 2) - k0);
+    const double2 *src = reinterpret_cast<const double2 *>(V + (size_t)k0 * np);
+    double2 *dst = reinterpret_cast<double2 *>(Vt + (size_t)(b & 1) * WB * np);
+    const int q_valid = m * per_row;  // chunks of the rows that exist
+    for (int q = tid; q < WB * per_row; q += WT) {
+      if (q < q_valid) cp_async16(dst + q, src + q);
+      else dst[q] = make_double2(0.0, 0.0);
+    }
+    if (tid < WB * WB / 2)
+      cp_async16(reinterpret_cast<double2 *>(Tt + (b & 1) * WB * WB) + tid,
+                 reinterpret_cast<const double2 *>(Tf + (size_t)b * WB * WB) + tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(nblk - 1);
+  for (int b = nblk - 1; b >= 0; --b) {
+    if (b > 0) {
+      prefetch(b - 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const double *Vb = Vt + (size_t)(b & 1) * WB * np;
+    // u = V_b^T z: warp w takes reflectors w and w + 8
+    {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      const double *v0 = Vb + warp * np, *v1 = Vb + (warp + 8) * np;
+      for (int i = lane; i < np; i += 64) {
+        const bool two = i + 32 < np;  // np is a multiple of 32, not necessarily of 64
+        const double za = zs[i], zb = two ? zs[i + 32] : 0.0;
+        s0 = fma(v0[i], za, s0);
+        s1 = fma(v1[i], za, s1);
+        s2 = fma(two ? v0[i + 32] : 0.0, zb, s2);
+        s3 = fma(two ? v1[i + 32] : 0.0, zb, s3);
+      }
+      s0 += s2;
+      s1 += s3;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(FULL, s0, o);
+        s1 += __shfl_xor_sync(FULL, s1, o);
+      }
+      if (lane == 0) { us[warp] = s0; us[warp + 8] = s1; }
+    }
+    __syncthreads();
+    // w = T_b u
+    if (tid < WB) {
+      const double *Tb = Tt + (b & 1) * WB * WB + tid * WB;
+      double a0 = 0.0, a1 = 0.0;
+      for (int c = tid; c < WB; c += 2) {
+        a0 = fma(Tb[c], us[c], a0);
+        if (c + 1 < WB) a1 = fma(Tb[c + 1], us[c + 1], a1);
+      }
+      ws[tid] = a0 + a1;
+    }
+    __syncthreads();
+    // z -= V_b w
+#pragma unroll
+    for (int q = 0; q < WZ; ++q) {
+      const int i = tid + WT * q;
+      if (i < np) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < WB; r += 2) {
+          a0 = fma(Vb[r * np + i], ws[r], a0);
+          a1 = fma(Vb[(r + 1) * np + i], ws[r + 1], a1);
+        }
+        z[q] -= a0 + a1;
+        zs[i] = z[q];
+      }
+    }
+    __syncthreads();
+  }
+  // sklearn svd_flip(u_based_decision=False): largest-|.| entry (first occurrence) made positive
+  double best = -1.0, bval = 0.0;
+  int bidx = 0;
+#pragma unroll
+  for (int q = 0; q < WZ; ++q) {
+    const int i = tid + WT * q;
+    if (i < n) {
+      const double a = fabs(z[q]);
+      if (a > best) { best = a; bidx = i; bval = z[q]; }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(FULL, best, o);
+    const int oi = __shfl_xor_sync(FULL, bidx, o);
+    const double ov = __shfl_xor_sync(FULL, bval, o);
+    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; bval = ov; }
+  }
+  if (lane == 0) { s_best[warp] = best; s_idx[warp] = bidx; s_val[warp] = bval; }
+  __syncthreads();
+  best = s_best[0]; bidx = s_idx[0]; bval = s_val[0];
+  for (int w = 1; w < WT / 32; ++w)
+    if (s_best[w] > best || (s_best[w] == best && s_idx[w] < bidx)) { best = s_best[w]; bidx = s_idx[w]; bval = s_val[w]; }
+  const double sgn = bval < 0.0 ? -1.0 : 1.0;
+#pragma unroll
+  for (int q = 0; q < WZ; ++q) {
+    const int i = tid + WT * q;
+    if (i < n) evecs[(size_t)j * n + i] = sgn * z[q];
+  }
+  if (tid == 0) evals[j] = lam[j];
+}
+
 inline int round_up32(int x) { return (x + 31) & ~31; }
 
 struct TopWork {
-  double *V, *tau, *d, *e, *lam, *Y, *dbg, *orth;
+  double *V, *tau, *d, *e, *lam, *Y, *dbg, *orth, *Tf;
 };
 
 int64_t carve_top(void *base, int n, int P, TopWork *w) {
@@ -1173,6 +1362,7 @@ int64_t carve_top(void *base, int n, int P, TopWork *w) {
   t.Y = take((int64_t)P * np * 8);
   t.dbg = take(256);
   t.orth = take(((int64_t)2 * P * P + 8) * 8);
+  t.Tf = take((int64_t)((n + WB - 1) / WB) * WB * WB * 8);
   if (w) *w = t;
   return off;
 }
@@ -1265,8 +1455,21 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
   }
   // 5. back-transformation
   {
-    backtransform_kernel<<<P, KT, 0, st>>>(w.V, w.tau, n, np, P, w.Y, w.lam, d_evals, d_evecs);
-    AM_LAUNCHED("backtransform_kernel");
+    const char *bs = getenv("AM_BACKTRANSFORM_SEQ");
+    if (n < 3 + WB || (bs && bs[0] == '1')) {
+      backtransform_kernel<<<P, KT, 0, st>>>(w.V, w.tau, n, np, P, w.Y, w.lam, d_evals, d_evecs);
+      AM_LAUNCHED("backtransform_kernel");
+    } else {
+      const int nblk = (n - 2 + WB - 1) / WB;
+      const size_t sm1 = ((size_t)WB * (np + 1) + 2 * WB * (WB + 1)) * sizeof(double);
+      const size_t sm2 = ((size_t)2 * WB * np + 2 * WB * WB + np + 64 + 2 * WB) * sizeof(double);
+      AM_CUDA(cudaFuncSetAttribute(wy_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+      AM_CUDA(cudaFuncSetAttribute(backtransform_wy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+      wy_factor_kernel<<<nblk, WT, sm1, st>>>(w.V, w.tau, n, np, w.Tf);
+      AM_LAUNCHED("wy_factor_kernel");
+      backtransform_wy_kernel<<<P, WT, sm2, st>>>(w.V, w.Tf, n, np, P, w.Y, w.lam, d_evals, d_evecs);
+      AM_LAUNCHED("backtransform_wy_kernel");
+    }
   }
   return AM_OK;
 }
