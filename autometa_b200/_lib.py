@@ -51,6 +51,7 @@ _SIGS = {
     "am_pack_code_words": (_i64, [_i64]),
     "am_pack_bitmap_words": (_i64, [_i64]),
     "am_pack_host": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _i32]),
+    "am_pack_work_words": (_i64, [_i64]),
     "am_pack_device": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "am_pack_device_gc": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "am_gc_finish": (C.c_int, [_p, _i64, _p, _p]),

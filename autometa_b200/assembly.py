@@ -218,7 +218,7 @@ def pack_device_arrays(d_seq, d_off, d_starts, n, total, lengths, starts_host, t
         codes = torch.empty(nwords, dtype=torch.int32, device=device)
         bitmap = torch.empty(nbw, dtype=torch.int32, device=device)
         rank = torch.empty(nbw, dtype=torch.int32, device=device)
-        work = torch.empty(nbw, dtype=torch.int32, device=device)
+        work = torch.empty(L.lib.am_pack_work_words(total), dtype=torch.int32, device=device)
         n_exc = torch.zeros(1, dtype=torch.int64, device=device)
         gc_at = torch.empty((max(n, 1), 2), dtype=torch.int32, device=device) if gc else None
         cap = exc_capacity if exc_capacity > 0 else max(1024, total // 64 // 16)

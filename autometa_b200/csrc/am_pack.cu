@@ -175,6 +175,11 @@ extern "C" int am_gc_finish(const uint32_t *d_gc_at, int64_t n_contigs, double *
   return AM_OK;
 }
 
+extern "C" int64_t am_pack_work_words(int64_t total_packed_bases) {
+  const int64_t n_words = am_pack_bitmap_words(total_packed_bases);
+  return n_words + am::scan_tmp_words(n_words);
+}
+
 extern "C" int am_pack_device(const uint8_t *d_seq, const int64_t *d_offsets, const int64_t *d_starts,
                               int64_t n_contigs, int64_t total_packed_bases, uint32_t *d_codes,
                               uint32_t *d_exc_bitmap, uint32_t *d_exc_rank, uint64_t *d_exc_mask,
@@ -214,9 +219,9 @@ extern "C" int am_pack_device_gc(const uint8_t *d_seq, const int64_t *d_offsets,
                                                  reinterpret_cast<uint4 *>(d_codes), d_exc_bitmap, pop, nullptr);
     AM_LAUNCHED("pack_kernel");
   }
-  // rank[w] = flagged groups before bitmap word w; rank needs n_words + 1 slots
-  am::exclusive_scan_kernel<<<1, 1024, 0, st>>>(pop, d_exc_rank, (int)(n_words - 1));
-  AM_LAUNCHED("exclusive_scan_kernel");
+  // rank[w] = flagged groups before bitmap word w (multi-CTA scan; its tile totals live behind pop in d_work)
+  const int n_scan = am::exclusive_scan(pop, d_exc_rank, (int)(n_words - 1), pop + n_words, st);
+  for (int i = 0; i < n_scan; ++i) AM_LAUNCHED("exclusive_scan");
   if (blocks) {
     pack_mask_kernel<<<blocks, 256, 0, st>>>(d_seq, d_offsets, d_starts, n_contigs, n_groups,
                                              d_exc_bitmap, d_exc_rank, n_words, d_exc_mask,

@@ -109,7 +109,8 @@ int am_pack_host(const uint8_t *h_seq, const int64_t *h_offsets, int64_t n_conti
  * 4-byte aligned and readable up to 4 bytes past the last base; d_exc_mask holds
  * exc_capacity entries; d_n_exc receives the number of flagged groups (if it
  * exceeds exc_capacity the surplus masks were dropped: call again with a larger
- * buffer).  d_work: am_pack_bitmap_words(total) uint32 of scratch. */
+ * buffer).  d_work: am_pack_work_words(total) uint32 of scratch. */
+int64_t am_pack_work_words(int64_t total_packed_bases);
 int am_pack_device(const uint8_t *d_seq, const int64_t *d_offsets,
                    const int64_t *d_starts, int64_t n_contigs,
                    int64_t total_packed_bases, uint32_t *d_codes,
