@@ -43,6 +43,10 @@ def _fit_project(packed, counts, method, n_components, row_index, col_index, gro
     zbuf = torch.zeros(2 * D + D + 2, dtype=torch.float64, device=dev)  # cs | cm | sample sums + count
     cs = zbuf[:Dout]
     fused = method in ("am_clr", "clr", "ilr") and D == 512 and col_index is None and n_out > 0
+    # fused path: Gram, column sums and row count share one buffer so that ONE all-reduce carries all three
+    gbuf = torch.zeros(Dout * Dout + D + 1, dtype=torch.float64, device=dev) if fused else None
+    if fused:
+        cs = gbuf[Dout * Dout : Dout * Dout + Dout]
     planes = e = center = None
     if fused:
         # provisional centre from a strided row sample (the exact mean needs the full pass);
@@ -76,7 +80,7 @@ def _fit_project(packed, counts, method, n_components, row_index, col_index, gro
                 bound = float(max(2.0 * np.log(D), np.log(max(longest, 1.0))) + 1.0)
                 packed._plans["log_range"] = bound
         e, sc = _dev.plane_scales(center, None, bound)
-        X, planes = _dev.normalize_planes(counts, method, row_index, center, sc, zbuf[:D])
+        X, planes = _dev.normalize_planes(counts, method, row_index, center, sc, gbuf[Dout * Dout : Dout * Dout + D])
         center = center[:Dout]
     elif method == "ilr" or Dout > 1024:
         X = _dev.normalize_counts(counts, method, row_index, col_index)
@@ -86,9 +90,13 @@ def _fit_project(packed, counts, method, n_components, row_index, col_index, gro
         cm = zbuf[Dout : 2 * Dout]  # column max|x|: fixed-point scale
         X = _dev.normalize_counts(counts, method, row_index, col_index, colsum=cs, colmaxabs=cm)
     mark("normalise")
-    n_t = torch.full((1,), float(X.shape[0]), dtype=torch.float64, device=dev)
-    if distributed:
-        _dist.allreduce_sum_([cs, n_t], group)
+    if fused:
+        n_t = gbuf[Dout * Dout + D :]
+        n_t.fill_(float(X.shape[0]))
+    else:
+        n_t = torch.full((1,), float(X.shape[0]), dtype=torch.float64, device=dev)
+        if distributed:
+            _dist.allreduce_sum_([cs, n_t], group)
     mu = None
     if not fused and X.shape[0] > 0:
         mu = cs / n_t
@@ -96,10 +104,15 @@ def _fit_project(packed, counts, method, n_components, row_index, col_index, gro
         center = mu
         e, sc = _dev.plane_scales(center, cm)
         planes = _dev.quantize_planes(X, center, sc)
-    G = _dev.gram_planes(planes, X.shape[0], Dout, e) if planes is not None else torch.zeros(
-        (Dout, Dout), dtype=torch.float64, device=dev)
-    if distributed:
-        _dist.allreduce_sum_([G], group)
+    if fused:
+        G = _dev.gram_planes(planes, X.shape[0], Dout, e, out=gbuf[: Dout * Dout].view(Dout, Dout))
+        if distributed:
+            _dist.allreduce_sum_([gbuf], group)  # G | column sums | row count
+    else:
+        G = _dev.gram_planes(planes, X.shape[0], Dout, e) if planes is not None else torch.zeros(
+            (Dout, Dout), dtype=torch.float64, device=dev)
+        if distributed:
+            _dist.allreduce_sum_([G], group)
     # mu and C = (G - n (mu - centre)(mu - centre)^T) / (n - 1) in one launch (in place on G)
     mu = _dev.cov_finish(G, cs, center if fused else None, n_t)
     C = G
