@@ -85,3 +85,27 @@ def allgather_rows(t, group=None):
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+
+
+def bind_to_gpu_numa_node(device_index: int) -> bool:
+    """Pin this process (and the pages it first-touches from now on, e.g. pinned staging buffers) to the CPU
+    cores NVML reports as local to the GPU.  With one process per GPU on a two-socket host this keeps every
+    rank's host->device copies off the inter-socket link.  Returns False when NVML or the affinity call is
+    unavailable (the run then continues unbound)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False

@@ -309,6 +309,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
+    numa_bound = False
+    if distributed:  # one process per GPU: keep each rank's pinned staging buffers on the GPU's own socket
+        numa_bound = DD.bind_to_gpu_numa_node(local_rank)
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -411,6 +414,7 @@ def main():
         e2e = {"value": job_bp / (e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e_ms,
                "serial_latency_ms": lat_ms, "steps": e_steps,
                "h2d_bytes_per_step": int(hf.h2d_bytes), "d2h_bytes_per_step": int(hf.d2h_bytes),
+               "numa_bound": numa_bound,
                "path": "pinned host ASCII -> H2D -> am_pack_device -> count -> am_clr -> PCA -> D2H scores; "
                        "back-to-back steps, the H2D copy of step i+1 overlaps the compute of step i "
                        "(PCIe-bound: 1 byte per bp)"}
