@@ -523,9 +523,11 @@ long long tprev = 0;
       if (c == (k % TC) && tid == 0) { out.e[k] = beta; out.tau[k] = tau; }
     }
     AM_TICK(tA);
+    if (PROBE && out.dbg && c == 0 && tid == 0 && (k & 63) == 0 && (k >> 6) < 8) out.dbg[24 + (k >> 6)] = t1 - tprev;
     // slot 0 is used by steps 0, 2, ..; slot 1 by the prologue and steps 1, 3, ..
     if (warp < RAW) mbar_wait_cluster(mbar0 + 8u * cur, (uint32_t)((cur ? ((k + 1) >> 1) : (k >> 1)) & 1));
     AM_TICK(tS);
+    if (PROBE && out.dbg && c == 0 && tid == 0 && (k & 63) == 0 && (k >> 6) < 8) out.dbg[16 + (k >> 6)] = t1 - tprev;
     // ---- C. w_k and the next column (algebra warps; the other warps wait at the barriers)
     const double2 *ib = inbox + cur * np;
     const double ts = tau * scale;

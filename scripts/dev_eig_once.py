@@ -20,11 +20,13 @@ al = lambda b: (b + 255) & ~255
 npad = (n + 31) & ~31
 off = al(n * npad * 8) + 3 * al(npad * 8) + al(128 * 8) + al(P * npad * 8)
 w = D._work_cache[("eigtop", 0, 0)]
-dbg = w[off:off + 160].view(torch.int64).cpu().numpy()
+dbg = w[off:off + 256].view(torch.int64).cpu().numpy()
 tot = dbg[:4].sum() + dbg[4] + dbg[5]
 names = ["S scalars", "B update+matvec+send", "wait inbox", "C w/next column"]
 for nm, v in zip(names, dbg[:4]):
     print("%-24s %9d clk  %5.1f %%  %6.0f clk/step" % (nm, v, 100.0 * v / tot, v / (n - 2)))
 print("  of B: compute %d clk/step, reduce %d clk/step, send = rest" % (dbg[4] / (n - 2), dbg[5] / (n - 2)))
 print("B compute at k = 0, 64, ..., 448:", dbg[8:16].tolist())
+print("S scalars  at k = 0, 64, ...:", dbg[24:32].tolist())
+print("inbox wait at k = 0, 64, ...:", dbg[16:24].tolist())
 print("total %d clk = %.3f ms at 1.965 GHz" % (tot, tot / 1.965e6))
