@@ -336,9 +336,12 @@ constexpr int RAT = RAW * 32;
 constexpr int RNE = (32 * NB + RAT - 1) / RAT;
 
 // PROBE = true: per-phase cycle counters (scripts/dev_eig_once.py, AM_TRIDIAG_PROBE=1); off in production
-template <bool PROBE>
+// EXACT = true: n = np = 512 (the k = 5 table) are compile-time constants, which removes the bounds tests
+// (a seventh of the loop body's instructions) from the 510-step loop.
+template <bool PROBE, bool EXACT>
 __global__ void __cluster_dims__(TC, 1, 1) __launch_bounds__(RT, 1)
-tridiag_reg_kernel(const double *__restrict__ A, int n, int np, int RL, TriOut out) {
+tridiag_reg_kernel(const double *__restrict__ A, int n_, int np_, int RL_, TriOut out) {
+  const int n = EXACT ? 32 * NB : n_, np = EXACT ? 32 * NB : np_, RL = EXACT ? RR * RW : RL_;
   cg::cluster_group cluster = cg::this_cluster();
   const int c = (int)cluster.block_rank();
   extern __shared__ double sm[];
@@ -1396,7 +1399,10 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
     const char *tv = getenv("AM_TRIDIAG_SMEM");
     const bool reg = np <= 32 * NB && RL <= RR * RW && !(tv && tv[0] == '1');
     const bool probe = getenv("AM_TRIDIAG_PROBE") != nullptr;
-    auto kern = reg ? (probe ? tridiag_reg_kernel<true> : tridiag_reg_kernel<false>) : tridiag_cluster_kernel;
+    const bool exact = n == 32 * NB;
+    auto kern = !reg ? tridiag_cluster_kernel
+                     : probe ? (exact ? tridiag_reg_kernel<true, true> : tridiag_reg_kernel<true, false>)
+                             : (exact ? tridiag_reg_kernel<false, true> : tridiag_reg_kernel<false, false>);
     AM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
