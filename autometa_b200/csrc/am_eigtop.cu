@@ -42,6 +42,31 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// 1/q and 1/sqrt(q) to full double precision from the hardware approximations + Newton steps (q finite,
+// positive for rsqrt, normal): a third of the latency of the IEEE sqrt / division sequences, which sit on
+// the critical path of every Householder step
+__device__ __forceinline__ double fast_rcp(double q) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(q));
+  double e = fma(-q, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-q, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double q) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(q));
+  // r <- r + r (1 - q r^2) / 2, three times (the approximation carries ~20 bits)
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const double h = 0.5 * r;
+    const double e = fma(-q * r, r, 1.0);
+    r = fma(h, e, r);
+  }
+  return r;
+}
+
 // all threads get the same, order-deterministic total; `red` holds >= 32 doubles
 template <int NW>
 __device__ __forceinline__ double block_sum(double v, double *red) {
@@ -513,9 +538,15 @@ long long tprev = 0;
       if (!(sigma > 1e-290)) {
         beta = alpha; tau = 0.0; scale = 0.0;
       } else {
-        beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
-        tau = (beta - alpha) / beta;
-        scale = 1.0 / (alpha - beta);
+        // |x| = q / sqrt(q) with one correction; tau = (beta - alpha) / beta = 1 + |alpha| / |x|;
+        // 1 / (alpha - beta) = sign(alpha) / (|alpha| + |x|)
+        const double q = fma(alpha, alpha, sigma);
+        const double rs = fast_rsqrt(q);
+        double nrm = q * rs;
+        nrm = fma(0.5 * rs, fma(-nrm, nrm, q), nrm);
+        beta = -copysign(nrm, alpha);
+        tau = fma(fabs(alpha), rs, 1.0);
+        scale = copysign(fast_rcp(fabs(alpha) + nrm), alpha);
       }
 #pragma unroll
       for (int m = 0; m < RNE; ++m) {
@@ -726,16 +757,6 @@ bisect_kernel(const double *__restrict__ dg, const double *__restrict__ eg, int 
   if (tid == 0) lam[jtop] = 0.5 * (lo + hi) * sup;
 }
 
-// 1/q to full double precision without the IEEE-division slow path (q is finite, non-zero, normal)
-__device__ __forceinline__ double fast_rcp(double q) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(q));
-  double e = fma(-q, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-q, r, 1.0);
-  r = fma(r, e, r);
-  return r;
-}
 
 // ------------------------------------------------------------------ 3. inverse iteration
 __global__ void __launch_bounds__(32)
