@@ -147,6 +147,20 @@ project_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PJ_M >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
+      // per-op descriptor offsets, instruction descriptors and TMEM columns once, in registers: the index
+      // arithmetic of 12 MMAs per stage in ONE issuing thread was the longest part of the pipeline
+      constexpr int MAXOPS = 8;
+      uint32_t a_off[MAXOPS], b_off[MAXOPS], idn[MAXOPS], tdc[MAXOPS];
+#pragma unroll
+      for (int i = 0; i < MAXOPS; ++i) {
+        const bool on = i < p.n_ops;
+        a_off[i] = on ? ((uint32_t)p.os[i] * PJ_A_BYTES) >> 4 : 0u;
+        b_off[i] = on ? ((uint32_t)p.ot[i] * PJ_B_BYTES) >> 4 : 0u;
+        idn[i] = idesc0 | ((uint32_t)((PJ_N * (on ? p.on[i] : 1)) >> 3) << 17);
+        tdc[i] = tmem + (uint32_t)(on ? p.od[i] : 0) * PJ_N;
+      }
+      // K-major, 64B swizzle: rows of 64 B, 8-row groups 512 B apart; the second K step starts 32 B into the row
+      const uint64_t dA0 = make_desc(base, 0, 512, 4), dB0 = make_desc(base + PJ_NP * PJ_A_BYTES, 0, 512, 4);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         mbar_wait(bar_acce, acc_phase ^ 1u);
         tc_fence_after();
@@ -156,25 +170,33 @@ project_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)stage * stage_bytes;
           const uint32_t sb = sa + PJ_NP * PJ_A_BYTES;
+          const uint64_t so = (uint64_t)(((uint32_t)stage * stage_bytes) >> 4);
+#pragma unroll
           for (int kk = 0; kk < PJ_BK / 32; ++kk) {
-            for (int i = 0; i < p.n_ops; ++i) {
-              // K-major, 64B swizzle: rows of 64 B, 8-row groups 512 B apart; the second K step
-              // starts 32 B into the row
-              const uint64_t da = make_desc(sa + (uint32_t)p.os[i] * PJ_A_BYTES + 32u * kk, 0, 512, 4);
-              const uint32_t td = tmem + (uint32_t)p.od[i] * PJ_N;
-              if (first && p.ofirst[i]) {
-                for (int j = 0; j < p.on[i]; ++j) {
-                  const uint64_t dbj = make_desc(sb + (uint32_t)(p.ot[i] + j) * PJ_B_BYTES + 32u * kk, 0, 512, 4);
-                  umma_i8(td + (uint32_t)j * PJ_N, da, dbj, idesc0 | ((uint32_t)(PJ_N >> 3) << 17),
-                          ((p.ofirst[i] >> j) & 1) ? 0u : 1u);
+            if (first) {
+              // first K step of a tile: the planes of an op are issued one by one with their own accumulate flag
+              for (int i = 0; i < p.n_ops; ++i) {
+                const uint64_t da = make_desc(sa + (uint32_t)p.os[i] * PJ_A_BYTES + 32u * kk, 0, 512, 4);
+                const uint32_t td = tmem + (uint32_t)p.od[i] * PJ_N;
+                if (p.ofirst[i]) {
+                  for (int j = 0; j < p.on[i]; ++j) {
+                    const uint64_t dbj = make_desc(sb + (uint32_t)(p.ot[i] + j) * PJ_B_BYTES + 32u * kk, 0, 512, 4);
+                    umma_i8(td + (uint32_t)j * PJ_N, da, dbj, idesc0 | ((uint32_t)(PJ_N >> 3) << 17),
+                            ((p.ofirst[i] >> j) & 1) ? 0u : 1u);
+                  }
+                } else {
+                  const uint64_t db = make_desc(sb + (uint32_t)p.ot[i] * PJ_B_BYTES + 32u * kk, 0, 512, 4);
+                  umma_i8(td, da, db, idesc0 | ((uint32_t)((PJ_N * p.on[i]) >> 3) << 17), 1u);
                 }
-              } else {
-                // planes t .. t+on-1 are adjacent 64-row blocks: one N = 64 on operand
-                const uint64_t db = make_desc(sb + (uint32_t)p.ot[i] * PJ_B_BYTES + 32u * kk, 0, 512, 4);
-                umma_i8(td, da, db, idesc0 | ((uint32_t)((PJ_N * p.on[i]) >> 3) << 17), 1u);
               }
+              first = false;
+            } else {
+              const uint64_t oa = so + (uint64_t)(2 * kk), ob = so + (uint64_t)(2 * kk);
+#pragma unroll
+              for (int i = 0; i < MAXOPS; ++i)
+                if (i < p.n_ops)  // planes t .. t+on-1 are adjacent 64-row blocks: one N = 64 on operand
+                  umma_i8(tdc[i], dA0 + oa + a_off[i], dB0 + ob + b_off[i], idn[i], 1u);
             }
-            first = false;
           }
           umma_commit(bar_empty + 8u * stage);
           if (++stage == PJ_STAGES) { stage = 0; phase ^= 1u; }
