@@ -618,3 +618,38 @@ def test_featurise_full_size_properties(torch_cuda, case):
     CV = (Xc.T @ (Xc @ res["components"].T)) / (n - 1)
     resid = (CV - res["components"].T * res["explained_variance"]).abs().max()
     assert float(resid) <= 1e-9 * float(ev[0])
+
+
+# ----------------------------------------------------------------------------- embed() through its own call site
+def test_embed_pca_stage_matches_reference_embed_call(torch_cuda, golden_pca, tmp_path, monkeypatch):
+    """The reference's embed() was run (tests/golden/make_golden.py) with a stub ``tsne.bh_sne`` that returns
+    the first d columns it is handed, i.e. the PCA scores.  The same stub here: embed() must return the
+    reference's frame (PCA stage on the GPU), write/read it back unchanged and keep the error behaviour."""
+    import sys
+    import types
+
+    from autometa_b200.common import kmers
+    from autometa_b200.common.exceptions import TableFormatError
+
+    stub = types.ModuleType("tsne")
+    stub.bh_sne = lambda data, d, **kw: np.ascontiguousarray(data[:, :d])
+    monkeypatch.setitem(sys.modules, "tsne", stub)
+    X = golden_pca["X"]
+    df = pd.DataFrame(X, index=pd.Index([f"c{i}" for i in range(X.shape[0])], name="contig"))
+    out = tmp_path / "kmers.embedded.tsv"
+    emb = kmers.embed(df, out=str(out), method="bhsne", embed_dimensions=3, pca_dimensions=10, seed=42)
+    assert list(emb.columns) == ["x_1", "x_2", "x_3"] and emb.index.equals(df.index)
+    ref = golden_pca["embed_first3"]
+    assert np.max(np.abs(emb.to_numpy() - ref)) <= 1e-8 * np.max(np.abs(ref))
+    # cached file is returned as is; the TSV round trip is pandas-identical
+    again = kmers.embed(df, out=str(out), method="bhsne", embed_dimensions=3, pca_dimensions=10)
+    pd.testing.assert_frame_equal(again, pd.read_csv(out, sep="\t", index_col="contig"), check_exact=True)
+    # pca_dimensions = 0 or >= the number of columns: no PCA, the manifold step sees the input
+    raw = kmers.embed(df, method="bhsne", embed_dimensions=2, pca_dimensions=0)
+    assert np.array_equal(raw.to_numpy(), X[:, :2])
+    # sklearn's TSNE is installed: the sksne branch runs end to end on the GPU scores
+    small = kmers.embed(df.iloc[:120], method="sksne", embed_dimensions=2, pca_dimensions=10, seed=1)
+    assert small.shape == (120, 2) and np.isfinite(small.to_numpy()).all()
+    (tmp_path / "bad.tsv").write_text("id\tx\nq\t1.0\n")
+    with pytest.raises(TableFormatError):
+        kmers.embed(str(tmp_path / "bad.tsv"), method="bhsne")
