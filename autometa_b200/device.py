@@ -444,7 +444,8 @@ class ClusterMetrics:
         self.M = int(n_ref_markers)
         self.cutoffs = tuple(float(c) for c in cutoffs)
         with torch.cuda.device(device):
-            t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device)
+            # np.array(..., copy=True): pandas hands out read-only views, which torch.from_numpy warns about
+            t = lambda a, dt: torch.from_numpy(np.array(a, dtype=dt, order="C", copy=True)).to(device)
             self.nnz = int(len(marker_rows))
             self.rows = t(marker_rows if self.nnz else np.zeros(1), np.int32)
             self.cols = t(marker_cols if self.nnz else np.zeros(1), np.int32)
