@@ -371,3 +371,14 @@ def test_tsv_reader_equals_pandas_bit_for_bit(tmp_path):
     (tmp_path / "w.tsv").write_text("id\tx\nq\t1.0\n")
     with pytest.raises(ValueError):
         tsv.read_table(str(tmp_path / "w.tsv"))
+
+
+def test_numa_binding_helper_is_safe_without_a_gpu():
+    from autometa_b200 import dist as D
+
+    before = os.sched_getaffinity(0)
+    ok = D.bind_to_gpu_numa_node(0)  # no NVML device here: must report False and leave the affinity alone
+    assert ok in (False, True)
+    if not ok:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
