@@ -16,31 +16,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib as L
-
-
-@dataclass
-class HostAssembly:
-    """Contig ids + ASCII sequence bytes (concatenated) + offsets, on the host."""
-
-    ids: List[str]
-    seq: np.ndarray  # uint8, all contigs concatenated (may carry slack at the end)
-    offsets: np.ndarray  # int64 [N+1]
-
-    @property
-    def n_contigs(self) -> int:
-        return len(self.offsets) - 1
-
-    @property
-    def lengths(self) -> np.ndarray:
-        return np.diff(self.offsets)
-
-    @property
-    def total_bp(self) -> int:
-        return int(self.offsets[-1] - self.offsets[0])
-
-    def slice(self, lo: int, hi: int) -> "HostAssembly":
-        """Contigs [lo, hi) as a view (offsets stay absolute into ``seq``)."""
-        return HostAssembly(self.ids[lo:hi], self.seq, self.offsets[lo : hi + 1])
+from .hostdata import HostAssembly  # noqa: F401  (re-exported; lives in a module that needs no .so)
 
 
 @dataclass

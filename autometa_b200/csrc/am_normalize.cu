@@ -260,8 +260,8 @@ normalize512_planes_kernel(const int32_t *__restrict__ counts, int64_t n_out,
     const int col = 128 * (i >> 2) + 4 * l + (i & 3);
     // ilr has D - 1 output columns; the pad column is written as exact zeros
     const bool pad = METHOD == 2 && col == D - 1;
-    cen[q] = pad ? 0.0 : center[col];
-    scl[q] = pad ? 0.0 : sc[col];
+    cen[q] = (pad || !planes) ? 0.0 : center[col];
+    scl[q] = (pad || !planes) ? 0.0 : sc[col];
     if (METHOD == 2) {
       coef[q] = col ? sqrt((double)col / (double)(col + 1)) : 0.0;
       rcp[q] = col ? 1.0 / (double)col : 0.0;
@@ -351,29 +351,41 @@ normalize512_planes_kernel(const int32_t *__restrict__ counts, int64_t n_out,
         }
       }
     }
-    double2 *o2p = reinterpret_cast<double2 *>(out + r * D) + 2 * lane;
-    uint32_t *pl = reinterpret_cast<uint32_t *>(planes + (size_t)r * D) + lane;
-    const size_t plane_words = (size_t)n_out * (D / 4);
+    // either output may be absent (block-uniform): the planes feed the Gram on the critical path, the
+    // fp64 rows (the frame `normalize` returns) can be written by a second launch that overlaps the
+    // eigensolve — both launches run this same code, so the values are bit-identical
+    if (out) {
+      double2 *o2p = reinterpret_cast<double2 *>(out + r * D) + 2 * lane;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      __stcs(o2p + 64 * m, make_double2(l[4 * m], l[4 * m + 1]));
-      __stcs(o2p + 64 * m + 1, make_double2(l[4 * m + 2], l[4 * m + 3]));
-      uint32_t word[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = 4 * m + e;
-        csum[i] += l[i];
-        double v = (l[i] - cen[i * 32 + lane]) * scl[i * 32 + lane];
-        v = fmin(fmax(v, -lim), lim);
-        int a[6];
-        digits6(v, a);
-#pragma unroll
-        for (int s = 0; s < 6; ++s) word[s] |= (uint32_t)(a[s] & 255) << (8 * e);
+      for (int m = 0; m < 4; ++m) {
+        __stcs(o2p + 64 * m, make_double2(l[4 * m], l[4 * m + 1]));
+        __stcs(o2p + 64 * m + 1, make_double2(l[4 * m + 2], l[4 * m + 3]));
       }
+    }
 #pragma unroll
-      for (int s = 0; s < 6; ++s) __stcs(pl + (size_t)s * plane_words + 32 * m, word[s]);
+    for (int i = 0; i < 16; ++i) csum[i] += l[i];
+    if (planes) {
+      uint32_t *pl = reinterpret_cast<uint32_t *>(planes + (size_t)r * D) + lane;
+      const size_t plane_words = (size_t)n_out * (D / 4);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        uint32_t word[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 4 * m + e;
+          double v = (l[i] - cen[i * 32 + lane]) * scl[i * 32 + lane];
+          v = fmin(fmax(v, -lim), lim);
+          int a[6];
+          digits6(v, a);
+#pragma unroll
+          for (int s = 0; s < 6; ++s) word[s] |= (uint32_t)(a[s] & 255) << (8 * e);
+        }
+#pragma unroll
+        for (int s = 0; s < 6; ++s) __stcs(pl + (size_t)s * plane_words + 32 * m, word[s]);
+      }
     }
   }
+  if (!psum) return;
   // column sums: cross-warp reduction in a fixed order
 #pragma unroll
   for (int i = 0; i < 16; ++i) red[warp * D + 128 * (i >> 2) + 4 * lane + (i & 3)] = csum[i];
@@ -570,11 +582,12 @@ extern "C" int am_normalize_planes(const int32_t *d_counts, int64_t n_rows_out, 
   if (method != AM_NORM_AM_CLR && method != AM_NORM_CLR && method != AM_NORM_ILR)
     return am::fail(AM_EINVAL, "am_normalize_planes: unknown method");
   if (n_rows_out == 0) return AM_OK;
-  if (!d_counts || !d_out || !d_colsum || !d_center || !d_sc || !d_planes || !d_work || n_rows_out < 0)
+  if (!d_counts || n_rows_out < 0 || (!d_out && !d_planes) || (d_planes && (!d_center || !d_sc)) ||
+      (d_colsum && !d_work))
     return am::fail(AM_EINVAL, "am_normalize_planes: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = norm_grid(n_rows_out);
-  double *partials = (double *)d_work;
+  double *partials = d_colsum ? (double *)d_work : nullptr;
   const size_t smem = (size_t)(LOGT + 4 * 512 + NWARPS * 512) * sizeof(double);
   if (method == AM_NORM_AM_CLR) {
     AM_CUDA(cudaFuncSetAttribute(normalize512_planes_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -590,7 +603,9 @@ extern "C" int am_normalize_planes(const int32_t *d_counts, int64_t n_rows_out, 
                                                                    d_center, d_sc, d_planes);
   }
   AM_LAUNCHED("normalize512_planes_kernel");
-  reduce_partials_kernel<<<(512 + 31) / 32, dim3(32, 32), 0, st>>>(partials, nullptr, grid, 512, d_colsum, nullptr);
-  AM_LAUNCHED("reduce_partials_kernel");
+  if (partials) {
+    reduce_partials_kernel<<<(512 + 31) / 32, dim3(32, 32), 0, st>>>(partials, nullptr, grid, 512, d_colsum, nullptr);
+    AM_LAUNCHED("reduce_partials_kernel");
+  }
   return AM_OK;
 }

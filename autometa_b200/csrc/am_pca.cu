@@ -340,6 +340,48 @@ __global__ void count_flags_kernel(const int *__restrict__ present, int ncols, c
   }
 }
 
+// SUM-reducible form of the two am_clr tests (kmers.py:369), so that they ride in the same all-reduce as
+// the Gram: out[j] = 1.0 where column j occurs in this shard, out[ncols] = number of contigs without any
+// counted window.  Integer-valued doubles: the atomic sum is exact in any order.
+__global__ void stats_pack_kernel(const int *__restrict__ present, int ncols, const int *__restrict__ row_sum,
+                                  int64_t n, double *__restrict__ out) {
+  __shared__ int s_cnt[32];
+  int z = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    z += row_sum[i] <= 0;
+  for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = z;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    z = threadIdx.x < (blockDim.x >> 5) ? s_cnt[threadIdx.x] : 0;
+    for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    if (threadIdx.x == 0 && z) atomicAdd(out + ncols, (double)z);
+  }
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) out[c] = present[c] > 0 ? 1.0 : 0.0;
+}
+
+// G += n [ (mu - c_new)(mu - c_new)^T - (mu - c_old)(mu - c_old)^T ],  mu = colsum / n:
+// sum_r (x_r - a)(x_r - a)^T = sum_r (x_r - mu)(x_r - mu)^T + n (mu - a)(mu - a)^T for any a, so this moves a
+// Gram taken about c_old to one about c_new.  The multi-GPU path uses it to turn each rank's Gram about
+// its own provisional centre into one about a centre every rank knows without communicating
+// (c_new = NULL: the origin, which is what sklearn's X^T X - n mu mu^T uses, _pca.py:604-610), so that
+// one all-reduce of [G | colsum | n] is the only exchange.
+__global__ void gram_recenter_kernel(double *__restrict__ G, int D, const double *__restrict__ colsum,
+                                     const double *__restrict__ c_old, const double *__restrict__ c_new,
+                                     const double *__restrict__ n_ptr) {
+  const double n = *n_ptr;
+  if (!(n > 0.0)) return;
+  const int64_t total = (int64_t)D * D;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(q / D), j = (int)(q % D);
+    const double mi = colsum[i] / n, mj = colsum[j] / n;
+    const double oi = mi - (c_old ? c_old[i] : 0.0), oj = mj - (c_old ? c_old[j] : 0.0);
+    const double ni = mi - (c_new ? c_new[i] : 0.0), nj = mj - (c_new ? c_new[j] : 0.0);
+    G[q] += n * (ni * nj - oi * oj);
+  }
+}
+
 extern "C" int64_t am_colstats_work_bytes(int D) { return 2 * am_colsum_work_bytes(D); }
 
 extern "C" int am_colstats(const double *d_X, int64_t n_rows, int D, double *d_colsum,
@@ -418,5 +460,28 @@ extern "C" int am_project(const double *d_X, int64_t n_rows, int D, const double
   dim3 grid((unsigned)((n_rows + PM - 1) / PM), (P + PN - 1) / PN);
   project_kernel<<<grid, 256, 0, st>>>(d_X, n_rows, D, d_mu, d_comps, P, d_scores);
   AM_LAUNCHED("project_kernel");
+  return AM_OK;
+}
+
+extern "C" int am_stats_pack(const int32_t *d_col_present, int ncols, const int32_t *d_row_sum, int64_t n_contigs,
+                             double *d_out, void *stream) {
+  if (!d_col_present || !d_out || ncols < 1 || n_contigs < 0 || (n_contigs > 0 && !d_row_sum))
+    return am::fail(AM_EINVAL, "am_stats_pack: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  AM_CUDA(cudaMemsetAsync(d_out + ncols, 0, sizeof(double), st));
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_contigs + 255) / 256, 296));
+  stats_pack_kernel<<<grid, 256, 0, st>>>(d_col_present, ncols, d_row_sum, n_contigs, d_out);
+  AM_LAUNCHED("stats_pack_kernel");
+  return AM_OK;
+}
+
+extern "C" int am_gram_recenter(double *d_G, int D, const double *d_colsum, const double *d_c_old,
+                                const double *d_c_new, const double *d_n, void *stream) {
+  if (D < 1) return am::fail(AM_EINVAL, "am_gram_recenter: bad D");
+  if (!d_G || !d_colsum || !d_n) return am::fail(AM_EINVAL, "am_gram_recenter: null pointer");
+  const int64_t total = (int64_t)D * D;
+  gram_recenter_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 1024), 256, 0, (cudaStream_t)stream>>>(
+      d_G, D, d_colsum, d_c_old, d_c_new, d_n);
+  AM_LAUNCHED("gram_recenter_kernel");
   return AM_OK;
 }

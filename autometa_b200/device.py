@@ -215,10 +215,14 @@ def alloc_planes(n: int, D: int, dev, slices: int = GRAM_SLICES):
 
 
 def normalize_planes(counts, method: str, row_index, center, sc, colsum, out=None, planes=None,
-                     slices: int = GRAM_SLICES):
+                     slices: int = GRAM_SLICES, want_out: bool = True, want_planes: bool = True):
     """Fused kernel 2 + quantisation (D = 512): fp64 rows, column sums and the int8 digit planes of
     ``round((x - center) * sc)`` in one pass.  ``center``/``sc``/``colsum`` have 512 entries; for ilr
-    the returned matrix is the 511-column view of a pitch-512 buffer (last column zero)."""
+    the returned matrix is the 511-column view of a pitch-512 buffer (last column zero).
+
+    ``want_out=False`` writes only the planes (the Gram's operand, on the critical path),
+    ``want_planes=False`` only the fp64 rows into ``out``; the two launches compute bit-identical
+    values, so the rows can be written while the eigensolve runs (``pipeline.featurise``)."""
     import torch
 
     dev = counts.device
@@ -226,17 +230,21 @@ def normalize_planes(counts, method: str, row_index, center, sc, colsum, out=Non
     n_in, D = counts.shape
     n_out = n_in if row_index is None else int(row_index.numel())
     with torch.cuda.device(dev):
-        if out is None:
+        if out is None and want_out:
             out = torch.empty((n_out, D), dtype=torch.float64, device=dev)
-        if planes is None:
+        if planes is None and want_planes:
             planes = alloc_planes(n_out, D, dev, slices)
-        work = _work(dev, L.lib.am_normalize_work_bytes(D), "norm")
+        work = _work(dev, L.lib.am_normalize_work_bytes(D), "norm") if colsum is not None else None
         L.check(
-            L.lib.am_normalize_planes(L.t_ptr(counts), n_out, D, L.t_ptr(row_index), m, L.t_ptr(out),
-                                      L.t_ptr(colsum), L.t_ptr(center), L.t_ptr(sc), slices, L.t_ptr(planes),
-                                      L.t_ptr(work), L.stream_ptr(dev))
+            L.lib.am_normalize_planes(L.t_ptr(counts), n_out, D, L.t_ptr(row_index), m,
+                                      L.t_ptr(out) if want_out else None, L.t_ptr(colsum),
+                                      L.t_ptr(center), L.t_ptr(sc), slices,
+                                      L.t_ptr(planes) if want_planes else None, L.t_ptr(work), L.stream_ptr(dev))
         )
-    return (out[:, : D - 1] if method == "ilr" else out), planes
+    X = None
+    if want_out:
+        X = out[:, : D - 1] if method == "ilr" else out
+    return X, (planes if want_planes else None)
 
 
 def quantize_planes(X, center, sc, planes=None, slices: int = GRAM_SLICES):
@@ -289,6 +297,29 @@ def count_flags(present, row_sum, n: int):
         L.check(L.lib.am_count_flags(L.t_ptr(present), int(present.numel()), L.t_ptr(row_sum), int(n), L.t_ptr(flags),
                                      L.stream_ptr(dev)))
     return flags
+
+
+def stats_pack(present, row_sum, n: int, out):
+    """``out[:ncols]`` = 1.0 where the column occurs, ``out[ncols]`` = number of contigs without counts
+    (the SUM-reducible form of ``count_flags``; rides in the Gram all-reduce)."""
+    import torch
+
+    dev = present.device
+    with torch.cuda.device(dev):
+        L.check(L.lib.am_stats_pack(L.t_ptr(present), int(present.numel()), L.t_ptr(row_sum), int(n), L.t_ptr(out),
+                                    L.stream_ptr(dev)))
+    return out
+
+
+def gram_recenter(G, colsum, c_old, c_new, n_t):
+    """In place: the Gram about ``c_old`` becomes the Gram about ``c_new`` (``None`` = the origin)."""
+    import torch
+
+    dev = G.device
+    with torch.cuda.device(dev):
+        L.check(L.lib.am_gram_recenter(L.t_ptr(G), int(G.shape[0]), L.t_ptr(colsum), L.t_ptr(c_old), L.t_ptr(c_new),
+                                       L.t_ptr(n_t), L.stream_ptr(dev)))
+    return G
 
 
 def eigh_desc(A, max_sweeps: int = 30, tol: float = 0.0):

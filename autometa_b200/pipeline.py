@@ -31,8 +31,58 @@ def _sample_rows(n_out: int, dev, cache: dict):
     return t
 
 
-def _fit_project(packed, counts, method, n_components, row_index, col_index, group, distributed, mark):
-    """normalise -> PCA fit -> scores for the given row/column selection (device only, no host sync)."""
+def _ctx(dev):
+    import contextlib
+
+    import torch
+
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
+
+
+class _Side:
+    """Second (low-priority) stream per device for work that is off the critical path: the fp64
+    normalised rows are an OUTPUT of the pass but not an input of the Gram / eigensolve / projection
+    (those read the digit planes), so they are written while the eigensolve — 16 SMs, latency-bound —
+    leaves the rest of the chip idle."""
+
+    _streams: Dict[int, Any] = {}
+
+    @classmethod
+    def stream(cls, dev):
+        import torch
+
+        st = cls._streams.get(dev.index)
+        if st is None:
+            st = torch.cuda.Stream(device=dev, priority=0)
+            cls._streams[dev.index] = st
+        return st
+
+
+def _bound_for(packed, method: str, D: int) -> float:
+    """Hard bound of the transform (fixed-point range of the digit planes, no pass over the data):
+    |am_clr| <= log1p(longest contig); |clr|, |ilr| <= max log q - min log q <= log(1 / min q) with
+    min q >= min(1/D^2, 1/(row sum))."""
+    key = "log1p_maxlen" if method == "am_clr" else "log_range"
+    bound = packed._plans.get(key)
+    if bound is None:
+        longest = float(packed.lengths.max()) if packed.n_contigs else 1.0
+        if method == "am_clr":
+            bound = float(np.log1p(longest))
+        else:
+            bound = float(max(2.0 * np.log(D), np.log(max(longest, 1.0))) + 1.0)
+        packed._plans[key] = bound
+    return bound
+
+
+def _fit_project(packed, counts, stats, method, n_components, row_index, col_index, group, distributed, mark,
+                 overlap=True):
+    """normalise -> PCA fit -> scores for the given row/column selection (device only, no host sync).
+
+    Every rank issues the same collectives with the same sizes whatever its shard holds (an empty
+    shard, all-NA rows): the k = 5 path has exactly ONE all-reduce, of the buffer
+    ``[Gram | column sums | row count | column-presence flags | all-NA row count]``; the generic path
+    has two (``[column sums | row count]``, then the Gram).  ``stats`` = (col_present, row_sum) on the
+    first pass, ``None`` on the re-run after rows / columns were dropped."""
     import torch
 
     dev = counts.device
@@ -40,202 +90,254 @@ def _fit_project(packed, counts, method, n_components, row_index, col_index, gro
     Dk = D if col_index is None else int(col_index.numel())
     Dout = Dk - 1 if method == "ilr" else Dk
     n_out = counts.shape[0] if row_index is None else int(row_index.numel())
-    zbuf = torch.zeros(2 * D + D + 2, dtype=torch.float64, device=dev)  # cs | cm | sample sums + count
-    cs = zbuf[:Dout]
-    fused = method in ("am_clr", "clr", "ilr") and D == 512 and col_index is None and n_out > 0
-    # fused path: Gram, column sums and row count share one buffer so that ONE all-reduce carries all three
-    gbuf = torch.zeros(Dout * Dout + D + 1, dtype=torch.float64, device=dev) if fused else None
+    fused = method in ("am_clr", "clr", "ilr") and D == 512 and col_index is None
+    GG = Dout * Dout
+    # R: G | cs[D] | n | present[D] | bad rows — one SUM all-reduce carries all of it
+    R = torch.zeros(GG + 2 * D + 2, dtype=torch.float64, device=dev)
+    G = R[:GG].view(Dout, Dout)
+    cs = R[GG : GG + Dout]
+    n_t = R[GG + D : GG + D + 1]
+    tail = R[GG + D + 1 :]
+    zbuf = torch.zeros(2 * D + 1, dtype=torch.float64, device=dev)  # column max | centre sample sums
+    planes = e = center = X = None
+    side = None
+    if stats is not None and packed.n_contigs:
+        _dev.stats_pack(stats[0], stats[1], packed.n_contigs, tail)
     if fused:
-        cs = gbuf[Dout * Dout : Dout * Dout + Dout]
-    planes = e = center = None
-    if fused:
-        # provisional centre from a strided row sample (the exact mean needs the full pass);
-        # fixed-point range from the hard bound of the transform: |am_clr| <= log1p(longest
-        # contig), |clr|, |ilr| <= log(max(D^2, longest contig)) + 1
-        sample = _sample_rows(n_out, dev, packed._plans)
-        ns = int(sample.numel())
-        if row_index is not None:
-            sample = row_index[sample]
-        cs_s = zbuf[2 * D : 2 * D + D + 1]
-        if method == "ilr":  # the generic ilr kernel has no fused column sums; 2048 x 511 is tiny
-            cs_s[:Dout] = _dev.normalize_counts(counts, method, sample, None).sum(dim=0)
+        if n_out > 0:
+            # provisional centre from a strided row sample of THIS shard (the exact mean needs the full
+            # pass).  Ranks need not agree on it: each turns its Gram into one about the origin before
+            # the all-reduce (am_gram_recenter), so no exchange is needed for the centre.
+            sample = _sample_rows(n_out, dev, packed._plans)
+            ns = int(sample.numel())
+            if row_index is not None:
+                sample = row_index[sample]
+            cs_s = zbuf[D : 2 * D]
+            if method == "ilr":  # the generic ilr kernel has no fused column sums; 2048 x 511 is tiny
+                cs_s[:Dout] = _dev.normalize_counts(counts, method, sample, None).sum(dim=0)
+            else:
+                _dev.normalize_counts(counts, method, sample, None, colsum=cs_s)
+            center = cs_s * (1.0 / ns)
+            e, sc = _dev.plane_scales(center, None, _bound_for(packed, method, D))
+            Xfull = torch.empty((n_out, D), dtype=torch.float64, device=dev)
+            X = Xfull[:, : D - 1] if method == "ilr" else Xfull
+            _, planes = _dev.normalize_planes(counts, method, row_index, center, sc, R[GG : GG + D],
+                                              out=Xfull, want_out=not overlap)
+            center = center[:Dout]
         else:
-            _dev.normalize_counts(counts, method, sample, None, colsum=cs_s[:D])
+            X = torch.empty((0, Dout), dtype=torch.float64, device=dev)
+        mark("normalise")
+        n_t.fill_(float(n_out))
+        if n_out > 0:
+            _dev.gram_planes(planes, n_out, Dout, e, out=G)
+            if overlap:
+                # the fp64 rows: same kernel, planes switched off, queued behind the Gram on the side
+                # stream so that it shares the chip with the eigensolve and not with the Gram
+                cur = torch.cuda.current_stream(dev)
+                side = _Side.stream(dev)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    _dev.normalize_planes(counts, method, row_index, None, None, None, out=Xfull, want_planes=False)
+        c_fin = center
         if distributed:
-            cs_s[D] = float(ns)
-            _dist.allreduce_sum_([cs_s], group)
-            center = cs_s[:D] / cs_s[D]
+            if n_out > 0:
+                _dev.gram_recenter(G, cs, center, None, n_t)
+            _dist.allreduce_sum_([R], group)
+            c_fin = zbuf[:Dout]  # zeros: the all-reduced Gram is about the origin
+        elif n_out == 0:
+            c_fin = None
+    else:
+        cm = zbuf[:Dout]  # column max|x|: fixed-point scale
+        if method == "ilr" or Dout > 1024:
+            X = _dev.normalize_counts(counts, method, row_index, col_index)
+            if n_out > 0:
+                _dev.colstats(X, cs, cm)
         else:
-            center = cs_s[:D] * (1.0 / ns)
-        if method == "am_clr":
-            bound = packed._plans.get("log1p_maxlen")
-            if bound is None:
-                bound = float(np.log1p(float(packed.lengths.max()) if packed.n_contigs else 1.0))
-                packed._plans["log1p_maxlen"] = bound
-        else:
-            # |clr|, |ilr| <= max log q - min log q <= log(1 / min q), min q >= min(1/D^2, 1/(row sum))
-            bound = packed._plans.get("log_range")
-            if bound is None:
-                longest = float(packed.lengths.max()) if packed.n_contigs else 1.0
-                bound = float(max(2.0 * np.log(D), np.log(max(longest, 1.0))) + 1.0)
-                packed._plans["log_range"] = bound
-        e, sc = _dev.plane_scales(center, None, bound)
-        X, planes = _dev.normalize_planes(counts, method, row_index, center, sc, gbuf[Dout * Dout : Dout * Dout + D])
-        center = center[:Dout]
-    elif method == "ilr" or Dout > 1024:
-        X = _dev.normalize_counts(counts, method, row_index, col_index)
-        cm = zbuf[Dout : 2 * Dout]
-        _dev.colstats(X, cs, cm)
-    else:
-        cm = zbuf[Dout : 2 * Dout]  # column max|x|: fixed-point scale
-        X = _dev.normalize_counts(counts, method, row_index, col_index, colsum=cs, colmaxabs=cm)
-    mark("normalise")
-    if fused:
-        n_t = gbuf[Dout * Dout + D :]
-        n_t.fill_(float(X.shape[0]))
-    else:
-        n_t = torch.full((1,), float(X.shape[0]), dtype=torch.float64, device=dev)
+            X = _dev.normalize_counts(counts, method, row_index, col_index, colsum=cs, colmaxabs=cm)
+        mark("normalise")
+        n_t.fill_(float(n_out))
         if distributed:
-            _dist.allreduce_sum_([cs, n_t], group)
-    mu = None
-    if not fused and X.shape[0] > 0:
-        mu = cs / n_t
-        # generic route to the same tensor-core kernels: quantise the fp64 matrix about its exact mean
-        center = mu
-        e, sc = _dev.plane_scales(center, cm)
-        planes = _dev.quantize_planes(X, center, sc)
-    if fused:
-        G = _dev.gram_planes(planes, X.shape[0], Dout, e, out=gbuf[: Dout * Dout].view(Dout, Dout))
+            _dist.allreduce_sum_([R[GG:]], group)  # column sums | row count | flags
+        if n_out > 0:
+            # generic route to the same tensor-core kernels: quantise the fp64 matrix about the exact mean
+            center = cs / n_t
+            e, sc = _dev.plane_scales(center, cm)
+            planes = _dev.quantize_planes(X, center, sc)
+            _dev.gram_planes(planes, n_out, Dout, e, out=G)
         if distributed:
-            _dist.allreduce_sum_([gbuf], group)  # G | column sums | row count
-    else:
-        G = _dev.gram_planes(planes, X.shape[0], Dout, e) if planes is not None else torch.zeros(
-            (Dout, Dout), dtype=torch.float64, device=dev)
-        if distributed:
-            _dist.allreduce_sum_([G], group)
+            _dist.allreduce_sum_([R[:GG]], group)
+        c_fin = None
     # mu and C = (G - n (mu - centre)(mu - centre)^T) / (n - 1) in one launch (in place on G)
-    mu = _dev.cov_finish(G, cs, center if fused else None, n_t)
+    mu = _dev.cov_finish(G, cs, c_fin, n_t)
     C = G
     mark("gram")
     P = min(n_components, Dout)
     evals, comps, total = _dev.eigh_topk(C, P)
     mark("eigh")
     evals = torch.clamp(evals, min=0.0)
-    if planes is not None and P <= 64:
-        scores = _dev.project_planes(planes, X.shape[0], Dout, e, center, mu, comps)
+    if n_out == 0:
+        scores = torch.empty((0, P), dtype=torch.float64, device=dev)
+    elif planes is not None and P <= 64:
+        scores = _dev.project_planes(planes, n_out, Dout, e, center, mu, comps)
     else:
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
+            side = None
         scores = _dev.project(X, mu, comps)
+    if side is not None:
+        torch.cuda.current_stream(dev).wait_stream(side)  # everything is ordered on the caller's stream again
     mark("project")
     return dict(scores=scores, explained_variance=evals, explained_variance_ratio=evals / total,
-                components=comps, mean=mu, row_index=row_index, col_index=col_index, normalized=X)
+                components=comps, mean=mu, row_index=row_index, col_index=col_index, normalized=X,
+                stats=tail, n_total=n_t)
 
 
 def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_components: int = 50,
-              group=None, distributed: bool = False, keep: bool = True, marks=None) -> Dict[str, Any]:
+              group=None, distributed: bool = False, keep: bool = True, marks=None,
+              overlap: bool = True) -> Dict[str, Any]:
     """counts, normalised matrix and PCA scores of this rank's contig shard.
 
     am_clr's global column drop and all-NA row drop (kmers.py:369) are handled optimistically:
     the whole pass runs on the stream assuming every column occurs somewhere and every contig has
-    counts (true for any real assembly at k = 5); the two flags are read back ONCE, after the last
+    counts (true for any real assembly at k = 5); the two tests are read back ONCE, after the last
     kernel has been queued, and the rare other case re-runs with explicit row/column gathers.
+    With several GPUs the tests travel inside the Gram all-reduce, so every rank reads the same
+    (global) answer and takes the same branch.
     """
     import torch
 
     dev = packed.device
     mark = marks if marks is not None else (lambda name: None)
-    with torch.cuda.device(dev):
+    if dev.type != "cuda":
+        overlap = False  # only tests/test_dist_gloo.py gets here, with a stand-in for ``device``
+    with _ctx(dev):
         mark("start")
         counts, present, row_sum = _dev.count_packed(packed, k)
         mark("count")
-        if distributed:
-            _dist.allreduce_max_(present, group)
-        if packed.n_contigs:
-            flags = _dev.count_flags(present, row_sum, packed.n_contigs)
-        else:
-            flags = torch.ones(2, dtype=torch.int32, device=dev)
-        res = None
-        if packed.n_contigs:
-            res = _fit_project(packed, counts, method, n_components, None, None, group, distributed, mark)
-        flags_h = flags.cpu().numpy()  # the only host sync: after everything has been queued
-        cols_ok, rows_ok = bool(flags_h[0] > 0), bool(flags_h[1] > 0)
+        res = _fit_project(packed, counts, (present, row_sum), method, n_components, None, None, group,
+                           distributed, mark, overlap)
+        D = counts.shape[1]
+        st = res["stats"].cpu().numpy()  # the only host sync: after everything has been queued
+        present_g = st[:D] > 0
+        cols_ok, rows_ok = bool(present_g.all()), bool(st[D] == 0)
+        n_total = float(res["n_total"].item()) if distributed else float(packed.n_contigs)
         if method != "am_clr":
-            if packed.n_contigs and not rows_ok:
+            if n_total > 0 and not rows_ok:
                 raise ValueError("Input matrix cannot have rows with all zeros")
-        elif res is None or not (cols_ok and rows_ok):
-            col_index = None if cols_ok else torch.nonzero(present > 0).flatten().to(torch.int32)
+        elif n_total > 0 and not (cols_ok and rows_ok):
+            col_index = None if cols_ok else torch.from_numpy(np.flatnonzero(present_g).astype(np.int32)).to(dev)
             row_index = None if rows_ok else torch.nonzero(row_sum > 0).flatten()
-            res = _fit_project(packed, counts, method, n_components, row_index, col_index, group, distributed,
-                               lambda name: None)
+            res = _fit_project(packed, counts, None, method, n_components, row_index, col_index, group, distributed,
+                               lambda name: None, overlap)
         out = res
+        out.pop("stats")
+        out.pop("n_total")
         X = out.pop("normalized")
         if keep:
+            if distributed:
+                present = torch.from_numpy(present_g.astype(np.int32)).to(dev)
             out.update(counts=counts, normalized=X, col_present=present, row_sum=row_sum)
         return out
 
 
 class HostFeaturiser:
-    """End-to-end entry for host buffers: ASCII contig bytes in pinned host memory
-    -> H2D -> device pack -> featurise -> scores (+ explained variance) back on the
-    host.  Buffers are allocated once and reused across calls."""
+    """End-to-end entry for host buffers -> scores (+ explained variance) back on the host.
+    Buffers are allocated once and reused across calls.
 
-    def __init__(self, asm: HostAssembly, device=None, k: int = 5, method: str = "am_clr", n_components: int = 50):
+    ``host_format="packed"`` (default): the pinned host buffers hold the 2-bit codes and the sparse
+    exception structure written by the threaded host packer (``am_pack_host`` — in a real run the
+    FASTA parser fills them directly), 0.25 byte per base over PCIe.  ``host_format="ascii"``: pinned
+    ASCII bytes, 1 byte per base over PCIe, packed on the device (``am_pack_device``)."""
+
+    def __init__(self, asm: HostAssembly, device=None, k: int = 5, method: str = "am_clr", n_components: int = 50,
+                 host_format: str = "packed", threads: int = 0):
+        import time
+
         import torch
 
+        if host_format not in ("packed", "ascii"):
+            raise ValueError("host_format must be 'packed' or 'ascii'")
         self.dev = L.require_cuda(device)
         self.k, self.method, self.P = k, method, n_components
+        self.host_format = host_format
         offsets = np.ascontiguousarray(asm.offsets, dtype=np.int64)
         base = int(offsets[0])
         self.n = asm.n_contigs
         self.total_bp = asm.total_bp
-        self.starts_h, self.lengths, self.total = pack_plan(offsets)
+        self.ids = asm.ids
+        self.host_pack_ms = None
         with torch.cuda.device(self.dev):
-            self.h_seq = torch.empty(self.total_bp, dtype=torch.uint8).pin_memory()
-            self.h_seq.numpy()[:] = asm.seq[base : base + self.total_bp]
-            self.h_off = torch.from_numpy(offsets - base).pin_memory()
-            self.h_starts = torch.from_numpy(self.starts_h if self.n else np.zeros(1, np.int64)).pin_memory()
-            self.d_seq = torch.empty(self.total_bp + 64, dtype=torch.uint8, device=self.dev)
-            self.d_off = torch.empty(self.h_off.shape, dtype=torch.int64, device=self.dev)
-            self.d_starts = torch.empty(self.h_starts.shape, dtype=torch.int64, device=self.dev)
+            if host_format == "ascii":
+                self.starts_h, self.lengths, self.total = pack_plan(offsets)
+                h_seq = torch.empty(self.total_bp, dtype=torch.uint8).pin_memory()
+                h_seq.numpy()[:] = asm.seq[base : base + self.total_bp]
+                h_off = torch.from_numpy(offsets - base).pin_memory()
+                h_starts = torch.from_numpy(self.starts_h if self.n else np.zeros(1, np.int64)).pin_memory()
+                self.host = [h_seq, h_off, h_starts]
+                pad = [64, 0, 0]
+            else:
+                from .assembly import pack_host_arrays
+
+                pack_host_arrays(asm.slice(0, min(self.n, 64)), threads)  # thread pool / page warm-up
+                t0 = time.perf_counter()
+                starts, lengths, total, codes, bitmap, rank, masks = pack_host_arrays(asm, threads)
+                self.host_pack_ms = (time.perf_counter() - t0) * 1e3
+                self.starts_h, self.lengths, self.total = starts, lengths, total
+                self.n_exc = len(masks)
+                pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).view(dt)).pin_memory()
+                self.host = [pin(codes, np.int32), pin(bitmap, np.int32), pin(rank, np.int32),
+                             pin(masks if len(masks) else np.zeros(1, np.uint64), np.int64),
+                             pin(starts if self.n else np.zeros(1, np.int64), np.int64)]
+                pad = [0, 0, 0, 0, 0]
+            self.bufs = [[torch.empty(h.numel() + p, dtype=h.dtype, device=self.dev) for h, p in zip(self.host, pad)]]
             self.h_scores = None
-        self.h2d_bytes = self.total_bp + self.h_off.numel() * 8 + self.h_starts.numel() * 8
+        self.h2d_bytes = sum(h.numel() * h.element_size() for h in self.host)
         self.d2h_bytes = 0
         self.exc_cap = 0
+        self._plans = None
+
+    def describe(self) -> str:
+        if self.host_format == "packed":
+            return ("pinned host 2-bit codes + exception masks (threaded host packer am_pack_host, 0.25 B/bp) -> H2D "
+                    "-> count -> normalise -> PCA -> D2H scores; back-to-back steps, the H2D copy of step i+1 "
+                    "overlaps the compute of step i")
+        return ("pinned host ASCII (1 B/bp) -> H2D -> am_pack_device -> count -> normalise -> PCA -> D2H scores; "
+                "back-to-back steps, the H2D copy of step i+1 overlaps the compute of step i (PCIe-bound)")
+
+    def _upload(self, slot: int):
+        for h, d in zip(self.host, self.bufs[slot]):
+            d[: h.numel()].copy_(h, non_blocking=True)
 
     def run(self, group=None, distributed: bool = False):
-        """One assembly, strictly serial: H2D -> pack -> featurise -> D2H (latency path)."""
+        """One assembly, strictly serial: H2D -> (pack) -> featurise -> D2H (latency path)."""
         import torch
 
         with torch.cuda.device(self.dev):
-            self.d_seq[: self.total_bp].copy_(self.h_seq, non_blocking=True)
-            self.d_off.copy_(self.h_off, non_blocking=True)
-            self.d_starts.copy_(self.h_starts, non_blocking=True)
-            return self._compute(self.d_seq, self.d_off, self.d_starts, group, distributed)
+            self._upload(0)
+            return self._compute(self.bufs[0], group, distributed)
 
     def run_many(self, n_steps: int, group=None, distributed: bool = False):
         """``n_steps`` assemblies back to back with double buffering: the H2D copy of step i+1 runs on
-        a copy stream while step i is packed and featurised.  Every step still copies its input from
-        pinned host memory and reads its scores back; only the PCIe time of the NEXT step is hidden
-        behind the compute of the current one.  Returns the last step's host results."""
+        a copy stream while step i is featurised.  Every step still copies its input from pinned host
+        memory and reads its scores back; only the PCIe time of the NEXT step is hidden behind the
+        compute of the current one.  Returns the last step's host results."""
         import torch
 
         with torch.cuda.device(self.dev):
-            if getattr(self, "d_seq2", None) is None:
-                self.d_seq2 = torch.empty_like(self.d_seq)
-                self.d_off2 = torch.empty_like(self.d_off)
-                self.d_starts2 = torch.empty_like(self.d_starts)
+            if len(self.bufs) == 1:
+                self.bufs.append([torch.empty_like(b) for b in self.bufs[0]])
                 self.copy_stream = torch.cuda.Stream(device=self.dev)
                 self.ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
-            bufs = [(self.d_seq, self.d_off, self.d_starts), (self.d_seq2, self.d_off2, self.d_starts2)]
             cur = torch.cuda.current_stream(self.dev)
 
             def submit(slot):
                 # ALL host->device traffic of a step goes through the copy stream: a small copy queued on
-                # the compute stream would sit behind the next step's 1 GB transfer on the same DMA engine
+                # the compute stream would sit behind the next step's transfer on the same DMA engine
                 self.copy_stream.wait_stream(cur)  # the buffer's previous consumer has been queued before
                 with torch.cuda.stream(self.copy_stream):
-                    bufs[slot][0][: self.total_bp].copy_(self.h_seq, non_blocking=True)
-                    bufs[slot][1].copy_(self.h_off, non_blocking=True)
-                    bufs[slot][2].copy_(self.h_starts, non_blocking=True)
+                    self._upload(slot)
                     self.ev_copied[slot].record(self.copy_stream)
 
             out = None
@@ -245,17 +347,27 @@ class HostFeaturiser:
                 cur.wait_event(self.ev_copied[slot])
                 if i + 1 < n_steps:
                     submit((i + 1) & 1)  # buffer (i+1)&1 was last used by step i-1, which has completed
-                out = self._compute(bufs[slot][0], bufs[slot][1], bufs[slot][2], group, distributed)
+                out = self._compute(self.bufs[slot], group, distributed)
             return out
 
-    def _compute(self, d_seq, d_off, d_starts, group, distributed):
-        import torch
-
-        with torch.cuda.device(self.dev):
+    def _packed(self, bufs):
+        if self.host_format == "ascii":
+            d_seq, d_off, d_starts = bufs
             packed = pack_device_arrays(d_seq, d_off, d_starts, self.n, self.total,
                                         self.lengths, self.starts_h, self.total_bp, exc_capacity=self.exc_cap)
             self.exc_cap = max(self.exc_cap, packed.n_exc + 1024)
-            if getattr(self, "_plans", None):
+            return packed
+        codes, bitmap, rank, masks, starts = bufs
+        return PackedAssembly(n_contigs=self.n, total_bp=self.total_bp, total_packed_bases=self.total,
+                              lengths=self.lengths, starts_host=self.starts_h, codes=codes, exc_bitmap=bitmap,
+                              exc_rank=rank, exc_mask=masks, starts=starts, n_exc=self.n_exc, ids=self.ids)
+
+    def _compute(self, bufs, group, distributed):
+        import torch
+
+        with torch.cuda.device(self.dev):
+            packed = self._packed(bufs)
+            if self._plans:
                 packed._plans = self._plans  # the work list depends only on the contig lengths
             res = featurise(packed, self.k, self.method, self.P, group=group, distributed=distributed, keep=False)
             self._plans = packed._plans

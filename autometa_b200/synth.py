@@ -21,7 +21,7 @@ from typing import List, Tuple
 
 import numpy as np
 
-from .assembly import HostAssembly
+from .hostdata import HostAssembly
 
 _ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 

@@ -231,6 +231,17 @@ int am_cov_finish(double *d_G, int D, const double *d_colsum, const double *d_ce
  * (kmers.py:369) in one launch. */
 int am_count_flags(const int32_t *d_col_present, int ncols, const int32_t *d_row_sum,
                    int64_t n_contigs, int32_t *d_flags, void *stream);
+/* SUM-reducible form of the same two tests, for the single all-reduce of the multi-GPU path:
+ * d_out[0..ncols) = 1.0 where the column occurs in this shard, d_out[ncols] = number of contigs
+ * without any counted window (kmers.py:369). */
+int am_stats_pack(const int32_t *d_col_present, int ncols, const int32_t *d_row_sum,
+                  int64_t n_contigs, double *d_out, void *stream);
+/* Move a Gram taken about d_c_old to one about d_c_new (NULL = the origin for either):
+ * G += n [(mu - c_new)(mu - c_new)^T - (mu - c_old)(mu - c_old)^T], mu = colsum / n.  Lets every
+ * rank quantise about its own provisional centre and still all-reduce one buffer [G | colsum | n]
+ * (sklearn's own form is the Gram about the origin, _pca.py:604-610). */
+int am_gram_recenter(double *d_G, int D, const double *d_colsum, const double *d_c_old,
+                     const double *d_c_new, const double *d_n, void *stream);
 int64_t am_gram_work_bytes(int D);
 int am_gram(const double *d_X, int64_t n_rows, int D, const double *d_mu,
             double *d_G, void *d_work, void *stream);

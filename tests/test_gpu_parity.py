@@ -300,6 +300,86 @@ def test_eigh_against_numpy(torch_cuda):
         assert np.all(V[np.arange(n), idx] > 0)  # svd_flip(u_based_decision=False)
 
 
+def test_clr_ilr_kernels_match_skbio_published_vectors(torch_cuda):
+    """The normalise kernels on the integer compositions of scikit-bio's own doctest vectors
+    (tests/test_oracle.py: SKBIO_*): clr / ilr of [1, 3, 4, 2] are the published clr / ilr of
+    [.1, .3, .4, .2]; rows with zeros go through multiplicative_replacement's published example."""
+    import torch
+
+    from test_oracle import SKBIO_CLR, SKBIO_ILR, SKBIO_MR_OUT
+
+    from autometa_b200 import device as D
+
+    counts = torch.tensor([[1, 3, 4, 2], [10, 30, 40, 20], [2, 4, 4, 0], [0, 5, 5, 0]], dtype=torch.int32).cuda()
+    clr = D.normalize_counts(counts, "clr").cpu().numpy()
+    ilr = D.normalize_counts(counts, "ilr").cpu().numpy()
+    for r in (0, 1):
+        np.testing.assert_allclose(clr[r], SKBIO_CLR, rtol=0, atol=5e-9)
+        np.testing.assert_allclose(ilr[r], SKBIO_ILR, rtol=0, atol=5e-9)
+    for r, q in ((2, SKBIO_MR_OUT[0]), (3, SKBIO_MR_OUT[1])):
+        lq = np.log(q)
+        np.testing.assert_allclose(clr[r], lq - lq.mean(), rtol=0, atol=1e-14)
+        np.testing.assert_allclose(ilr[r], (lq - lq.mean()) @ O.ilr_basis(4).T, rtol=0, atol=1e-14)
+
+
+def test_eigh_topk_direct(torch_cuda):
+    """am_eigh_topk itself (the production solver: cluster tridiagonalisation, bisection, inverse iteration,
+    re-orthonormalisation, WY back-transformation) against numpy.linalg.eigh: every kernel branch by shape
+    (D < 19: reflector-pair back-transformation; D <= 512: register tridiagonalisation; 512 < D <= 576:
+    shared-memory tridiagonalisation), P up to 128, repeated and tightly clustered eigenvalues (the CholeskyQR2
+    branch), rank-deficient input, and no silent downgrade to the Jacobi solver."""
+    import torch
+
+    from autometa_b200 import device as D
+
+    rng = np.random.default_rng(7)
+
+    def spectrum_matrix(n, lam):
+        Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+        A = (Q * lam) @ Q.T
+        return 0.5 * (A + A.T)
+
+    def check(A, P, tag, sep_tol=1e-6):
+        n = A.shape[0]
+        w, V, tr = D.eigh_topk(torch.from_numpy(A).cuda(), P)
+        w, V, tr = w.cpu().numpy(), V.cpu().numpy(), float(tr.item())
+        wr, Vr = np.linalg.eigh(A)
+        wr, Vr = wr[::-1], Vr[:, ::-1].T
+        scale = max(abs(wr[0]), abs(wr[-1]), 1e-300)
+        assert np.max(np.abs(w - wr[:P])) <= 1e-12 * scale, tag
+        assert abs(tr - np.trace(A)) <= 1e-12 * max(abs(np.trace(A)), scale), tag
+        assert np.max(np.abs(V @ V.T - np.eye(P))) < 1e-11, tag
+        assert np.max(np.abs(A @ V.T - V.T * w)) <= 1e-11 * scale, tag
+        idx = np.argmax(np.abs(V), axis=1)
+        assert np.all(V[np.arange(P), idx] > 0), tag  # svd_flip(u_based_decision=False)
+        # isolated eigenvalues: the vector itself must match (up to nothing: the sign rule is applied)
+        gaps = np.minimum(np.abs(np.diff(wr, prepend=np.inf)), np.abs(np.diff(wr, append=-np.inf)))[:P]
+        iso = gaps > sep_tol * scale
+        if iso.any():
+            cos = np.abs(np.sum(V[iso] * Vr[:P][iso], axis=1))
+            assert np.all(cos >= 1 - 1e-9), (tag, cos.min())
+
+    for n in (3, 18, 19, 64, 511, 512, 576):
+        B = rng.normal(size=(n, n + 5))
+        S = B @ B.T / n
+        for P in (1, 50, 128):
+            if P <= n:
+                check(S, P, f"wishart n={n} P={P}")
+    for n in (64, 512):
+        # a triple eigenvalue at the top, a cluster 1e-11 apart around rank 10, then a smooth decay
+        lam = np.sort(np.concatenate([[9.0, 9.0, 9.0], 5.0 + 1e-11 * np.arange(4), rng.uniform(0.1, 4.0, n - 7)]))[::-1]
+        check(spectrum_matrix(n, lam.copy()), min(50, n), f"clustered n={n}")
+        # rank-deficient: 20 non-zero eigenvalues, P beyond the rank (null-space vectors are arbitrary but
+        # must stay orthonormal with zero residual)
+        lam = np.concatenate([np.linspace(3.0, 1.0, 20), np.zeros(n - 20)])
+        check(spectrum_matrix(n, lam), min(50, n), f"rank20 n={n}")
+    # the covariance of clr rows is exactly singular (rows sum to zero): D = 512 with one zero eigenvalue
+    Xr = rng.normal(size=(6000, 512))
+    Xr -= Xr.mean(axis=1, keepdims=True)
+    check(np.cov(Xr, rowvar=False), 50, "clr-like singular covariance")
+    assert not D._topk_state.get("disabled"), "am_eigh_topk fell back to the Jacobi solver on this GPU"
+
+
 # ---------------------------------------------------------------------------- DBSCAN
 def _sweep_table():
     from autometa_b200 import synth
@@ -371,8 +451,8 @@ def test_sweep_incremental_equals_fresh_and_oracle(torch_cuda):
 
 
 def test_sweep_full_size_c4(torch_cuda):
-    """C4: 200k points, reference eps grid; identical to sklearn at a few eps (sklearn is what
-    recursive_dbscan.py:109 executes) and monotone merging everywhere."""
+    """C4: 200k points, the reference's 48-value eps grid; the label vector is identical to sklearn's
+    (what recursive_dbscan.py:109 executes) at EVERY eps of the grid."""
     import torch
     from sklearn.cluster import DBSCAN
 
@@ -382,17 +462,16 @@ def test_sweep_full_size_c4(torch_cuda):
     X = np.ascontiguousarray(table[["x_1", "x_2", "coverage"]].to_numpy())
     sweep = D.EpsSweep(torch.from_numpy(X).cuda())
     grid = O.eps_schedule(48)
-    check = {0: None, 5: None, 17: None, 47: None}
     prev = None
     for i, eps in enumerate(grid):
-        lab = sweep.step(eps)
+        lab = sweep.step(eps).cpu().numpy()
         n = int(sweep.n_clusters.item())
         if prev is not None:
             assert n <= prev
         prev = n
-        if i in check:
-            ref = DBSCAN(eps=eps, min_samples=1, n_jobs=-1).fit(X).labels_
-            assert np.array_equal(lab.cpu().numpy(), ref.astype(np.int64)), eps
+        ref = DBSCAN(eps=eps, min_samples=1, n_jobs=-1).fit(X).labels_
+        assert np.array_equal(lab, ref.astype(np.int64)), (i, eps)
+    assert i == 47
 
 
 def test_device_cluster_metrics_match_host_mirror(torch_cuda):
@@ -613,6 +692,18 @@ def test_featurise_full_size_properties(torch_cuda, case):
     s_ref = (Xs - mean.cpu().numpy()) @ V.T
     s_got = S[torch.from_numpy(sample).cuda()].cpu().numpy()
     assert np.max(np.abs(s_got - s_ref)) <= 1e-8 * float(S.abs().max())
+    if case == "C2_am_clr":
+        # directly against sklearn on the full 200k x 512 matrix (what kmers.py:605 executes)
+        from sklearn.decomposition import PCA
+
+        Xh = X.cpu().numpy()
+        p = PCA(n_components=50, random_state=np.random.RandomState(42))
+        sc = p.fit_transform(Xh)
+        assert p._fit_svd_solver == "covariance_eigh"
+        _check_pca(dict(explained_variance=ev, explained_variance_ratio=evr, components=V, scores=S.cpu().numpy()),
+                   dict(explained_variance=p.explained_variance_, explained_variance_ratio=p.explained_variance_ratio_,
+                        components=p.components_, scores=sc))
+        del Xh, sc
     # C V^T = V^T diag(ev): the components are eigenvectors of the sample covariance
     Xc = X - mean
     CV = (Xc.T @ (Xc @ res["components"].T)) / (n - 1)

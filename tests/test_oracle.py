@@ -154,3 +154,39 @@ def test_c_port_matches_numpy_oracle_and_golden(golden_kmers, small_fna):
     a = oracle_c.am_clr(got[keep], 2)
     b, _, _ = O.am_clr(O.counts_to_float_frame(ref))
     assert np.max(np.abs(a - b)) <= 1e-13 * np.max(np.abs(b))
+
+
+# ----------------------------------------------------------------------------- scikit-bio published vectors
+# scikit-bio is not installable here (no wheel, no network), so clr / ilr / multiplicative_replacement are
+# restated from its documentation (oracle_np.py).  These are the known answers scikit-bio itself publishes in
+# the doctests of skbio.stats.composition (0.5.x / 0.6.x: closure, multiplicative_replacement, clr, ilr) — the
+# same functions the reference calls at kmers.py:23,418-421 — so the restatement is pinned to the library's
+# own published vectors, not only to itself.
+SKBIO_CLOSURE_IN = np.array([[2, 2, 6], [4, 4, 2]], dtype=np.float64)
+SKBIO_CLOSURE_OUT = np.array([[0.2, 0.2, 0.6], [0.4, 0.4, 0.2]])
+SKBIO_MR_IN = np.array([[0.2, 0.4, 0.4, 0.0], [0.0, 0.5, 0.5, 0.0]])
+SKBIO_MR_OUT = np.array([[0.1875, 0.375, 0.375, 0.0625], [0.0625, 0.4375, 0.4375, 0.0625]])
+SKBIO_X = np.array([0.1, 0.3, 0.4, 0.2])
+SKBIO_CLR = np.array([-0.79451346, 0.30409883, 0.5917809, -0.10136628])
+SKBIO_ILR = np.array([-0.7768362, -0.68339802, 0.11704769])
+
+
+def test_skbio_published_vectors():
+    # closure (the first step of multiplicative_replacement / clr / ilr)
+    mr = O.multiplicative_replacement(SKBIO_CLOSURE_IN)  # no zeros: reduces to closure
+    np.testing.assert_allclose(mr, SKBIO_CLOSURE_OUT, rtol=0, atol=1e-15)
+    # multiplicative_replacement, default delta = (1/D)^2
+    np.testing.assert_allclose(O.multiplicative_replacement(SKBIO_MR_IN), SKBIO_MR_OUT, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(O.multiplicative_replacement(SKBIO_MR_IN).sum(axis=1), 1.0, atol=1e-15)
+    # clr / ilr doctest vectors (8 printed digits)
+    np.testing.assert_allclose(O.clr(SKBIO_X[None, :])[0], SKBIO_CLR, rtol=0, atol=5e-9)
+    np.testing.assert_allclose(O.ilr(SKBIO_X[None, :])[0], SKBIO_ILR, rtol=0, atol=5e-9)
+    # the call site hands over COUNTS (kmers.py:418-421): the same composition as integers
+    np.testing.assert_allclose(O.clr(np.array([[1.0, 3.0, 4.0, 2.0]]))[0], SKBIO_CLR, rtol=0, atol=5e-9)
+    np.testing.assert_allclose(O.ilr(np.array([[10.0, 30.0, 40.0, 20.0]]))[0], SKBIO_ILR, rtol=0, atol=5e-9)
+    # ilr basis: orthonormal rows, orthogonal to the ones vector (the documented Gram-Schmidt basis)
+    B = O.ilr_basis(4)
+    np.testing.assert_allclose(B @ B.T, np.eye(3), atol=1e-15)
+    np.testing.assert_allclose(B.sum(axis=1), 0.0, atol=1e-15)
+    with pytest.raises(ValueError):
+        O.multiplicative_replacement(np.array([[0.0, 0.0, 0.0]]))
