@@ -97,6 +97,79 @@ __device__ __forceinline__ uint32_t window_byte(const uint32_t (&w)[5], int j) {
   return v ^ ((v >> 5) & 0x7cu);   // same mix as swz(), on the pre-scaled value
 }
 
+// One warp tile: lane l takes the SEG bases that start at window t0 + SEG * l of the work item (SEG = 64: one
+// 16-byte load per lane, the steady state; SEG = 32 / 16: the remainder of a contig spread over all 32
+// lanes, so that the last tile of a contig costs what it holds instead of a full 2048-window tile — at
+// 5 kbp per contig the half-empty last tile was most of the per-contig overhead).  A segment never
+// straddles a 64-base group (SEG divides 64), so the exception mask of ONE group (+ K-1 bits of the
+// next) covers all its windows.
+template <int K, int SEG>
+__device__ __forceinline__ void count_tile(const uint4 *__restrict__ codes4, const uint32_t *__restrict__ codes,
+                                           const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ rank,
+                                           const uint64_t *__restrict__ exc_mask, int64_t gbase, int t0, int nw,
+                                           int lane, uint32_t *hist) {
+  constexpr int NB = 1 << (2 * K);
+  constexpr int NWORD = SEG / 16;
+  constexpr uint64_t SEGMASK = SEG == 64 ? ~0ull : ((1ull << SEG) - 1ull);
+  const int seg = t0 + lane * SEG;
+  int nv = nw - seg;
+  nv = nv < 0 ? 0 : (nv > SEG ? SEG : nv);
+  uint64_t valid_out = 0ull;
+  uint32_t wreg[5] = {0u, 0u, 0u, 0u, 0u};
+  if (nv > 0) {
+    const int64_t g = gbase + (seg >> 6);
+    const int sub = seg & 63;
+    if (SEG == 64) {
+      const uint4 x = __ldg(codes4 + g);
+      wreg[0] = x.x; wreg[1] = x.y; wreg[2] = x.z; wreg[3] = x.w;
+      wreg[4] = __ldg(codes + 4 * g + 4);
+    } else if (SEG == 32) {
+      const uint2 x = __ldg(reinterpret_cast<const uint2 *>(codes + 4 * g + (sub >> 4)));
+      wreg[0] = x.x; wreg[1] = x.y;
+      wreg[2] = __ldg(codes + 4 * g + (sub >> 4) + 2);
+    } else {
+      wreg[0] = __ldg(codes + 4 * g + (sub >> 4));
+      wreg[1] = __ldg(codes + 4 * g + (sub >> 4) + 1);
+    }
+    const int64_t g1 = g + 1;
+    const uint32_t bw = __ldg(bitmap + (g >> 5));
+    const uint32_t bw1 = ((g1 >> 5) == (g >> 5)) ? bw : __ldg(bitmap + (g1 >> 5));
+    const uint32_t bit = (bw >> (g & 31)) & 1u;
+    const uint32_t bit1 = (bw1 >> (g1 & 31)) & 1u;
+    uint64_t valid = (nv == 64) ? ~0ull : ((1ull << nv) - 1ull);
+    if (bit | bit1) {
+      uint64_t m = 0, m1 = 0;
+      if (bit) m = __ldg(exc_mask + __ldg(rank + (g >> 5)) + __popc(bw & ((1u << (g & 31)) - 1u)));
+      if (bit1) m1 = __ldg(exc_mask + __ldg(rank + (g1 >> 5)) + __popc(bw1 & ((1u << (g1 & 31)) - 1u)));
+      uint64_t bad = m;
+      if (K > 1) {
+        const uint64_t hi = m1 & ((1ull << (K - 1)) - 1ull);
+#pragma unroll
+        for (int s = 1; s < K; ++s) bad |= (m >> s) | (hi << (64 - s));
+      }
+      if (SEG != 64) bad >>= sub;  // windows of this segment
+      valid &= ~bad;
+    }
+    valid_out = valid & SEGMASK;
+  }
+  // warp-uniform choice: the common all-valid tile takes the 3-instruction path; a tile with
+  // any partial / flagged lane sends its invalid windows to a dummy bin (no divergent branches)
+  char *hb = reinterpret_cast<char *>(hist);
+  (void)NWORD;
+  if (__all_sync(FULL, valid_out == SEGMASK)) {
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) atomicAdd(reinterpret_cast<uint32_t *>(hb + window_byte<K>(wreg, j)), 1u);
+  } else {
+    const uint32_t vlo = (uint32_t)valid_out, vhi = (uint32_t)(valid_out >> 32);
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) {
+      const uint32_t bit = ((j < 32 ? vlo : vhi) >> (j & 31)) & 1u;
+      const uint32_t off = bit ? window_byte<K>(wreg, j) : (uint32_t)(NB * 4);
+      atomicAdd(reinterpret_cast<uint32_t *>(hb + off), 1u);
+    }
+  }
+}
+
 template <int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 count_kernel(const uint4 *__restrict__ codes4, const uint32_t *__restrict__ codes,
@@ -125,56 +198,14 @@ count_kernel(const uint4 *__restrict__ codes4, const uint32_t *__restrict__ code
     const int row = it.x, w0 = it.y, nw = it.z, flags = it.w;
     const int64_t gbase = (__ldg(starts + row) + (int64_t)w0) >> 6;
 
-    for (int t0 = 0; t0 < nw; t0 += AM_TILE_BASES) {
-      const int seg = t0 + lane * 64;
-      int nv = nw - seg;
-      nv = nv < 0 ? 0 : (nv > 64 ? 64 : nv);
-      uint64_t valid_out = 0ull;
-      uint32_t wreg[5] = {0u, 0u, 0u, 0u, 0u};
-      if (nv > 0) {
-        const int64_t g = gbase + (seg >> 6);
-        const uint4 x = __ldg(codes4 + g);
-        uint32_t w[5];
-        w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
-        w[4] = __ldg(codes + 4 * g + 4);
-        const int64_t g1 = g + 1;
-        const uint32_t bw = __ldg(bitmap + (g >> 5));
-        const uint32_t bw1 = ((g1 >> 5) == (g >> 5)) ? bw : __ldg(bitmap + (g1 >> 5));
-        const uint32_t bit = (bw >> (g & 31)) & 1u;
-        const uint32_t bit1 = (bw1 >> (g1 & 31)) & 1u;
-        uint64_t valid = (nv == 64) ? ~0ull : ((1ull << nv) - 1ull);
-        if (bit | bit1) {
-          uint64_t m = 0, m1 = 0;
-          if (bit) m = __ldg(exc_mask + __ldg(rank + (g >> 5)) + __popc(bw & ((1u << (g & 31)) - 1u)));
-          if (bit1) m1 = __ldg(exc_mask + __ldg(rank + (g1 >> 5)) + __popc(bw1 & ((1u << (g1 & 31)) - 1u)));
-          uint64_t bad = m;
-          if (K > 1) {
-            const uint64_t hi = m1 & ((1ull << (K - 1)) - 1ull);
-#pragma unroll
-            for (int s = 1; s < K; ++s) bad |= (m >> s) | (hi << (64 - s));
-          }
-          valid &= ~bad;
-        }
-        valid_out = valid;
-#pragma unroll
-        for (int q = 0; q < 5; ++q) wreg[q] = w[q];
-      }
-      // warp-uniform choice: the common all-valid tile takes the 3-instruction path; a tile with
-      // any partial / flagged lane sends its invalid windows to a dummy bin (no divergent branches)
-      char *hb = reinterpret_cast<char *>(hist);
-      if (__all_sync(FULL, valid_out == ~0ull)) {
-#pragma unroll
-        for (int j = 0; j < 64; ++j) atomicAdd(reinterpret_cast<uint32_t *>(hb + window_byte<K>(wreg, j)), 1u);
-      } else {
-        const uint32_t vlo = (uint32_t)valid_out, vhi = (uint32_t)(valid_out >> 32);
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const uint32_t bit = ((j < 32 ? vlo : vhi) >> (j & 31)) & 1u;
-          const uint32_t off = bit ? window_byte<K>(wreg, j) : (uint32_t)(NB * 4);
-          atomicAdd(reinterpret_cast<uint32_t *>(hb + off), 1u);
-        }
-      }
-    }
+    // full-width tiles while more than half a tile remains; then the remainder at 32 or 16 bases per lane
+    int t0 = 0;
+    for (; nw - t0 > AM_TILE_BASES / 2; t0 += AM_TILE_BASES)
+      count_tile<K, 64>(codes4, codes, bitmap, rank, exc_mask, gbase, t0, nw, lane, hist);
+    if (nw - t0 > AM_TILE_BASES / 4)
+      count_tile<K, 32>(codes4, codes, bitmap, rank, exc_mask, gbase, t0, nw, lane, hist);
+    else if (nw - t0 > 0)
+      count_tile<K, 16>(codes4, codes, bitmap, rank, exc_mask, gbase, t0, nw, lane, hist);
     __syncwarp();
 
     // flush: fold the raw histogram into canonical columns, store the row

@@ -74,9 +74,9 @@ def _bound_for(packed, method: str, D: int) -> float:
     return bound
 
 
-def _fit_project(packed, counts, stats, method, n_components, row_index, col_index, group, distributed, mark,
-                 overlap=True):
-    """normalise -> PCA fit -> scores for the given row/column selection (device only, no host sync).
+def _fit(packed, counts, stats, method, row_index, col_index, group, distributed, mark, overlap=True):
+    """Stage 1 — normalise -> digit planes -> Gram -> (all-reduce) -> covariance, for the given row/column
+    selection (device only, no host sync).  Everything whose work grows with the assembly.
 
     Every rank issues the same collectives with the same sizes whatever its shard holds (an empty
     shard, all-NA rows): the k = 5 path has exactly ONE all-reduce, of the buffer
@@ -171,8 +171,18 @@ def _fit_project(packed, counts, stats, method, n_components, row_index, col_ind
         c_fin = None
     # mu and C = (G - n (mu - centre)(mu - centre)^T) / (n - 1) in one launch (in place on G)
     mu = _dev.cov_finish(G, cs, c_fin, n_t)
-    C = G
     mark("gram")
+    return dict(C=G, mu=mu, planes=planes, e=e, center=center, X=X, n_out=n_out, Dout=Dout, side=side,
+                row_index=row_index, col_index=col_index, stats=tail, n_total=n_t, R=R, counts=counts)
+
+
+def _project(st, n_components, mark):
+    """Stage 2 — top-P eigenpairs of the covariance (N-independent, latency-bound) and the scores."""
+    import torch
+
+    C, mu, planes, e, center, X = st["C"], st["mu"], st["planes"], st["e"], st["center"], st["X"]
+    n_out, Dout, side = st["n_out"], st["Dout"], st["side"]
+    dev = C.device
     P = min(n_components, Dout)
     evals, comps, total = _dev.eigh_topk(C, P)
     mark("eigh")
@@ -190,8 +200,14 @@ def _fit_project(packed, counts, stats, method, n_components, row_index, col_ind
         torch.cuda.current_stream(dev).wait_stream(side)  # everything is ordered on the caller's stream again
     mark("project")
     return dict(scores=scores, explained_variance=evals, explained_variance_ratio=evals / total,
-                components=comps, mean=mu, row_index=row_index, col_index=col_index, normalized=X,
-                stats=tail, n_total=n_t)
+                components=comps, mean=mu, row_index=st["row_index"], col_index=st["col_index"], normalized=X,
+                stats=st["stats"], n_total=st["n_total"])
+
+
+def _fit_project(packed, counts, stats, method, n_components, row_index, col_index, group, distributed, mark,
+                 overlap=True):
+    return _project(_fit(packed, counts, stats, method, row_index, col_index, group, distributed, mark, overlap),
+                    n_components, mark)
 
 
 def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_components: int = 50,
@@ -239,6 +255,84 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
             if distributed:
                 present = torch.from_numpy(present_g.astype(np.int32)).to(dev)
             out.update(counts=counts, normalized=X, col_present=present, row_sum=row_sum)
+        return out
+
+
+class FeatureStream:
+    """Throughput mode: assemblies (or partitions of one) featurised back to back with up to ``depth`` of them
+    in flight on two streams.
+
+    A pass has two parts of very different shape: stage 1 (count -> normalise -> Gram; all the work that grows
+    with the assembly, every SM busy) and stage 2 (top-P eigenpairs of the 512 x 512 covariance + scores;
+    a latency-bound chain of small kernels, 16 SMs for most of its 1.2 ms).  Run one after the other the chip
+    idles through stage 2; here stage 1 of pass i+1 is queued on stream A while stage 2 of pass i runs on the
+    (higher-priority) stream B, so the eigensolve hides behind the next pass's counting.  Results are
+    identical to ``featurise`` (same kernels, same order within a pass); the optimistic am_clr tests are read
+    back when a pass retires and the rare failing pass is redone by ``featurise``."""
+
+    def __init__(self, device, k: int = 5, method: str = "am_clr", n_components: int = 50, group=None,
+                 distributed: bool = False, depth: int = 2, keep: bool = False):
+        import torch
+
+        self.dev = L.require_cuda(device)
+        self.k, self.method, self.P = k, method, n_components
+        self.group, self.distributed, self.depth, self.keep = group, distributed, max(1, depth), keep
+        lo, hi = torch.cuda.Stream.priority_range()  # (lowest, highest): numerically hi <= lo
+        self.sA = torch.cuda.Stream(device=self.dev, priority=lo)
+        self.sB = torch.cuda.Stream(device=self.dev, priority=hi)
+        self.inflight = []
+        self.done = []
+
+    def submit(self, packed: PackedAssembly, marks=None):
+        import torch
+
+        mark = marks if marks is not None else (lambda name: None)
+        while len(self.inflight) >= self.depth:
+            self._retire()
+        with torch.cuda.device(self.dev):
+            cur = torch.cuda.current_stream(self.dev)
+            self.sA.wait_stream(cur)  # inputs produced on the caller's stream
+            with torch.cuda.stream(self.sA):
+                mark("start")
+                counts, present, row_sum = _dev.count_packed(packed, self.k)
+                mark("count")
+                st = _fit(packed, counts, (present, row_sum), self.method, None, None, self.group, self.distributed,
+                          mark, True)
+                evA = torch.cuda.Event()
+                evA.record(self.sA)
+            self.sB.wait_event(evA)
+            with torch.cuda.stream(self.sB):
+                res = _project(st, self.P, mark)
+                evB = torch.cuda.Event()
+                evB.record(self.sB)
+            self.inflight.append((packed, st, res, evB, row_sum, present))
+
+    def _retire(self):
+        import torch
+
+        packed, st, res, evB, row_sum, present = self.inflight.pop(0)
+        evB.synchronize()
+        D = st["counts"].shape[1]
+        flags = res["stats"].cpu().numpy()
+        cols_ok, rows_ok = bool((flags[:D] > 0).all()), bool(flags[D] == 0)
+        n_total = float(res["n_total"].item()) if self.distributed else float(packed.n_contigs)
+        if n_total > 0 and not (cols_ok and rows_ok):
+            # rare: redo this pass on the general path (row / column gathers, or the clr / ilr error)
+            with torch.cuda.device(self.dev):
+                res = featurise(packed, self.k, self.method, self.P, self.group, self.distributed, keep=self.keep)
+        else:
+            res.pop("stats")
+            res.pop("n_total")
+            X = res.pop("normalized")
+            if self.keep:
+                res.update(counts=st["counts"], normalized=X, col_present=present, row_sum=row_sum)
+        self.done.append(res)
+
+    def drain(self):
+        """Wait for everything submitted; returns the results in submission order."""
+        while self.inflight:
+            self._retire()
+        out, self.done = self.done, []
         return out
 
 

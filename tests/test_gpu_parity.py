@@ -711,6 +711,27 @@ def test_featurise_full_size_properties(torch_cuda, case):
     assert float(resid) <= 1e-9 * float(ev[0])
 
 
+def test_feature_stream_equals_serial_featurise(torch_cuda):
+    """Throughput mode (two passes in flight on two streams) returns exactly what the serial pass returns,
+    for every submitted assembly, including one whose optimistic am_clr assumption fails (tiny contigs ->
+    all-NA rows -> that pass is redone on the general path)."""
+    from autometa_b200 import assembly as A, pipeline, synth
+
+    asms = [synth.make_assembly(5200, 5200 * 3400, seed=31), synth.make_assembly(5300, 5300 * 3300, seed=32, tiny=True),
+            synth.make_assembly(5400, 5400 * 3200, seed=33), synth.make_assembly(5200, 5200 * 3400, seed=31)]
+    packed = [A.pack_to_device(a, device="cuda:0", on_device=True) for a in asms]
+    fs = pipeline.FeatureStream("cuda:0", 5, "am_clr", 50, depth=2, keep=True)
+    for p in packed:
+        fs.submit(p)
+    got = fs.drain()
+    assert len(got) == len(packed)
+    for p, g in zip(packed, got):
+        ref = pipeline.featurise(p, 5, "am_clr", 50)
+        for key in ("counts", "normalized", "scores", "explained_variance", "explained_variance_ratio", "components",
+                    "mean"):
+            assert torch_cuda.equal(g[key], ref[key]), key
+
+
 # ----------------------------------------------------------------------------- embed() through its own call site
 def test_embed_pca_stage_matches_reference_embed_call(torch_cuda, golden_pca, tmp_path, monkeypatch):
     """The reference's embed() was run (tests/golden/make_golden.py) with a stub ``tsne.bh_sne`` that returns
