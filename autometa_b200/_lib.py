@@ -79,6 +79,7 @@ _SIGS = {
     "am_count_flags": (C.c_int, [_p, _i32, _p, _i64, _p, _p]),
     "am_stats_pack": (C.c_int, [_p, _i32, _p, _i64, _p, _p]),
     "am_gram_recenter": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p]),
+    "am_table_stats": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p]),
     "am_gram_work_bytes": (_i64, [_i32]),
     "am_gram": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
     "am_eigh_work_bytes": (_i64, [_i32]),

@@ -249,7 +249,8 @@ def pca_device(Xd, n_components: int, group=None) -> Dict[str, Any]:
         dist.all_reduce(n_t, group=group if group is not True else None)
     n = n_t  # stays on device: no host sync in the fit
     mu = cs / n
-    # tcgen05 int8 digit-plane product (exact integer accumulation); the planes are reused by the projection
+    # tcgen05 int8 digit-plane product (int32 accumulation is exact; digit pairs of weight >= 7 are dropped:
+    # <= 2^-48 of (column range)^2 per term, on top of the 2^-46 quantisation); the planes are reused by the projection
     e, sc = _dev.plane_scales(mu, cm)
     planes = _dev.quantize_planes(Xd, mu, sc)
     G = _dev.gram_planes(planes, n_local, D, e)

@@ -377,14 +377,10 @@ tridiag_reg_kernel(const double *__restrict__ A, int n_, int np_, int RL_, TriOu
   double2 *inbox = reinterpret_cast<double2 *>(xs + 2 * np);  // 2 x np  {y_i, A[i][k+1]}
   double *red = reinterpret_cast<double *>(inbox + 2 * np);   // 4 x TW rotating reduction slots
   double *sigp = red + 4 * TW;                // 2 x TW   per-warp partials of sigma (layout shared with the other kernel)
-  // per-warp partials of v_{k-1}.x_k and w_{k-1}.x_k (2 x RAW each): the mat-vec of step k runs on the matrix
-  // WITHOUT the pending rank-2 update and is corrected by  - v_i (w.x) - w_i (v.x)
-  __shared__ double s_dvx[2 * RAW], s_dwx[2 * RAW];
   __shared__ __align__(8) unsigned long long s_mbar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t mbar0 = (uint32_t)__cvta_generic_to_shared(&s_mbar[0]);
   const uint32_t inbox_s = (uint32_t)__cvta_generic_to_shared(inbox);
-  if (tid < 2 * RAW) { s_dvx[tid] = 0.0; s_dwx[tid] = 0.0; }
   
   for (int lr = 0; lr < RL; ++lr) {
     const int i = c + TC * lr;
@@ -454,10 +450,7 @@ long long tprev = 0;
     if (tid == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                    ::"r"(mbar0 + 8u * cur), "r"((uint32_t)(n - k - 1) * 16u) : "memory");
-    // ---- B. pass over own rows >= k, matrix in registers.  B1 (on the critical path): y = A_old x_k with the
-    // matrix as it stands (one FMA per element), corrected for the pending update (k-1) through the two
-    // dot products formed with x_k in step k-1:  (A_old - v w^T - w v^T) x = A_old x - v (w.x) - w (v.x); rows
-    // are sent at once.  B2 (while the all-gather is in flight): the pending update itself, two FMAs per element.
+    // ---- B. fused pass over own rows >= k, matrix in registers: pending update (k-1), y = A x_k
     {
       const int kb = k >> 5, jb1 = (k + 1) >> 5, l1 = (k + 1) & 31;
       bool act[RR];
@@ -475,38 +468,39 @@ long long tprev = 0;
         any |= act[r];
       }
       if (any) {
-        double dvx = 0.0, dwx = 0.0;
-#pragma unroll
-        for (int w = 0; w < RAW; ++w) { dvx += s_dvx[cur * RAW + w]; dwx += s_dwx[cur * RAW + w]; }
-        const double wp1 = wprev[k + 1], vp1 = vprev[k + 1];
-        double acc2[RR];
-#pragma unroll
-        for (int r = 0; r < RR; ++r) acc2[r] = 0.0;
-        // column blocks in groups of JG: one (warp-uniform) branch per group; two accumulators per row halve
-        // the dependent fp64 chain
+        // column blocks in groups of JG: one (warp-uniform) branch per group, so that the loads and the
+        // 3-deep fp64 chains of JG x RR elements are scheduled together (a branch per block serialises
+        // load latency + chain latency 16 times per step)
 #pragma unroll
         for (int g = 0; g < NB / JG; ++g) {
           if (JG * g + JG - 1 >= kb && 32 * JG * g < np) {
-            double xj[JG];
+            double vpj[JG], wpj[JG], xj[JG];
 #pragma unroll
             for (int q = 0; q < JG; ++q) {
               const int j = 32 * (JG * g + q) + lane;
-              xj[q] = (j < np) ? xk[j] : 0.0;
+              const bool ok = j < np;
+              vpj[q] = ok ? vprev[j] : 0.0;
+              wpj[q] = ok ? wprev[j] : 0.0;
+              xj[q] = ok ? xk[j] : 0.0;
             }
 #pragma unroll
             for (int q = 0; q < JG; ++q) {
               const int jj = JG * g + q;
 #pragma unroll
               for (int r = 0; r < RR; ++r) {
-                if (q & 1) acc2[r] = fma(am[r][jj], xj[q], acc2[r]);
-                else acc[r] = fma(am[r][jj], xj[q], acc[r]);
+                if (act[r]) {
+                  double a = am[r][jj];
+                  a = fma(-vpi[r], wpj[q], a);
+                  a = fma(-wpi[r], vpj[q], a);
+                  am[r][jj] = a;
+                  acc[r] = fma(a, xj[q], acc[r]);
+                }
               }
             }
           }
         }
-#pragma unroll
-        for (int r = 0; r < RR; ++r) acc[r] += acc2[r];
-        // pre-update A[i][k+1] lives in column block jb1 of lane l1
+        // post-update A[i][k+1] lives in column block jb1 of lane l1 (picked up outside the update code:
+        // a test per block inside it splits the block into branches)
 #define AM_PICK(JJ) case JJ: a1v[0] = am[0][JJ]; a1v[1] = am[1][JJ]; a1v[2] = am[2][JJ]; a1v[3] = am[3][JJ]; break;
         switch (jb1) {
           AM_PICK(0) AM_PICK(1) AM_PICK(2) AM_PICK(3) AM_PICK(4) AM_PICK(5) AM_PICK(6) AM_PICK(7)
@@ -525,41 +519,10 @@ long long tprev = 0;
         const uint32_t rbar = mapa_u32(mbar0 + 8u * cur, (uint32_t)(lane & (TC - 1)));
 #pragma unroll
         for (int r = 0; r < RR; ++r) {
-          double a1 = __shfl_sync(FULL, a1v[r], l1);
-          a1 = fma(-vpi[r], wp1, a1);
-          a1 = fma(-wpi[r], vp1, a1);          // post-update A[i][k+1]
-          double y = fma(-vpi[r], dwx, acc[r]);
-          y = fma(-wpi[r], dvx, y);            // (A_old - v w^T - w v^T) x_k, row i
+          const double a1 = __shfl_sync(FULL, a1v[r], l1);  // post-update A[i][k+1]
           const int i = c + TC * (warp + RW * r);
           if (act[r] && i >= k + 1 && lane < TC)
-            st_async_f64x2(mapa_u32(inbox_s + (uint32_t)(cur * np + i) * 16u, lane), y, a1, rbar);
-        }
-        // B2: the pending rank-2 update, off the critical path
-#pragma unroll
-        for (int g = 0; g < NB / JG; ++g) {
-          if (JG * g + JG - 1 >= kb && 32 * JG * g < np) {
-            double vpj[JG], wpj[JG];
-#pragma unroll
-            for (int q = 0; q < JG; ++q) {
-              const int j = 32 * (JG * g + q) + lane;
-              const bool ok = j < np;
-              vpj[q] = ok ? vprev[j] : 0.0;
-              wpj[q] = ok ? wprev[j] : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < JG; ++q) {
-              const int jj = JG * g + q;
-#pragma unroll
-              for (int r = 0; r < RR; ++r) {
-                if (act[r]) {
-                  double a = am[r][jj];
-                  a = fma(-vpi[r], wpj[q], a);
-                  a = fma(-wpi[r], vpj[q], a);
-                  am[r][jj] = a;
-                }
-              }
-            }
-          }
+            st_async_f64x2(mapa_u32(inbox_s + (uint32_t)(cur * np + i) * 16u, lane), acc[r], a1, rbar);
         }
       }
     }
@@ -628,7 +591,7 @@ long long tprev = 0;
       const double2 gk = ib[k + 1];
       const double wk1 = ts * fma(-beta, gk.y, gk.x) - Kc;  // w_k[k+1]  (v_k[k+1] = 1)
       double *xn = xs + prv * np;
-      double sp = 0.0, pvx = 0.0, pwx = 0.0;
+      double sp = 0.0;
 #pragma unroll
       for (int m = 0; m < RNE; ++m) {
         const int i = tid + RAT * m;
@@ -638,16 +601,9 @@ long long tprev = 0;
         x[m] = (i >= k + 2 && i < n) ? av[m] - v[m] * wk1 - w : 0.0;
         if (i < np) xn[i] = x[m];
         if (i >= k + 3) sp = fma(x[m], x[m], sp);
-        pvx = fma(v[m], x[m], pvx);
-        pwx = fma(w, x[m], pwx);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        sp += __shfl_xor_sync(FULL, sp, o);
-        pvx += __shfl_xor_sync(FULL, pvx, o);
-        pwx += __shfl_xor_sync(FULL, pwx, o);
-      }
-      if (lane == 0) { sigp[prv * RAW + warp] = sp; s_dvx[prv * RAW + warp] = pvx; s_dwx[prv * RAW + warp] = pwx; }
+      sp = warp_sum(sp);
+      if (lane == 0) sigp[prv * RAW + warp] = sp;
     }
     __syncthreads();
     AM_TICK(tC);

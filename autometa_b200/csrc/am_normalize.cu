@@ -369,17 +369,32 @@ normalize512_planes_kernel(const int32_t *__restrict__ counts, int64_t n_out,
       const size_t plane_words = (size_t)n_out * (D / 4);
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        uint32_t word[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        // balanced base-256 digits without a carry chain: with B = 0x80 in each of the six digit bytes, the
+        // plain bytes b_j of q + B satisfy q = sum (b_j - 128) 256^j, and b_j - 128 as an int8 is b_j ^ 0x80.
+        // (|q| <= 2^46 < B keeps q + B inside [0, 256^6).)  Same digits as digits6(), 3 instructions instead
+        // of ~30; the 4 x 6 bytes of a lane's four columns are then transposed into the six plane words
+        // with byte permutes.
+        uint32_t lo[4], hi[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int i = 4 * m + e;
           double v = (l[i] - cen[i * 32 + lane]) * scl[i * 32 + lane];
           v = fmin(fmax(v, -lim), lim);
-          int a[6];
-          digits6(v, a);
-#pragma unroll
-          for (int s = 0; s < 6; ++s) word[s] |= (uint32_t)(a[s] & 255) << (8 * e);
+          const unsigned long long B = 0x0000808080808080ull;
+          const unsigned long long x = ((unsigned long long)__double2ll_rn(v) + B) ^ B;
+          lo[e] = (uint32_t)x;
+          hi[e] = (uint32_t)(x >> 32);
         }
+        const uint32_t t0 = __byte_perm(lo[0], lo[1], 0x5140), t1 = __byte_perm(lo[2], lo[3], 0x5140);
+        const uint32_t t2 = __byte_perm(lo[0], lo[1], 0x7362), t3 = __byte_perm(lo[2], lo[3], 0x7362);
+        const uint32_t t4 = __byte_perm(hi[0], hi[1], 0x5140), t5 = __byte_perm(hi[2], hi[3], 0x5140);
+        uint32_t word[6];
+        word[5] = __byte_perm(t0, t1, 0x5410);  // least significant digit
+        word[4] = __byte_perm(t0, t1, 0x7632);
+        word[3] = __byte_perm(t2, t3, 0x5410);
+        word[2] = __byte_perm(t2, t3, 0x7632);
+        word[1] = __byte_perm(t4, t5, 0x5410);
+        word[0] = __byte_perm(t4, t5, 0x7632);  // most significant digit
 #pragma unroll
         for (int s = 0; s < 6; ++s) __stcs(pl + (size_t)s * plane_words + 32 * m, word[s]);
       }

@@ -463,6 +463,41 @@ extern "C" int am_project(const double *d_X, int64_t n_rows, int D, const double
   return AM_OK;
 }
 
+// Column presence and row sums of a ROW SUBSET of a count table (one partition of the large-data-mode driver,
+// large_data_mode.py:454-470: counts.loc[counts.index.isin(rank_df.index)]): what am_count_kmers reports for a
+// whole assembly, for tables that arrive as TSV.  One warp per row; presence is OR-ed per lane over the rows
+// a warp visits and written once per warp.
+__global__ void __launch_bounds__(256)
+table_stats_kernel(const int32_t *__restrict__ counts, const int64_t *__restrict__ row_index, int64_t n, int D,
+                   int32_t *__restrict__ present, int32_t *__restrict__ row_sum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int c0 = 0; c0 < D; c0 += 32 * 32) {  // 32 columns per lane per sweep (bit j of `seen` <-> column c0 + 32 j + lane)
+    uint32_t seen = 0u;
+    for (int64_t r = warp; r < n; r += n_warps) {
+      const int32_t *x = counts + (row_index ? row_index[r] : r) * (int64_t)D;
+      int sum = 0;
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        const int c = c0 + 32 * j + lane;
+        const int v = c < D ? __ldg(x + c) : 0;
+        sum += v;
+        seen |= (uint32_t)(v > 0) << j;
+      }
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) {
+        if (c0 == 0) row_sum[r] = sum;
+        else row_sum[r] += sum;
+      }
+    }
+    for (int j = 0; j < 32; ++j) {
+      const int c = c0 + 32 * j + lane;
+      if (c < D && ((seen >> j) & 1u)) present[c] = 1;
+    }
+  }
+}
+
 extern "C" int am_stats_pack(const int32_t *d_col_present, int ncols, const int32_t *d_row_sum, int64_t n_contigs,
                              double *d_out, void *stream) {
   if (!d_col_present || !d_out || ncols < 1 || n_contigs < 0 || (n_contigs > 0 && !d_row_sum))
@@ -483,5 +518,18 @@ extern "C" int am_gram_recenter(double *d_G, int D, const double *d_colsum, cons
   gram_recenter_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 1024), 256, 0, (cudaStream_t)stream>>>(
       d_G, D, d_colsum, d_c_old, d_c_new, d_n);
   AM_LAUNCHED("gram_recenter_kernel");
+  return AM_OK;
+}
+
+extern "C" int am_table_stats(const int32_t *d_counts, const int64_t *d_row_index, int64_t n_rows, int D,
+                              int32_t *d_col_present, int32_t *d_row_sum, void *stream) {
+  if (D < 1 || n_rows < 0) return am::fail(AM_EINVAL, "am_table_stats: bad shape");
+  if (!d_col_present || (n_rows > 0 && (!d_counts || !d_row_sum))) return am::fail(AM_EINVAL, "am_table_stats: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  AM_CUDA(cudaMemsetAsync(d_col_present, 0, sizeof(int32_t) * (size_t)D, st));
+  if (n_rows == 0) return AM_OK;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_rows + 7) / 8, (int64_t)am::num_sms() * 8));
+  table_stats_kernel<<<grid, 256, 0, st>>>(d_counts, d_row_index, n_rows, D, d_col_present, d_row_sum);
+  AM_LAUNCHED("table_stats_kernel");
   return AM_OK;
 }

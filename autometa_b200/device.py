@@ -93,7 +93,9 @@ _work_cache: Dict[Tuple[str, int, int], "torch.Tensor"] = {}
 def _work(dev, nbytes: int, tag: str):
     import torch
 
-    key = (tag, dev.index, 0)
+    # scratch is per (kernel family, device, stream): passes running on different streams (pipeline.FeatureStream,
+    # per-partition streams of the large-data-mode driver) must not share partial-result buffers
+    key = (tag, dev.index, torch.cuda.current_stream(dev).cuda_stream)
     t = _work_cache.get(key)
     if t is None or t.numel() < nbytes:
         t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)

@@ -74,7 +74,7 @@ def _bound_for(packed, method: str, D: int) -> float:
     return bound
 
 
-def _fit(packed, counts, stats, method, row_index, col_index, group, distributed, mark, overlap=True):
+def _fit(packed, counts, stats, method, row_index, col_index, group, distributed, mark, overlap=False):
     """Stage 1 — normalise -> digit planes -> Gram -> (all-reduce) -> covariance, for the given row/column
     selection (device only, no host sync).  Everything whose work grows with the assembly.
 
@@ -176,15 +176,33 @@ def _fit(packed, counts, stats, method, row_index, col_index, group, distributed
                 row_index=row_index, col_index=col_index, stats=tail, n_total=n_t, R=R, counts=counts)
 
 
-def _project(st, n_components, mark):
-    """Stage 2 — top-P eigenpairs of the covariance (N-independent, latency-bound) and the scores."""
+def _project(st, n_components, mark, eig_owner=None, eig_group=None):
+    """Stage 2 — top-P eigenpairs of the covariance (N-independent, latency-bound) and the scores.
+
+    ``eig_owner`` (a rank of ``eig_group``): only that rank solves the eigenproblem and broadcasts
+    ``[eigenvalues | components | trace]`` (P + P D + 1 doubles, 0.2 MB); the others receive.  The covariance is
+    bit-identical on every rank after the all-reduce, so this is the same result as the replicated solve
+    — ``FeatureStream`` uses it to spread the eigensolves of the passes in flight over the GPUs."""
     import torch
 
     C, mu, planes, e, center, X = st["C"], st["mu"], st["planes"], st["e"], st["center"], st["X"]
     n_out, Dout, side = st["n_out"], st["Dout"], st["side"]
     dev = C.device
     P = min(n_components, Dout)
-    evals, comps, total = _dev.eigh_topk(C, P)
+    if eig_owner is None:
+        evals, comps, total = _dev.eigh_topk(C, P)
+    else:
+        import torch.distributed as dist
+
+        buf = torch.empty(P + P * Dout + 1, dtype=torch.float64, device=dev)
+        if dist.get_rank(eig_group) == eig_owner:
+            evals, comps, total = _dev.eigh_topk(C, P)
+            buf[:P] = evals
+            buf[P : P + P * Dout] = comps.reshape(-1)
+            buf[P + P * Dout :] = total.reshape(-1)
+        dist.broadcast(buf, src=dist.get_global_rank(eig_group, eig_owner) if eig_group is not None else eig_owner,
+                       group=eig_group)
+        evals, comps, total = buf[:P], buf[P : P + P * Dout].view(P, Dout), buf[P + P * Dout :]
     mark("eigh")
     evals = torch.clamp(evals, min=0.0)
     if n_out == 0:
@@ -205,14 +223,14 @@ def _project(st, n_components, mark):
 
 
 def _fit_project(packed, counts, stats, method, n_components, row_index, col_index, group, distributed, mark,
-                 overlap=True):
+                 overlap=False):
     return _project(_fit(packed, counts, stats, method, row_index, col_index, group, distributed, mark, overlap),
                     n_components, mark)
 
 
 def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_components: int = 50,
               group=None, distributed: bool = False, keep: bool = True, marks=None,
-              overlap: bool = True) -> Dict[str, Any]:
+              overlap: bool = False) -> Dict[str, Any]:
     """counts, normalised matrix and PCA scores of this rank's contig shard.
 
     am_clr's global column drop and all-NA row drop (kmers.py:369) are handled optimistically:
@@ -221,6 +239,11 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
     kernel has been queued, and the rare other case re-runs with explicit row/column gathers.
     With several GPUs the tests travel inside the Gram all-reduce, so every rank reads the same
     (global) answer and takes the same branch.
+
+    ``overlap=True`` writes the fp64 normalised rows from a second launch on a side stream, behind the
+    Gram, instead of from the pass that writes the digit planes.  Measured on B200 (profiles/r2c): the
+    planes-only pass is ALU-bound (0.29 ms against 0.33 ms fused), and the row writer then shares SMs with
+    the latency-critical eigensolve (+0.2 ms) — a net loss, so it is off by default.
     """
     import torch
 
@@ -271,12 +294,27 @@ class FeatureStream:
     back when a pass retires and the rare failing pass is redone by ``featurise``."""
 
     def __init__(self, device, k: int = 5, method: str = "am_clr", n_components: int = 50, group=None,
-                 distributed: bool = False, depth: int = 2, keep: bool = False):
+                 distributed: bool = False, depth: int = 2, keep: bool = False, spread_eigh: bool = True):
+        """``spread_eigh`` (several GPUs): the eigensolve of pass i is done by rank i mod N only and broadcast,
+        instead of being replicated on every rank — with N passes in flight each GPU solves one eigenproblem
+        per N passes, which removes the replicated, N-independent 1.2 ms from every rank's critical path
+        (the Amdahl term of strong scaling).  The broadcasts use their own communicator so that they never
+        queue behind the next pass's Gram all-reduce."""
         import torch
 
         self.dev = L.require_cuda(device)
         self.k, self.method, self.P = k, method, n_components
         self.group, self.distributed, self.depth, self.keep = group, distributed, max(1, depth), keep
+        self.n_submitted = 0
+        self.eig_group = None
+        self.world = 1
+        if distributed and spread_eigh:
+            import torch.distributed as dist
+
+            self.world = dist.get_world_size(group)
+            if self.world > 1:
+                ranks = list(range(dist.get_world_size())) if group is None else dist.get_process_group_ranks(group)
+                self.eig_group = dist.new_group(ranks=ranks)  # collective call: every rank constructs the stream
         lo, hi = torch.cuda.Stream.priority_range()  # (lowest, highest): numerically hi <= lo
         self.sA = torch.cuda.Stream(device=self.dev, priority=lo)
         self.sB = torch.cuda.Stream(device=self.dev, priority=hi)
@@ -297,12 +335,14 @@ class FeatureStream:
                 counts, present, row_sum = _dev.count_packed(packed, self.k)
                 mark("count")
                 st = _fit(packed, counts, (present, row_sum), self.method, None, None, self.group, self.distributed,
-                          mark, True)
+                          mark, False)
                 evA = torch.cuda.Event()
                 evA.record(self.sA)
             self.sB.wait_event(evA)
+            owner = (self.n_submitted % self.world) if self.eig_group is not None else None
+            self.n_submitted += 1
             with torch.cuda.stream(self.sB):
-                res = _project(st, self.P, mark)
+                res = _project(st, self.P, mark, owner, self.eig_group)
                 evB = torch.cuda.Event()
                 evB.record(self.sB)
             self.inflight.append((packed, st, res, evB, row_sum, present))
@@ -317,8 +357,10 @@ class FeatureStream:
         cols_ok, rows_ok = bool((flags[:D] > 0).all()), bool(flags[D] == 0)
         n_total = float(res["n_total"].item()) if self.distributed else float(packed.n_contigs)
         if n_total > 0 and not (cols_ok and rows_ok):
-            # rare: redo this pass on the general path (row / column gathers, or the clr / ilr error)
+            # rare: redo this pass on the general path (row / column gathers, or the clr / ilr error).  The
+            # library's scratch buffers are shared per device: let the passes in flight finish first
             with torch.cuda.device(self.dev):
+                torch.cuda.synchronize(self.dev)
                 res = featurise(packed, self.k, self.method, self.P, self.group, self.distributed, keep=self.keep)
         else:
             res.pop("stats")

@@ -367,6 +367,40 @@ def time_steps(torch, dist, pipeline, L, packed, norm, steps, warmup, distribute
     return ms_per_step, stage_ms, launches, clocks
 
 
+def time_pipelined(torch, dist, pipeline, L, packed, norm, steps, warmup, distributed, dev, depth):
+    """Throughput mode (pipeline.FeatureStream): `depth` steps in flight, stage 1 (count -> normalise -> Gram) of
+    step i+1 on one stream while stage 2 (eigensolve + projection) of step i runs on another; with several GPUs the
+    eigensolve of step i is done by rank i mod N and broadcast.  Every step's work is complete inside the timed
+    region (drain() before the closing event); barrier + synchronize on both sides; max over ranks."""
+    fs = pipeline.FeatureStream(dev, K, norm, NCOMP, distributed=distributed, depth=depth)
+    for _ in range(warmup):
+        fs.submit(packed)
+    fs.drain()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = L.launch_count()
+    t0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        fs.submit(packed)
+    fs.drain()
+    ev1.record()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    launches = L.launch_count() - l0
+    tp = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    del fs
+    return float(tp.item()) / steps, launches, t0, t1
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -386,8 +420,8 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="N>1: skip the extra weak-scaling measurement")
     ap.add_argument("--norm", default=None, choices=["am_clr", "clr", "ilr"])
-    ap.add_argument("--pipeline-depth", type=int, default=2,
-                    help="steps in flight for the `pipelined` throughput figure (1 = skip it)")
+    ap.add_argument("--pipeline-depth", type=int, default=0,
+                    help="steps in flight in the timed region (0 = max(2, N + 1); 1 = strictly one step at a time)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -437,9 +471,21 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.5)
-    ms_per_step, stage_ms, launches, clocks = time_steps(torch, dist, pipeline, L, packed, args.norm, args.steps,
-                                                         args.warmup, distributed, dev, sampler, rank)
+    t_load = time.time()
+    ms_serial, stage_ms, launches_serial, _ = time_steps(torch, dist, pipeline, L, packed, args.norm, args.steps,
+                                                         args.warmup, distributed, dev)
+    depth = args.pipeline_depth if args.pipeline_depth > 0 else max(2, world + 1)
+    if depth > 1:
+        ms_per_step, launches, tt0, tt1 = time_pipelined(torch, dist, pipeline, L, packed, args.norm, args.steps,
+                                                         args.warmup, distributed, dev, depth)
+    else:
+        ms_per_step, launches, tt0, tt1 = ms_serial, launches_serial, t_load, time.time()
+    clocks = sampler.stop(tt0, tt1, t_load) if rank == 0 else None
     value = job_bp / (ms_per_step * 1e-3) / 1e9
+    serial = {"value": job_bp / (ms_serial * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_serial,
+              "gpu_launches": int(launches_serial),
+              "what": "one step at a time on one stream (the latency of a single featurise call); the per-stage "
+                      "times under `stages` come from this run"}
 
     # the same steps with a 512 MB buffer rewritten before each one (L2 = 126 MB): states once what the
     # missing flush is worth; the headline keeps back-to-back steps (inputs and outputs exceed L2)
@@ -449,49 +495,20 @@ def main():
         ms_f, _, _, _ = time_steps(torch, dist, pipeline, L, packed, args.norm, max(3, min(args.steps, 5)), 1,
                                    distributed, dev, flush=fl)
         del fl
-        flush_check = {"ms_per_step_with_l2_flush": round(ms_f, 4), "ms_per_step": round(ms_per_step, 4)}
-
-    # ---- throughput mode: the same K steps with two in flight (stage 1 of step i+1 on one stream while the
-    # eigensolve + projection of step i run on another); every step's work is complete inside the timed region
-    pipelined = None
-    if args.pipeline_depth > 1:
-        fs = pipeline.FeatureStream(dev, K, args.norm, NCOMP, distributed=distributed, depth=args.pipeline_depth)
-        for _ in range(args.warmup):
-            fs.submit(packed)
-        fs.drain()
-        torch.cuda.synchronize()
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
-        l0 = L.launch_count()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(args.steps):
-            fs.submit(packed)
-        fs.drain()
-        ev1.record()
-        torch.cuda.synchronize()
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
-        tp = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-        if distributed:
-            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-        ms_p = float(tp.item()) / args.steps
-        pipelined = {"value": job_bp / (ms_p * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_p, "depth": args.pipeline_depth,
-                     "steps": args.steps, "gpu_launches": int(L.launch_count() - l0),
-                     "how": "pipeline.FeatureStream: count/normalise/Gram of step i+1 on stream A while the eigensolve + "
-                            "projection of step i run on stream B; same kernels and results as the serial pass"}
-        del fs
+        flush_check = {"serial_ms_per_step_with_l2_flush": round(ms_f, 4), "serial_ms_per_step": round(ms_serial, 4)}
 
     # ---- N>1: the weak-scaling figure next to the strong one (every rank its own full-size assembly)
     weak = None
     if distributed and scaling == "strong" and not c5 and not args.no_weak:
         asm_w = make_shard(args, synth, DD, world, rank, "weak")
         packed_w = assembly.pack_to_device(asm_w, device=dev, on_device=True)
-        ms_w, stage_w, _, _ = time_steps(torch, dist, pipeline, L, packed_w, args.norm, max(3, min(args.steps, 10)), 3,
-                                         distributed, dev)
+        ws = max(3, min(args.steps, 10))
+        ms_ws, stage_w, _, _ = time_steps(torch, dist, pipeline, L, packed_w, args.norm, ws, 3, distributed, dev)
+        ms_w = ms_ws
+        if depth > 1:
+            ms_w, _, _, _ = time_pipelined(torch, dist, pipeline, L, packed_w, args.norm, ws, 3, distributed, dev, depth)
         weak = {"value": world * asm_w.total_bp / (ms_w * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_w,
+                "serial_ms_per_step": ms_ws,
                 "per_gpu": f"{asm_w.n_contigs} contigs / {asm_w.total_bp / 1e9:.3f} Gbp",
                 "stages_ms": {k2: round(v, 4) for k2, v in stage_w.items()}}
         del packed_w, asm_w
@@ -596,6 +613,7 @@ def main():
             "algorithmic_GB": round(comp_bytes / 1e9, 3),
             "achieved_GBps": round(comp_bytes / (ms_per_step * 1e-3) / 1e9, 1),
             "frac": round(comp_bytes / (ms_per_step * 1e-3) / 1e9 / hbm, 4),
+            "serial_frac": round(comp_bytes / (ms_serial * 1e-3) / 1e9 / hbm, 4),
         }
         cpu = None
         if not args.no_cpu_baseline and world == 1 and not c5:  # reported once, on rank 0 at N=1
@@ -615,7 +633,12 @@ def main():
                          f"{job_bp / 1e9:.3f} Gbp",
                 "k": K, "norm": args.norm, "pca_dimensions": NCOMP,
                 "parallelism": f"contigs sharded by bp over {world} GPU(s); ONE NCCL all-reduce per step "
-                               "([Gram | column sums | row count | column presence | all-NA rows], 2.0 MiB)",
+                               "([Gram | column sums | row count | column presence | all-NA rows], 2.0 MiB)"
+                               + ("; the eigensolve of step i runs on rank i mod N and is broadcast (0.2 MB)"
+                                  if (world > 1 and depth > 1) else ""),
+                "pipelining": (f"{depth} steps in flight (pipeline.FeatureStream): count/normalise/Gram of step i+1 on one "
+                               "stream while the eigensolve + projection of step i run on another; all K steps complete "
+                               "inside the timed region; `serial` = one step at a time") if depth > 1 else "none",
                 "l2": "inputs larger than L2 (0.25 GB codes, 0.41 GB counts, 0.82 GB features per step at N=1); no flush "
                       "in the headline, see `l2_flush_check`",
             },
@@ -624,7 +647,7 @@ def main():
             "n_independent_note": "top-50 eigenpairs of the 512x512 covariance (tridiagonalisation + bisection + inverse "
                                   "iteration + back-transformation): the same time whatever the assembly size, replicated "
                                   "on every rank; the longest stage of the step, not a bandwidth-bound one",
-            "l2_flush_check": flush_check, "pipelined": pipelined, "weak": weak,
+            "l2_flush_check": flush_check, "serial": serial, "weak": weak,
             "cpu_baseline": cpu, "e2e": e2e, "sweep": sweep,
             "gpu_launches": int(launches), "clocks": clocks,
         }

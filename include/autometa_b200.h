@@ -242,6 +242,11 @@ int am_stats_pack(const int32_t *d_col_present, int ncols, const int32_t *d_row_
  * (sklearn's own form is the Gram about the origin, _pca.py:604-610). */
 int am_gram_recenter(double *d_G, int D, const double *d_colsum, const double *d_c_old,
                      const double *d_c_new, const double *d_n, void *stream);
+/* Column presence (0/1) and row sums of the rows d_row_index[0..n_rows) (NULL = all rows) of an int32
+ * count table [. x D]: the two statistics am_count_kmers reports for an assembly, for a partition of a
+ * table that arrived as TSV (large_data_mode.py:454-470 subsets counts per taxon before normalising). */
+int am_table_stats(const int32_t *d_counts, const int64_t *d_row_index, int64_t n_rows, int D,
+                   int32_t *d_col_present, int32_t *d_row_sum, void *stream);
 int64_t am_gram_work_bytes(int D);
 int am_gram(const double *d_X, int64_t n_rows, int D, const double *d_mu,
             double *d_G, void *d_work, void *stream);

@@ -19,7 +19,7 @@ print("eigh_topk %.3f ms" % (e0.elapsed_time(e1) / 10))
 al = lambda b: (b + 255) & ~255
 npad = (n + 31) & ~31
 off = al(n * npad * 8) + 3 * al(npad * 8) + al(128 * 8) + al(P * npad * 8)
-w = D._work_cache[("eigtop", 0, 0)]
+w = [v for k, v in D._work_cache.items() if k[0] == "eigtop"][0]
 dbg = w[off:off + 256].view(torch.int64).cpu().numpy()
 tot = dbg[:4].sum() + dbg[4] + dbg[5]
 names = ["S scalars", "B update+matvec+send", "wait inbox", "C w/next column"]

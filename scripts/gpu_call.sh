@@ -11,7 +11,7 @@ import json
 try:
     d = json.load(open("$O/${TAG}_bench.json"))
     print("value", round(d["value"], 1), "ms", round(d["ms_per_step"], 4), "stages", {k: v["ms"] for k, v in d["stages"].items()})
-    print("pipelined", d.get("pipelined"))
+    print("serial", d.get("serial"))
     print("e2e", {k: d["e2e"][k] for k in ("value", "ms_per_step", "serial_latency_ms", "h2d_bytes_per_step")}, "ascii", {k: d["e2e"]["ascii"][k] for k in ("value", "ms_per_step")})
     print("flush", d.get("l2_flush_check"), "sweep", d["sweep"]["value"], d["sweep"].get("api"))
     print("cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"])
