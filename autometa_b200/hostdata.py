@@ -7,7 +7,7 @@ without loading the extension.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List
+from typing import List, Optional
 
 import numpy as np
 
@@ -19,6 +19,7 @@ class HostAssembly:
     ids: List[str]
     seq: np.ndarray  # uint8, all contigs concatenated (may carry slack at the end)
     offsets: np.ndarray  # int64 [N+1]
+    genome: Optional[np.ndarray] = None  # synthetic assemblies only: source genome of every contig
 
     @property
     def n_contigs(self) -> int:
@@ -34,4 +35,5 @@ class HostAssembly:
 
     def slice(self, lo: int, hi: int) -> "HostAssembly":
         """Contigs [lo, hi) as a view (offsets stay absolute into ``seq``)."""
-        return HostAssembly(self.ids[lo:hi], self.seq, self.offsets[lo : hi + 1])
+        return HostAssembly(self.ids[lo:hi], self.seq, self.offsets[lo : hi + 1],
+                            None if self.genome is None else self.genome[lo:hi])

@@ -95,7 +95,8 @@ def make_assembly(n_contigs: int, total_bp: int, seed: int, noise: bool = True, 
             pos += L
             offsets = np.append(offsets, pos)
             ids.append(f"NODE_tiny{k}_length_{L}_cov_1.000")
-    return HostAssembly(ids, seq, offsets)
+        genome = np.concatenate([genome, np.full(3, -1, dtype=genome.dtype)])
+    return HostAssembly(ids, seq, offsets, genome)
 
 
 def write_fasta(asm: HostAssembly, path: str, width: int = 60) -> None:

@@ -4,13 +4,20 @@
 ``df.to_csv(out, sep="\\t", index=True, header=True)`` and
 ``pd.read_csv(path, sep="\\t", index_col="contig")`` of the reference
 (autometa/common/kmers.py:116,328,431,704) with the multi-threaded C routines
-``am_tsv_*``: byte-identical files, identical frames.  Anything outside the fast
-path (mixed dtypes, quoted labels, compressed files ...) goes through pandas, so the
-result is the same either way.
+``am_tsv_*``: byte-identical files, identical frames.  ``.gz`` paths (the embedding
+caches of large-data mode, large_data_mode.py:104,112) take the same fast formatter /
+parser around a multi-member gzip stream compressed on all host threads (the decompressed
+bytes are what pandas writes; any gzip reader, pandas included, reads the file).  Anything
+outside the fast path (mixed dtypes, quoted labels, other compressions ...) goes through
+pandas, so the result is the same either way.
 """
 from __future__ import annotations
 
+import gzip
 import os
+import tempfile
+import zlib
+from concurrent.futures import ThreadPoolExecutor
 from typing import Optional, Sequence
 
 import numpy as np
@@ -61,10 +68,31 @@ def write_counts(path: str, ids: Sequence[str], names: Sequence[str], counts: np
                                    L.np_ptr(counts) if counts.size else None, _threads()))
 
 
+_GZ_CHUNK = 8 << 20
+
+
+def _gzip_members(raw: bytes, path: str, level: int = 6) -> None:
+    """Write ``raw`` as a gzip file made of independent members of _GZ_CHUNK input bytes each, compressed in
+    parallel (zlib releases the GIL).  Multi-member streams are standard gzip (RFC 1952 2.2)."""
+    chunks = [raw[i : i + _GZ_CHUNK] for i in range(0, len(raw), _GZ_CHUNK)] or [b""]
+
+    def one(c):
+        co = zlib.compressobj(level, zlib.DEFLATED, 31)  # wbits 31: gzip container
+        return co.compress(c) + co.flush()
+
+    with ThreadPoolExecutor(max_workers=min(len(chunks), _threads())) as pool:
+        parts = list(pool.map(one, chunks))
+    with open(path, "wb") as fh:
+        for part in parts:
+            fh.write(part)
+
+
 def write_frame(df: pd.DataFrame, path: str) -> None:
-    """``df.to_csv(path, sep="\\t", index=True, header=True)``; the fast writer when every column is float64."""
+    """``df.to_csv(path, sep="\t", index=True, header=True)``; the fast writer when every column is float64
+    (plain or ``.gz``)."""
+    spath = str(path) if isinstance(path, (str, os.PathLike)) else ""
     simple = (
-        isinstance(path, (str, os.PathLike)) and not str(path).endswith((".gz", ".bz2", ".zip", ".xz", ".zst"))
+        bool(spath) and not spath.endswith((".bz2", ".zip", ".xz", ".zst"))
         and df.index.nlevels == 1 and df.columns.nlevels == 1 and df.shape[1] > 0
         and all(dt == np.float64 for dt in df.dtypes)
         and (df.index.dtype == object or pd.api.types.is_string_dtype(df.index.dtype))
@@ -76,9 +104,22 @@ def write_frame(df: pd.DataFrame, path: str) -> None:
     values = np.ascontiguousarray(df.to_numpy(dtype=np.float64))
     blob, offsets = _labels_blob(df.index)
     hdr = _header(df.index.name, df.columns)
-    L.check(L.lib.am_tsv_write_f64(os.fsencode(str(path)), hdr, len(hdr), L.np_ptr(blob), L.np_ptr(offsets),
-                                   values.shape[0], values.shape[1], L.np_ptr(values) if values.size else None,
-                                   _threads()))
+    target = spath
+    tmp = None
+    if spath.endswith(".gz"):
+        fd, tmp = tempfile.mkstemp(suffix=".tsv", dir=os.path.dirname(os.path.abspath(spath)) or None)
+        os.close(fd)
+        target = tmp
+    try:
+        L.check(L.lib.am_tsv_write_f64(os.fsencode(target), hdr, len(hdr), L.np_ptr(blob), L.np_ptr(offsets),
+                                       values.shape[0], values.shape[1], L.np_ptr(values) if values.size else None,
+                                       _threads()))
+        if tmp is not None:
+            with open(tmp, "rb") as fh:
+                _gzip_members(fh.read(), spath)
+    finally:
+        if tmp is not None and os.path.exists(tmp):
+            os.remove(tmp)
 
 
 def _looks_numeric(label: str) -> bool:
@@ -90,16 +131,24 @@ def _looks_numeric(label: str) -> bool:
 
 
 def read_table(path: str, index_col: str = "contig") -> pd.DataFrame:
-    """``pd.read_csv(path, sep="\\t", index_col=index_col)`` for a table of numbers."""
-    fast = isinstance(path, (str, os.PathLike)) and not str(path).endswith((".gz", ".bz2", ".zip", ".xz", ".zst"))
-    df = _read_fast(str(path), index_col) if fast else None
+    """``pd.read_csv(path, sep="\t", index_col=index_col)`` for a table of numbers (plain or ``.gz``)."""
+    spath = str(path) if isinstance(path, (str, os.PathLike)) else ""
+    fast = bool(spath) and not spath.endswith((".bz2", ".zip", ".xz", ".zst"))
+    df = None
+    if fast:
+        if spath.endswith(".gz"):
+            with open(spath, "rb") as fh:
+                raw = gzip.decompress(fh.read())  # handles multi-member files
+            buf = np.frombuffer(raw, dtype=np.uint8)
+        else:
+            buf = np.fromfile(spath, dtype=np.uint8)
+        df = _read_fast(buf, index_col)
     if df is None:
         df = pd.read_csv(path, sep="\t", index_col=index_col)
     return df
 
 
-def _read_fast(path: str, index_col: str) -> Optional[pd.DataFrame]:
-    buf = np.fromfile(path, dtype=np.uint8)
+def _read_fast(buf: np.ndarray, index_col: str) -> Optional[pd.DataFrame]:
     if buf.size == 0:
         return None
     end = int(np.argmax(buf == 10)) if (buf == 10).any() else buf.size

@@ -9,6 +9,8 @@ Tolerances (BASELINE.json north_star / SURVEY.md §8d):
                     sklearn sign rule (|cos| >= 1 - 1e-9); scores within 1e-8 * max|score|
   DBSCAN            label vectors identical (min_samples=1: no border points exist)
 """
+import os
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -643,6 +645,93 @@ def test_taxon_guided_binning_matches_reference_golden(torch_cuda, golden_binnin
         R.taxon_guided_binning(tax.copy(), markers.iloc[:0], method="dbscan")
     with pytest.raises(BinningError):
         R.taxon_guided_binning(tax.loc[[markers.index[0]]].copy(), markers, method="dbscan")
+
+
+# ----------------------------------------------------------------------------- large-data mode (8f-3 / 8f-4)
+LDM_KW = dict(norm_method="am_clr", pca_dimensions=10, embed_dimensions=2, embed_method="bhsne", completeness=20.0,
+              purity=90.0, coverage_stddev=25.0, gc_content_stddev=5.0, starting_rank="superkingdom", method="dbscan")
+
+
+@pytest.fixture()
+def stub_bhsne(monkeypatch):
+    """The golden runs of the reference used a ``tsne.bh_sne`` that returns the first d columns it is handed
+    (the PCA scores): the same stub here, so that the frames are comparable end to end."""
+    import sys
+    import types
+
+    stub = types.ModuleType("tsne")
+    stub.bh_sne = lambda data, d, **kw: np.ascontiguousarray(data[:, :d])
+    monkeypatch.setitem(sys.modules, "tsne", stub)
+
+
+def test_partition_pca_matches_sequential_path(torch_cuda):
+    """PartitionPCA (all partitions of a rank queued together over CUDA streams) == kmers.normalize + kmers.pca
+    partition by partition, for the fused k = 5 path with row gathers (incl. a partition with an all-NA contig
+    and one with an absent k-mer column -> the general path) and for a k = 4 table."""
+    from autometa_b200 import assembly as A, synth
+    from autometa_b200.binning.large_data_mode import PartitionPCA
+    from autometa_b200.common import kmers
+
+    asm = synth.make_assembly(2600, 2600 * 3300, seed=41, tiny=True)
+    from oracle import oracle_c
+
+    for k in (5, 4):
+        cnt = oracle_c.count(asm.seq, asm.offsets, k, 1).astype(np.float64)
+        if k == 5:
+            cnt[100:160, 7] = 0  # a k-mer absent from one partition only
+        cnt[cnt == 0] = np.nan
+        names, _ = O.kmer_columns(k)
+        counts = pd.DataFrame(cnt, index=pd.Index(asm.ids, name="contig"), columns=names)
+        rng = np.random.default_rng(5)
+        perm = rng.permutation(2600)
+        parts = {"a": counts.index[np.sort(perm[:900])], "b": counts.index[np.sort(perm[900:1500])],
+                 "gap": counts.index[100:160], "tail": counts.index[2400:]}  # "tail" holds the length-4/5/6 contigs
+        for method in ("am_clr", "ilr"):
+            use = {n: i for n, i in parts.items() if not (method == "ilr" and n == "tail")}
+            got = PartitionPCA(counts, method, 20).run(use)
+            for name, idx in use.items():
+                norm = kmers.normalize(counts.loc[idx], method=method)
+                ref = kmers.pca(norm.to_numpy(), n_components=20)["scores"]
+                assert got[name].index.tolist() == norm.index.tolist(), (k, method, name)
+                assert np.max(np.abs(got[name].to_numpy() - ref)) <= 1e-8 * np.max(np.abs(ref)), (k, method, name)
+
+
+def test_large_data_mode_matches_reference_golden(torch_cuda, stub_bhsne, tmp_path):
+    """cluster_by_taxon_partitioning on the seeded inputs of tests/_ldm_input.py against the frames the
+    unmodified reference produced (tests/golden/make_ldm_golden.py): bins, metrics, column order; with a cache
+    directory also the embedding-cache file names, the checkpoint columns and the checkpoint header; and a
+    second call on the same cache resumes from the checkpoint instead of starting over."""
+    import _ldm_input
+
+    from autometa_b200.binning import large_data_mode as M
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ldm_golden.npz"))
+    main, counts, markers = _ldm_input.make_ldm_input()
+    df = M.cluster_by_taxon_partitioning(main.copy(), counts.copy(), markers, max_partition_size=10000, **LDM_KW)
+    _check_binning_frame(df, g, "ldm")
+    cache = str(tmp_path / "cache")
+    df2 = M.cluster_by_taxon_partitioning(main.copy(), counts.copy(), markers, max_partition_size=400, cache=cache,
+                                          **LDM_KW)
+    _check_binning_frame(df2, g, "ldm400")
+    files = sorted(os.path.relpath(os.path.join(d, f), cache) for d, _, fs in os.walk(cache) for f in fs)
+    assert files == g["ldm400_cache_files"].tolist()
+    info = M.get_checkpoint_info(os.path.join(cache, "binning_checkpoints.tsv.gz"))
+    assert info["binning_checkpoints"].columns.tolist() == g["ldm400_checkpoint_columns"].tolist()
+    assert [info["starting_rank"], info["starting_rank_name_txt"]] == g["ldm400_checkpoint_rank"].tolist()
+    # every cached embedding is a gzip TSV that pandas reads back as the frame we read back
+    for f in files:
+        if f.endswith(".tsv.gz") and "binning_checkpoints" not in f:
+            a = pd.read_csv(os.path.join(cache, f), sep="\t", index_col="contig")
+            b = M._tsv.read_table(os.path.join(cache, f), index_col="contig")
+            pd.testing.assert_frame_equal(a, b, check_exact=True)
+    # resume: the checkpointed bins are kept as they are
+    df3 = M.cluster_by_taxon_partitioning(main.copy(), counts.copy(), markers, max_partition_size=400, cache=cache,
+                                          **LDM_KW)
+    binned = df2["cluster"].notna()
+    assert df3.loc[df2.index[binned], "cluster"].tolist() == df2.loc[binned, "cluster"].tolist()
+    with pytest.raises(FileNotFoundError):
+        M.cluster_by_taxon_partitioning(main.copy(), counts.copy(), markers, binning_checkpoints_fpath=str(tmp_path / "no.tsv"),
+                                        **LDM_KW)
 
 
 # ----------------------------------------------------------------------------- full-size featurise properties

@@ -382,3 +382,63 @@ def test_numa_binding_helper_is_safe_without_a_gpu():
     if not ok:
         assert os.sched_getaffinity(0) == before
     os.sched_setaffinity(0, before)
+
+
+# ------------------------------------------------------------------ large-data-mode caches and checkpoints (8f-4)
+def test_gz_tsv_round_trip_matches_pandas(tmp_path):
+    """``.tsv.gz`` (the large-data-mode embedding caches, large_data_mode.py:104,112): decompressed bytes equal
+    pandas' ``to_csv``; pandas reads our multi-member gzip; our reader returns pandas' frame."""
+    import gzip
+
+    from autometa_b200 import tsv
+
+    rng = np.random.default_rng(3)
+    df = pd.DataFrame(rng.normal(size=(4000, 3)) * 10.0 ** rng.integers(-8, 8, size=(4000, 3)),
+                      index=pd.Index([f"NODE_{i}_length_{3000 + i}_cov_1.5" for i in range(4000)], name="contig"),
+                      columns=["x_1", "x_2", "x_3"])
+    ours, theirs = str(tmp_path / "a.tsv.gz"), str(tmp_path / "b.tsv.gz")
+    old = tsv._GZ_CHUNK
+    tsv._GZ_CHUNK = 50_000  # several gzip members
+    try:
+        tsv.write_frame(df, ours)
+    finally:
+        tsv._GZ_CHUNK = old
+    df.to_csv(theirs, sep="\t", index=True, header=True)
+    with gzip.open(ours, "rb") as a, gzip.open(theirs, "rb") as b:
+        assert a.read() == b.read()
+    ref = pd.read_csv(theirs, sep="\t", index_col="contig")
+    pd.testing.assert_frame_equal(pd.read_csv(ours, sep="\t", index_col="contig"), ref, check_exact=True)
+    pd.testing.assert_frame_equal(tsv.read_table(ours), ref, check_exact=True)
+    pd.testing.assert_frame_equal(tsv.read_table(theirs), ref, check_exact=True)
+
+
+def test_ldm_checkpoint_round_trip(tmp_path):
+    """checkpoint() / get_checkpoint_info() (large_data_mode.py:117-224): '#' header with the run parameters and
+    the rank / taxon the run stopped at, then the table; plain and gzip; columns accumulate per taxon."""
+    import gzip
+
+    from autometa_b200.binning import large_data_mode as M
+
+    idx = pd.Index([f"c{i}" for i in range(6)], name="contig")
+    first = pd.DataFrame({"cluster": ["bin_0", "bin_0", "bin_1"], "purity": [99.0, 99.0, 97.0]}, index=idx[:3])
+    second = pd.DataFrame({"cluster": ["bin_2", "bin_2"]}, index=idx[3:5])
+    for name in ("binning_checkpoints.tsv", "binning_checkpoints.tsv.gz"):
+        path = str(tmp_path / name)
+        kw = dict(completeness=20.0, purity=95.0, coverage_stddev=25.0, gc_content_stddev=5.0, cluster_method="dbscan",
+                  norm_method="am_clr", pca_dimensions=50, embed_dimensions=2, embed_method="bhsne", min_contigs=51,
+                  max_partition_size=10000, binning_checkpoints_fpath=path)
+        ck = M.checkpoint(pd.DataFrame(), first, rank="phylum", rank_name_txt="Proteobacteria", **kw)
+        ck = M.checkpoint(ck, second, rank="class", rank_name_txt="Bacilli", **kw)
+        assert ck.columns.tolist() == ["Proteobacteria", "Bacilli"]
+        info = M.get_checkpoint_info(path)
+        assert info["starting_rank"] == "class" and info["starting_rank_name_txt"] == "Bacilli"
+        got = info["binning_checkpoints"]
+        assert got.columns.tolist() == ["Proteobacteria", "Bacilli"] and got.index.tolist() == idx[:5].tolist()
+        assert got.loc["c0", "Proteobacteria"] == "bin_0" and got.loc["c4", "Bacilli"] == "bin_2"
+        assert pd.isna(got.loc["c4", "Proteobacteria"]) and pd.isna(got.loc["c0", "Bacilli"])
+        opener = gzip.open if name.endswith(".gz") else open
+        with opener(path, "rt") as fh:
+            head = [next(fh) for _ in range(18)]
+        assert head[0].strip() == "#-- Parameters --#" and head[12].strip() == "#-- Runtime Variables --#"
+        assert head[10].startswith("# min-partition-size: 51 (max([pca_dimensions + 1, embed_dimensions + 1])")
+        assert head[13].strip() == "# rank: class" and head[14].strip() == "# name: Bacilli"
