@@ -13,6 +13,8 @@
 // Invalid bases (N, IUPAC, lower case) are handled through the sparse exception
 // structure written by the packers: one flag bit per 64-base group, a rank array
 // and one 64-bit mask per flagged group; the common case touches only the flag.
+#include <stdlib.h>
+
 #include "am_common.cuh"
 
 namespace {
@@ -103,19 +105,21 @@ __device__ __forceinline__ uint32_t window_byte(const uint32_t (&w)[5], int j) {
 // 5 kbp per contig the half-empty last tile was most of the per-contig overhead).  A segment never
 // straddles a 64-base group (SEG divides 64), so the exception mask of ONE group (+ K-1 bits of the
 // next) covers all its windows.
+// The tile is split in its LOAD (codes + validity of the lane's segment) and its COUNT (the shared-memory
+// atomics) so that the kernel can issue the loads of the next tile before it counts the current one: the
+// global-load latency (the top stall reason, 21 % of the samples in profiles/r2c) then overlaps the atomics.
 template <int K, int SEG>
-__device__ __forceinline__ void count_tile(const uint4 *__restrict__ codes4, const uint32_t *__restrict__ codes,
-                                           const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ rank,
-                                           const uint64_t *__restrict__ exc_mask, int64_t gbase, int t0, int nw,
-                                           int lane, uint32_t *hist) {
-  constexpr int NB = 1 << (2 * K);
-  constexpr int NWORD = SEG / 16;
+__device__ __forceinline__ void tile_load(const uint4 *__restrict__ codes4, const uint32_t *__restrict__ codes,
+                                          const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ rank,
+                                          const uint64_t *__restrict__ exc_mask, int64_t gbase, int t0, int nw,
+                                          int lane, uint32_t (&wreg)[5], uint64_t &valid_out) {
   constexpr uint64_t SEGMASK = SEG == 64 ? ~0ull : ((1ull << SEG) - 1ull);
   const int seg = t0 + lane * SEG;
   int nv = nw - seg;
   nv = nv < 0 ? 0 : (nv > SEG ? SEG : nv);
-  uint64_t valid_out = 0ull;
-  uint32_t wreg[5] = {0u, 0u, 0u, 0u, 0u};
+  valid_out = 0ull;
+#pragma unroll
+  for (int q = 0; q < 5; ++q) wreg[q] = 0u;
   if (nv > 0) {
     const int64_t g = gbase + (seg >> 6);
     const int sub = seg & 63;
@@ -152,10 +156,15 @@ __device__ __forceinline__ void count_tile(const uint4 *__restrict__ codes4, con
     }
     valid_out = valid & SEGMASK;
   }
+}
+
+template <int K, int SEG>
+__device__ __forceinline__ void tile_count(const uint32_t (&wreg)[5], uint64_t valid_out, uint32_t *hist) {
+  constexpr int NB = 1 << (2 * K);
+  constexpr uint64_t SEGMASK = SEG == 64 ? ~0ull : ((1ull << SEG) - 1ull);
   // warp-uniform choice: the common all-valid tile takes the 3-instruction path; a tile with
   // any partial / flagged lane sends its invalid windows to a dummy bin (no divergent branches)
   char *hb = reinterpret_cast<char *>(hist);
-  (void)NWORD;
   if (__all_sync(FULL, valid_out == SEGMASK)) {
 #pragma unroll
     for (int j = 0; j < SEG; ++j) atomicAdd(reinterpret_cast<uint32_t *>(hb + window_byte<K>(wreg, j)), 1u);
@@ -170,8 +179,8 @@ __device__ __forceinline__ void count_tile(const uint4 *__restrict__ codes4, con
   }
 }
 
-template <int K, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int K, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 count_kernel(const uint4 *__restrict__ codes4, const uint32_t *__restrict__ codes,
              const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ rank,
              const uint64_t *__restrict__ exc_mask, const int64_t *__restrict__ starts,
@@ -189,23 +198,55 @@ count_kernel(const uint4 *__restrict__ codes4, const uint32_t *__restrict__ code
   uint32_t present = 0;  // bit s <-> column lane + 32*s (used when ncols <= 1024)
   const bool present_in_reg = ncols <= 1024;
 
-  while (true) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(work_counter, 1);
-    item = __shfl_sync(FULL, item, 0);
-    if (item >= n_items) break;
-    const int4 it = __ldg(items + item);
+  // work items are claimed one ahead: the atomic on the work counter, the item record and the contig's start
+  // offset (three dependent global loads) are in flight while the current item is counted / flushed
+  int item = 0;
+  if (lane == 0) item = atomicAdd(work_counter, 1);
+  item = __shfl_sync(FULL, item, 0);
+  int4 it = make_int4(0, 0, 0, 0);
+  int64_t start = 0;
+  if (item < n_items) {
+    it = __ldg(items + item);
+    start = __ldg(starts + it.x);
+  }
+  while (item < n_items) {
+    int next_item = 0;
+    if (lane == 0) next_item = atomicAdd(work_counter, 1);
     const int row = it.x, w0 = it.y, nw = it.z, flags = it.w;
-    const int64_t gbase = (__ldg(starts + row) + (int64_t)w0) >> 6;
+    const int64_t gbase = (start + (int64_t)w0) >> 6;
 
-    // full-width tiles while more than half a tile remains; then the remainder at 32 or 16 bases per lane
-    int t0 = 0;
-    for (; nw - t0 > AM_TILE_BASES / 2; t0 += AM_TILE_BASES)
-      count_tile<K, 64>(codes4, codes, bitmap, rank, exc_mask, gbase, t0, nw, lane, hist);
-    if (nw - t0 > AM_TILE_BASES / 4)
-      count_tile<K, 32>(codes4, codes, bitmap, rank, exc_mask, gbase, t0, nw, lane, hist);
-    else if (nw - t0 > 0)
-      count_tile<K, 16>(codes4, codes, bitmap, rank, exc_mask, gbase, t0, nw, lane, hist);
+    // full-width tiles while more than half a tile remains, then the remainder at 32 or 16 bases per lane;
+    // the loads of tile i+1 (or of the remainder) are issued before tile i is counted
+    const int nfull = nw > AM_TILE_BASES / 2 ? (nw - AM_TILE_BASES / 2 + AM_TILE_BASES - 1) / AM_TILE_BASES : 0;
+    const int rem_t0 = nfull * AM_TILE_BASES, rem = nw - rem_t0;
+    uint32_t wa[5];
+    uint64_t va;
+    if (nfull > 0) tile_load<K, 64>(codes4, codes, bitmap, rank, exc_mask, gbase, 0, nw, lane, wa, va);
+    for (int i = 0; i < nfull; ++i) {
+      uint32_t wb[5];
+      uint64_t vb;
+      if (i + 1 < nfull) tile_load<K, 64>(codes4, codes, bitmap, rank, exc_mask, gbase, (i + 1) * AM_TILE_BASES, nw, lane, wb, vb);
+      else if (rem > AM_TILE_BASES / 4) tile_load<K, 32>(codes4, codes, bitmap, rank, exc_mask, gbase, rem_t0, nw, lane, wb, vb);
+      else tile_load<K, 16>(codes4, codes, bitmap, rank, exc_mask, gbase, rem_t0, nw, lane, wb, vb);
+      tile_count<K, 64>(wa, va, hist);
+#pragma unroll
+      for (int q = 0; q < 5; ++q) wa[q] = wb[q];
+      va = vb;
+    }
+    if (nfull == 0) {
+      if (rem > AM_TILE_BASES / 4) tile_load<K, 32>(codes4, codes, bitmap, rank, exc_mask, gbase, rem_t0, nw, lane, wa, va);
+      else tile_load<K, 16>(codes4, codes, bitmap, rank, exc_mask, gbase, rem_t0, nw, lane, wa, va);
+    }
+    // the next item's record and start offset: in flight during the remainder tile and the flush
+    next_item = __shfl_sync(FULL, next_item, 0);
+    int4 nit = make_int4(0, 0, 0, 0);
+    int64_t nstart = 0;
+    if (next_item < n_items) {
+      nit = __ldg(items + next_item);
+      nstart = __ldg(starts + nit.x);
+    }
+    if (rem > AM_TILE_BASES / 4) tile_count<K, 32>(wa, va, hist);
+    else if (rem > 0) tile_count<K, 16>(wa, va, hist);
     __syncwarp();
 
     // flush: fold the raw histogram into canonical columns, store the row
@@ -241,6 +282,9 @@ count_kernel(const uint4 *__restrict__ codes4, const uint32_t *__restrict__ code
     __syncwarp();
     for (int i = lane; i < NB; i += 32) hist[i] = 0;
     __syncwarp();
+    item = next_item;
+    it = nit;
+    start = nstart;
   }
   if (present_in_reg) {
     for (int s = 0; s * 32 < ncols; ++s) {
@@ -250,12 +294,12 @@ count_kernel(const uint4 *__restrict__ codes4, const uint32_t *__restrict__ code
   }
 }
 
-template <int K, int WARPS>
+template <int K, int WARPS, int MINB>
 int launch_count(const uint32_t *d_codes, const uint32_t *d_bitmap, const uint32_t *d_rank,
                  const uint64_t *d_exc_mask, const int64_t *d_starts, const int32_t *d_items,
                  int64_t n_items, const uint32_t *fold, int ncols, int32_t *d_counts,
                  int32_t *d_col_present, int32_t *d_row_sum, int *d_counter, cudaStream_t st) {
-  auto kern = count_kernel<K, WARPS>;
+  auto kern = count_kernel<K, WARPS, MINB>;
   const size_t smem = (size_t)WARPS * ((1u << (2 * K)) + 32) * sizeof(uint32_t);
   if (smem > 48 * 1024)
     AM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -301,11 +345,18 @@ extern "C" int am_count_kmers(const uint32_t *d_codes, const uint32_t *d_exc_bit
     zero_rows_kernel<<<grid, 256, 0, st>>>(d_counts, d_row_sum, d_multi_rows, n_multi, ncols);
     AM_LAUNCHED("zero_rows_kernel");
   }
-#define AM_COUNT_CASE(KK, WW)                                                                  \
-  case KK:                                                                                     \
-    return launch_count<KK, WW>(d_codes, d_exc_bitmap, d_exc_rank, d_exc_mask, d_starts,       \
-                                d_items, n_items, fold, ncols, d_counts, d_col_present,        \
-                                d_row_sum, counter, st);
+  // resident CTAs per SM the register allocation is sized for: 6 (40 registers, 12 bytes spilled) or 5 (48
+  // registers); AM_COUNT_MINB=5 selects the latter (timing experiments)
+  const char *mb = getenv("AM_COUNT_MINB");
+  const bool five = mb && mb[0] == '5';
+#define AM_COUNT_CASE(KK, WW)                                                                    \
+  case KK:                                                                                       \
+    return five ? launch_count<KK, WW, 5>(d_codes, d_exc_bitmap, d_exc_rank, d_exc_mask, d_starts, \
+                                          d_items, n_items, fold, ncols, d_counts, d_col_present,  \
+                                          d_row_sum, counter, st)                                  \
+                : launch_count<KK, WW, 6>(d_codes, d_exc_bitmap, d_exc_rank, d_exc_mask, d_starts, \
+                                          d_items, n_items, fold, ncols, d_counts, d_col_present,  \
+                                          d_row_sum, counter, st);
   switch (k) {
     AM_COUNT_CASE(1, 8)
     AM_COUNT_CASE(2, 8)

@@ -373,7 +373,7 @@ def time_pipelined(torch, dist, pipeline, L, packed, norm, steps, warmup, distri
     eigensolve of step i is done by rank i mod N and broadcast.  Every step's work is complete inside the timed
     region (drain() before the closing event); barrier + synchronize on both sides; max over ranks."""
     fs = pipeline.FeatureStream(dev, K, norm, NCOMP, distributed=distributed, depth=depth)
-    for _ in range(warmup):
+    for _ in range(max(warmup, depth + 1)):  # every buffer of every step in flight exists before the timed region
         fs.submit(packed)
     fs.drain()
     torch.cuda.synchronize()

@@ -48,6 +48,14 @@ def main():
         frame_to_dict(df2, "ldm400", out)
         files = sorted(os.path.relpath(os.path.join(d, f), cache) for d, _, fs in os.walk(cache) for f in fs)
         out["ldm400_cache_files"] = np.array(files)
+        # the cached embeddings themselves (first two PCA scores through the stub bh_sne): small, and the
+        # sharpest diagnostic when a bin differs
+        for f in files:
+            if "binning_checkpoints" in f:
+                continue
+            emb = pd.read_csv(os.path.join(cache, f), sep="\t", index_col="contig")
+            out[f"emb::{f}::index"] = np.array(emb.index.tolist())
+            out[f"emb::{f}::values"] = emb.to_numpy(dtype=np.float64)
         info = ldm.get_checkpoint_info(os.path.join(cache, "binning_checkpoints.tsv.gz"))
         out["ldm400_checkpoint_columns"] = np.array(info["binning_checkpoints"].columns.tolist())
         out["ldm400_checkpoint_rank"] = np.array([info["starting_rank"], info["starting_rank_name_txt"]])
