@@ -103,9 +103,11 @@ class PartitionPCA:
                 flags = res["stats"].cpu().numpy()
                 cols_ok, rows_ok = bool((flags[:D] > 0).all()), bool(flags[D] == 0)
                 keep_rows = rows
-                if not rows_ok and self.method != "am_clr":
-                    raise ValueError("Input matrix cannot have rows with all zeros")
-                if not (cols_ok and rows_ok):
+                if self.method != "am_clr":
+                    # clr / ilr keep every column (zeros are replaced, kmers.py:418-421); an empty row is an error
+                    if not rows_ok:
+                        raise ValueError("Input matrix cannot have rows with all zeros")
+                elif not (cols_ok and rows_ok):
                     # am_clr drops the k-mers absent from this partition and its contigs without counts
                     # (kmers.py:369): the general path with explicit gathers, on the caller's stream
                     col_index = None if cols_ok else torch.nonzero(present > 0).flatten().to(torch.int32)

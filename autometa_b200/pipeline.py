@@ -356,7 +356,7 @@ class FeatureStream:
         flags = res["stats"].cpu().numpy()
         cols_ok, rows_ok = bool((flags[:D] > 0).all()), bool(flags[D] == 0)
         n_total = float(res["n_total"].item()) if self.distributed else float(packed.n_contigs)
-        if n_total > 0 and not (cols_ok and rows_ok):
+        if n_total > 0 and not (rows_ok and (cols_ok or self.method != "am_clr")):
             # rare: redo this pass on the general path (row / column gathers, or the clr / ilr error).  The
             # library's scratch buffers are shared per device: let the passes in flight finish first
             with torch.cuda.device(self.dev):
