@@ -144,9 +144,32 @@ def require_cuda(device=None):
 
 
 def stream_ptr(device) -> int:
+    """Raw ``cudaStream_t`` of torch's current stream on ``device`` (the C call, not the Stream object: this
+    runs ~25 times per pass and the host-side cost of queueing a pass is what bounds small shards)."""
     import torch
 
-    return torch.cuda.current_stream(device).cuda_stream
+    idx = device.index if getattr(device, "index", None) is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def on_device(device):
+    """``torch.cuda.device(device)`` unless ``device`` is already current (then a no-op context)."""
+    import torch
+
+    if device.index is None or torch._C._cuda_getDevice() == device.index:
+        return _NULL
+    return torch.cuda.device(device)
 
 
 def launch_count() -> int:

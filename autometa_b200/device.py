@@ -67,7 +67,7 @@ def count_packed(packed: PackedAssembly, k: int = 5, counts=None, col_present=No
     ncols = num_columns(k)
     n = packed.n_contigs
     plan = get_count_plan(packed, k)
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         if counts is None:
             counts = torch.empty((n, ncols), dtype=torch.int32, device=dev)
         if col_present is None:
@@ -95,7 +95,7 @@ def _work(dev, nbytes: int, tag: str):
 
     # scratch is per (kernel family, device, stream): passes running on different streams (pipeline.FeatureStream,
     # per-partition streams of the large-data-mode driver) must not share partial-result buffers
-    key = (tag, dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    key = (tag, dev.index, L.stream_ptr(dev))
     t = _work_cache.get(key)
     if t is None or t.numel() < nbytes:
         t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
@@ -117,7 +117,7 @@ def normalize_counts(counts, method: str = "am_clr", row_index=None, col_index=N
     n_out = n_in if row_index is None else int(row_index.numel())
     Dk = D if col_index is None else int(col_index.numel())
     Dout = Dk - 1 if method == "ilr" else Dk
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         if out is None:
             out = torch.empty((n_out, Dout), dtype=torch.float64, device=dev)
         work = None
@@ -137,7 +137,7 @@ def colsum(X, out=None):
 
     dev = X.device
     n, D = X.shape
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         if out is None:
             out = torch.zeros(D, dtype=torch.float64, device=dev)
         work = _work(dev, L.lib.am_colsum_work_bytes(D), "colsum")
@@ -151,7 +151,7 @@ def gram_centered(X, mu, out=None):
 
     dev = X.device
     n, D = X.shape
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         if out is None:
             out = torch.zeros((D, D), dtype=torch.float64, device=dev)
         work = _work(dev, L.lib.am_gram_work_bytes(D), "gram")
@@ -165,7 +165,7 @@ def colstats(X, colsum_out=None, colmax_out=None):
 
     dev = X.device
     n, D = X.shape
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         if colsum_out is None:
             colsum_out = torch.zeros(D, dtype=torch.float64, device=dev)
         if colmax_out is None:
@@ -186,7 +186,7 @@ def gram_centered_i8(X, mu, colmaxabs, out=None, slices: int = GRAM_SLICES):
 
     dev = X.device
     n, D = X.shape
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         if out is None:
             out = torch.zeros((D, D), dtype=torch.float64, device=dev)
         work = _work(dev, L.lib.am_gram_i8_work_bytes(n, D, slices), "gram_i8")
@@ -202,7 +202,7 @@ def plane_scales(center, colmaxabs=None, bound: float = -1.0, slices: int = GRAM
 
     dev = center.device
     D = center.numel()
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         e = torch.empty(D, dtype=torch.int32, device=dev)
         sc = torch.empty(D, dtype=torch.float64, device=dev)
         L.check(L.lib.am_plane_scales(L.t_ptr(center), L.t_ptr(colmaxabs), float(bound), D, slices, L.t_ptr(e),
@@ -231,7 +231,7 @@ def normalize_planes(counts, method: str, row_index, center, sc, colsum, out=Non
     m = L.NORM_METHODS[method]
     n_in, D = counts.shape
     n_out = n_in if row_index is None else int(row_index.numel())
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         if out is None and want_out:
             out = torch.empty((n_out, D), dtype=torch.float64, device=dev)
         if planes is None and want_planes:
@@ -254,7 +254,7 @@ def quantize_planes(X, center, sc, planes=None, slices: int = GRAM_SLICES):
 
     dev = X.device
     n, D = X.shape
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         if planes is None:
             planes = alloc_planes(n, D, dev, slices)
         L.check(L.lib.am_quantize_planes(L.t_ptr(X), n, D, L.t_ptr(center), L.t_ptr(sc), slices, L.t_ptr(planes),
@@ -267,7 +267,7 @@ def gram_planes(planes, n: int, D: int, e, out=None, slices: int = GRAM_SLICES):
     import torch
 
     dev = planes.device
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         if out is None:
             out = torch.zeros((D, D), dtype=torch.float64, device=dev)
         work = _work(dev, L.lib.am_gram_planes_work_bytes(n, D, slices), "gram_planes")
@@ -282,7 +282,7 @@ def cov_finish(G, colsum, center, n_t):
 
     dev = G.device
     D = G.shape[0]
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         mu = torch.empty(D, dtype=torch.float64, device=dev)
         L.check(L.lib.am_cov_finish(L.t_ptr(G), D, L.t_ptr(colsum), L.t_ptr(center), L.t_ptr(n_t), L.t_ptr(mu),
                                     L.stream_ptr(dev)))
@@ -294,7 +294,7 @@ def count_flags(present, row_sum, n: int):
     import torch
 
     dev = present.device
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         flags = torch.empty(2, dtype=torch.int32, device=dev)
         L.check(L.lib.am_count_flags(L.t_ptr(present), int(present.numel()), L.t_ptr(row_sum), int(n), L.t_ptr(flags),
                                      L.stream_ptr(dev)))
@@ -307,7 +307,7 @@ def stats_pack(present, row_sum, n: int, out):
     import torch
 
     dev = present.device
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         L.check(L.lib.am_stats_pack(L.t_ptr(present), int(present.numel()), L.t_ptr(row_sum), int(n), L.t_ptr(out),
                                     L.stream_ptr(dev)))
     return out
@@ -318,7 +318,7 @@ def gram_recenter(G, colsum, c_old, c_new, n_t):
     import torch
 
     dev = G.device
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         L.check(L.lib.am_gram_recenter(L.t_ptr(G), int(G.shape[0]), L.t_ptr(colsum), L.t_ptr(c_old), L.t_ptr(c_new),
                                        L.t_ptr(n_t), L.stream_ptr(dev)))
     return G
@@ -331,7 +331,7 @@ def eigh_desc(A, max_sweeps: int = 30, tol: float = 0.0):
 
     dev = A.device
     D = A.shape[0]
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         evals = torch.empty(D, dtype=torch.float64, device=dev)
         evecs = torch.empty((D, D), dtype=torch.float64, device=dev)
         work = _work(dev, L.lib.am_eigh_work_bytes(D), "eigh")
@@ -359,7 +359,7 @@ def eigh_topk(A, P: int):
     if _topk_state.get("disabled") or not (3 <= D <= TOPK_MAX_D and 1 <= P <= min(D, TOPK_MAX_P)):
         evals, evecs = eigh_desc(A)
         return evals[:P].contiguous(), evecs[:P].contiguous(), torch.clamp(evals, min=0.0).sum().reshape(1)
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         evals = torch.empty(P, dtype=torch.float64, device=dev)
         evecs = torch.empty((P, D), dtype=torch.float64, device=dev)
         trace = torch.empty(1, dtype=torch.float64, device=dev)
@@ -388,7 +388,7 @@ def project(X, mu, comps, out=None):
     dev = X.device
     n, D = X.shape
     P = comps.shape[0]
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         if out is None:
             out = torch.empty((n, P), dtype=torch.float64, device=dev)
         L.check(
@@ -403,7 +403,7 @@ def project_planes(planes, n: int, D: int, e, center, mu, comps, out=None, slice
 
     dev = planes.device
     P = comps.shape[0]
-    with torch.cuda.device(dev):
+    with L.on_device(dev):
         if out is None:
             out = torch.empty((n, P), dtype=torch.float64, device=dev)
         work = _work(dev, L.lib.am_project_planes_work_bytes(D, slices), "project_planes")
@@ -422,7 +422,7 @@ class EpsSweep:
         self.X = X
         self.dev = X.device
         self.n, self.F = X.shape
-        with torch.cuda.device(self.dev):
+        with L.on_device(self.dev):
             self.parent = torch.empty(max(self.n, 1), dtype=torch.int32, device=self.dev)
             L.check(L.lib.am_iota_i32(L.t_ptr(self.parent), self.n, L.stream_ptr(self.dev)))
             self.work = torch.empty(max(256, L.lib.am_dbscan_work_bytes(self.n)), dtype=torch.uint8, device=self.dev)
@@ -439,7 +439,7 @@ class EpsSweep:
     def reset(self):
         import torch
 
-        with torch.cuda.device(self.dev):
+        with L.on_device(self.dev):
             L.check(L.lib.am_iota_i32(L.t_ptr(self.parent), self.n, L.stream_ptr(self.dev)))
         self.last_eps = 0.0
 
@@ -451,7 +451,7 @@ class EpsSweep:
         if eps < self.last_eps:
             self.reset()
         self.last_eps = eps
-        with torch.cuda.device(self.dev):
+        with L.on_device(self.dev):
             st = L.stream_ptr(self.dev)
             L.check(
                 L.lib.am_eps_union(L.t_ptr(self.X), self.n, self.F, float(eps), L.np_ptr(self.h_min),
@@ -476,7 +476,7 @@ class ClusterMetrics:
         self.n = int(n_points)
         self.M = int(n_ref_markers)
         self.cutoffs = tuple(float(c) for c in cutoffs)
-        with torch.cuda.device(device):
+        with L.on_device(device):
             # np.array(..., copy=True): pandas hands out read-only views, which torch.from_numpy warns about
             t = lambda a, dt: torch.from_numpy(np.array(a, dtype=dt, order="C", copy=True)).to(device)
             self.nnz = int(len(marker_rows))
@@ -501,7 +501,7 @@ class ClusterMetrics:
         import torch
 
         c = self.cutoffs
-        with torch.cuda.device(self.dev):
+        with L.on_device(self.dev):
             L.check(
                 L.lib.am_cluster_metrics(
                     L.t_ptr(labels), self.n, L.t_ptr(n_clusters), L.t_ptr(self.rows), L.t_ptr(self.cols),

@@ -294,7 +294,8 @@ class FeatureStream:
     back when a pass retires and the rare failing pass is redone by ``featurise``."""
 
     def __init__(self, device, k: int = 5, method: str = "am_clr", n_components: int = 50, group=None,
-                 distributed: bool = False, depth: int = 2, keep: bool = False, spread_eigh: bool = True):
+                 distributed: bool = False, depth: int = 2, keep: bool = False, spread_eigh: bool = True,
+                 on_result=None):
         """``spread_eigh`` (several GPUs): the eigensolve of pass i is done by rank i mod N only and broadcast,
         instead of being replicated on every rank — with N passes in flight each GPU solves one eigenproblem
         per N passes, which removes the replicated, N-independent 1.2 ms from every rank's critical path
@@ -305,6 +306,9 @@ class FeatureStream:
         self.dev = L.require_cuda(device)
         self.k, self.method, self.P = k, method, n_components
         self.group, self.distributed, self.depth, self.keep = group, distributed, max(1, depth), keep
+        # results are handed to ``on_result(result)`` as each pass retires (and not kept) when it is given;
+        # otherwise they accumulate until ``drain()`` — device memory of every pass stays allocated until then
+        self.on_result = on_result
         self.n_submitted = 0
         self.eig_group = None
         self.world = 1
@@ -368,7 +372,10 @@ class FeatureStream:
             X = res.pop("normalized")
             if self.keep:
                 res.update(counts=st["counts"], normalized=X, col_present=present, row_sum=row_sum)
-        self.done.append(res)
+        if self.on_result is not None:
+            self.on_result(res)
+        else:
+            self.done.append(res)
 
     def drain(self):
         """Wait for everything submitted; returns the results in submission order."""

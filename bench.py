@@ -372,7 +372,12 @@ def time_pipelined(torch, dist, pipeline, L, packed, norm, steps, warmup, distri
     step i+1 on one stream while stage 2 (eigensolve + projection) of step i runs on another; with several GPUs the
     eigensolve of step i is done by rank i mod N and broadcast.  Every step's work is complete inside the timed
     region (drain() before the closing event); barrier + synchronize on both sides; max over ranks."""
-    fs = pipeline.FeatureStream(dev, K, norm, NCOMP, distributed=distributed, depth=depth)
+    consumed = []  # the consumer keeps only the last pass's outputs (a service hands them on and lets go)
+
+    def consume(res):
+        consumed[:] = [res["scores"], res["explained_variance"]]
+
+    fs = pipeline.FeatureStream(dev, K, norm, NCOMP, distributed=distributed, depth=depth, on_result=consume)
     for _ in range(max(warmup, depth + 1)):  # every buffer of every step in flight exists before the timed region
         fs.submit(packed)
     fs.drain()
