@@ -43,6 +43,8 @@ _SIGS = {
     "am_version": (C.c_int, []),
     "am_last_error": (C.c_char_p, []),
     "am_launch_count": (_i64, []),
+    "am_set_reserved_sms": (C.c_int, [_i32]),
+    "am_get_reserved_sms": (C.c_int, []),
     "am_kmer_num_columns": (C.c_int, [_i32]),
     "am_kmer_column_lut": (C.c_int, [_i32, _p]),
     "am_kmer_column_names": (C.c_int, [_i32, _p]),

@@ -14,6 +14,7 @@ namespace am {
 
 extern thread_local char g_err[512];
 extern std::atomic<int64_t> g_launches;
+extern std::atomic<int> g_reserved_sms;
 
 inline int fail(int code, const char *fmt, const char *a = "", const char *b = "") {
   snprintf(g_err, sizeof(g_err), fmt, a, b);
@@ -47,6 +48,16 @@ inline int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+
+// SMs a persistent kernel with a STATIC work split may size its grid for: all of them, minus the ones the
+// caller has set aside (am_set_reserved_sms) for a latency-bound kernel that runs next to it — the 16-CTA
+// tridiagonalisation cluster of the previous pass in pipeline.FeatureStream.  A static split over 148 CTAs of
+// which 16 cannot be placed finishes only after those 16 get an SM, i.e. after the other kernel: the two
+// would run one after the other instead of side by side.
+inline int grid_sms() {
+  const int n = num_sms() - g_reserved_sms.load(std::memory_order_relaxed);
+  return n < 2 ? 2 : n;
 }
 
 // reverse complement of an MSB-first base-4 code with A=0,T=1,C=2,G=3

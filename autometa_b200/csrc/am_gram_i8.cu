@@ -651,7 +651,7 @@ extern "C" int am_gram_planes(const int8_t *d_planes, int64_t n_rows, int D, int
     const int ns = sv ? atoi(sv) : G2_STAGES;
     const size_t smem = (size_t)ns * G2_STAGE_BYTES + 16 * (size_t)ns + 64 + 1024;
     const int n_items = p.n_chunks * p.n_tiles;
-    const int pairs = std::max(1, std::min(n_items, am::num_sms() / 2));
+    const int pairs = std::max(1, std::min(n_items, am::grid_sms() / 2));
     auto launch = [&](auto kern) -> cudaError_t {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
@@ -670,7 +670,7 @@ extern "C" int am_gram_planes(const int8_t *d_planes, int64_t n_rows, int D, int
     const size_t smem = (size_t)p.stages * S * (GI_A_BYTES + GI_B_BYTES) + 16 * (size_t)p.stages + 64 + 1024;
     AM_CUDA(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_items = p.n_chunks * p.n_tiles;
-    const int grid = std::min(n_items, am::num_sms());
+    const int grid = std::min(n_items, am::grid_sms());
     gram_i8_kernel<<<grid, GI_THREADS, smem, st>>>(tmA, tmB, p, part);
     AM_LAUNCHED("gram_i8_kernel");
   }

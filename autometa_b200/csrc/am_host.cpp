@@ -10,6 +10,7 @@
 namespace am {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_reserved_sms{0};
 }  // namespace am
 
 extern "C" {
@@ -17,6 +18,12 @@ extern "C" {
 int am_version(void) { return 100; }
 const char *am_last_error(void) { return am::g_err; }
 int64_t am_launch_count(void) { return am::g_launches.load(); }
+int am_set_reserved_sms(int n) {
+  if (n < 0 || n > 64) return am::fail(AM_EINVAL, "am_set_reserved_sms: n must be in 0..64");
+  am::g_reserved_sms.store(n);
+  return AM_OK;
+}
+int am_get_reserved_sms(void) { return am::g_reserved_sms.load(); }
 
 // ---- k-mer column table (kmers.py:56-89) ------------------------------------
 static int build_columns(int k, std::vector<uint32_t> &canon_sorted, std::vector<int32_t> &lut) {

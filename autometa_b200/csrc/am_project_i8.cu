@@ -330,7 +330,7 @@ extern "C" int am_project_planes(const int8_t *d_planes, int64_t n_rows, int D, 
   }
   const size_t smem = (size_t)PJ_STAGES * PJ_NP * (PJ_A_BYTES + PJ_B_BYTES) + 16 * PJ_STAGES + 64 + 1024;
   AM_CUDA(cudaFuncSetAttribute(project_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = std::min(p.n_tiles, am::num_sms());
+  const int grid = std::min(p.n_tiles, am::grid_sms());
   project_i8_kernel<<<grid, PJ_THREADS, smem, st>>>(tmA, tmB, p, f, bconst, d_scores);
   AM_LAUNCHED("project_i8_kernel");
   return AM_OK;

@@ -325,10 +325,17 @@ class FeatureStream:
         self.inflight = []
         self.done = []
 
+    #: SMs the statically split kernels of stage 1 (Gram, projection) leave to the tridiagonalisation cluster of
+    #: the pass before (16 CTAs, one per SM): without it the Gram's last CTAs wait for the cluster to end and
+    #: the two stages run one after the other (measured: no overlap at all on 2 GPUs)
+    RESERVED_SMS = 16
+
     def submit(self, packed: PackedAssembly, marks=None):
         import torch
 
         mark = marks if marks is not None else (lambda name: None)
+        if self.depth > 1 and L.lib.am_get_reserved_sms() != self.RESERVED_SMS:
+            L.check(L.lib.am_set_reserved_sms(self.RESERVED_SMS))
         while len(self.inflight) >= self.depth:
             self._retire()
         with torch.cuda.device(self.dev):
@@ -381,6 +388,7 @@ class FeatureStream:
         """Wait for everything submitted; returns the results in submission order."""
         while self.inflight:
             self._retire()
+        L.check(L.lib.am_set_reserved_sms(0))
         out, self.done = self.done, []
         return out
 

@@ -52,6 +52,10 @@ int am_version(void);
 const char *am_last_error(void);
 /* number of CUDA kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t am_launch_count(void);
+/* SMs that kernels with a static work split (Gram, projection) leave free, so that a latency-bound kernel of
+ * another stream (the eigensolve of the previous pass, pipeline.FeatureStream) runs beside them; 0 = none. */
+int am_set_reserved_sms(int n);
+int am_get_reserved_sms(void);
 
 /* ---------------------------------------------------------------------------
  * k-mer column table — replaces init_kmers / _revcomp
