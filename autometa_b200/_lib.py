@@ -88,6 +88,8 @@ _SIGS = {
     "am_eigh": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _f64, _p]),
     "am_eigh_topk_work_bytes": (_i64, [_i32, _i32]),
     "am_eigh_topk": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p]),
+    "am_eigh_topk_signal": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, C.c_uint32, _p]),
+    "am_stream_wait_geq": (C.c_int, [_p, _p, C.c_uint32]),
     "am_project_planes_work_bytes": (_i64, [_i32, _i32]),
     "am_project_planes": (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "am_project": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _p, _p]),

@@ -17,6 +17,7 @@
 //   4. cholqr_kernel           re-orthonormalisation (CholeskyQR2) — only matters for clusters.
 //   5. backtransform_kernel    z = Q y (reflectors applied in reverse), sign rule, output.
 #include <cooperative_groups.h>
+#include <cuda.h>
 
 #include "am_common.cuh"
 
@@ -104,7 +105,19 @@ struct TriOut {
   double *d;     // [n]
   double *e;     // [n]  (e[i] couples i and i+1)
   long long *dbg;  // optional [8] phase cycle counters (CTA 0, thread 0); may be NULL
+  // optional "the cluster is resident" signal: CTA 0 stores started_value here as its first action, so that
+  // another stream can hold its next (SM-filling) kernel back until this cluster HAS its 16 SMs
+  // (am_stream_wait_geq); may be NULL
+  unsigned int *started;
+  unsigned int started_value;
 };
+
+__device__ __forceinline__ void signal_started(const TriOut &out) {
+  if (out.started && blockIdx.x == 0 && threadIdx.x == 0) {
+    *reinterpret_cast<volatile unsigned int *>(out.started) = out.started_value;
+    __threadfence_system();
+  }
+}
 
 // ------------------------------------------------------------------ 1. tridiagonalisation
 // Step k (LAPACK dsytd2 with the rank-2 update deferred by one step).  x_k = current column k below
@@ -128,6 +141,7 @@ __device__ __forceinline__ void st_async_f64x2(uint32_t raddr, double a, double 
 
 __global__ void __cluster_dims__(TC, 1, 1) __launch_bounds__(TT, 1)
 tridiag_cluster_kernel(const double *__restrict__ A, int n, int np, int RL, TriOut out) {
+  signal_started(out);
   cg::cluster_group cluster = cg::this_cluster();
   const int c = (int)cluster.block_rank();
   extern __shared__ double sm[];
@@ -366,6 +380,7 @@ constexpr int RNE = (32 * NB + RAT - 1) / RAT;
 template <bool PROBE, bool EXACT>
 __global__ void __cluster_dims__(TC, 1, 1) __launch_bounds__(RT, 1)
 tridiag_reg_kernel(const double *__restrict__ A, int n_, int np_, int RL_, TriOut out) {
+  signal_started(out);
   const int n = EXACT ? 32 * NB : n_, np = EXACT ? 32 * NB : np_, RL = EXACT ? RR * RW : RL_;
   cg::cluster_group cluster = cg::this_cluster();
   const int c = (int)cluster.block_rank();
@@ -1402,6 +1417,29 @@ extern "C" int64_t am_eigh_topk_work_bytes(int D, int P) {
 
 extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, double *d_evecs,
                             double *d_trace, void *d_work, void *stream) {
+  return am_eigh_topk_signal(d_A, D, P, d_evals, d_evecs, d_trace, d_work, nullptr, 0u, stream);
+}
+
+extern "C" int am_stream_wait_geq(void *stream, const uint32_t *d_flag, uint32_t value) {
+  typedef CUresult (*WaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+  static WaitFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (WaitFn)p;
+  }
+  if (!fn) return am::fail(AM_ECUDA, "am_stream_wait_geq: cuStreamWaitValue32 entry point unavailable");
+  if (!d_flag) return am::fail(AM_EINVAL, "am_stream_wait_geq: null pointer");
+  const CUresult r = fn((CUstream)stream, (CUdeviceptr)(uintptr_t)d_flag, value, CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) return am::fail(AM_ECUDA, "am_stream_wait_geq: cuStreamWaitValue32 failed");
+  return AM_OK;
+}
+
+extern "C" int am_eigh_topk_signal(const double *d_A, int D, int P, double *d_evals, double *d_evecs,
+                                   double *d_trace, void *d_work, uint32_t *d_started, uint32_t started_value,
+                                   void *stream) {
   if (D < 3 || D > SMEM_N_MAX) return am::fail(AM_EINVAL, "am_eigh_topk: D must be in 3..576 (use am_eigh otherwise)");
   if (P < 1 || P > D || P > PMAX) return am::fail(AM_EINVAL, "am_eigh_topk: P must be in 1..min(D,128)");
   if (!d_A || !d_evals || !d_evecs || !d_work) return am::fail(AM_EINVAL, "am_eigh_topk: null pointer");
@@ -1411,7 +1449,7 @@ extern "C" int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, do
   if (RL > MAXRPW * TW) return am::fail(AM_EINVAL, "am_eigh_topk: D too large for the cluster path");
   TopWork w;
   carve_top(d_work, n, P, &w);
-  TriOut out{w.V, w.tau, w.d, w.e, (long long *)w.dbg};
+  TriOut out{w.V, w.tau, w.d, w.e, (long long *)w.dbg, d_started, started_value};
 
   // 1. tridiagonalisation (one cluster of 16 CTAs)
   {

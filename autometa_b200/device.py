@@ -347,8 +347,12 @@ TOPK_MAX_D = 576
 TOPK_MAX_P = 128
 
 
-def eigh_topk(A, P: int):
+def eigh_topk(A, P: int, started=None, started_value: int = 0):
     """Leading ``P`` eigenpairs of symmetric ``A`` (descending) and the trace.
+
+    ``started`` (int32 device tensor, 1 element) receives ``started_value`` when the tridiagonalisation cluster is
+    resident (``am_eigh_topk_signal``) — and in any case once the solve has been queued behind it, so that a
+    stream waiting on it can never hang when another solver path is taken.
 
     Cluster/DSMEM tridiagonalisation path for 3 <= D <= 576 and P <= 128; other shapes
     go through the full Jacobi solver (``eigh_desc``) and are cut to P."""
@@ -357,6 +361,8 @@ def eigh_topk(A, P: int):
     dev = A.device
     D = A.shape[0]
     if _topk_state.get("disabled") or not (3 <= D <= TOPK_MAX_D and 1 <= P <= min(D, TOPK_MAX_P)):
+        if started is not None:
+            started.fill_(int(started_value))
         evals, evecs = eigh_desc(A)
         return evals[:P].contiguous(), evecs[:P].contiguous(), torch.clamp(evals, min=0.0).sum().reshape(1)
     with L.on_device(dev):
@@ -364,8 +370,8 @@ def eigh_topk(A, P: int):
         evecs = torch.empty((P, D), dtype=torch.float64, device=dev)
         trace = torch.empty(1, dtype=torch.float64, device=dev)
         work = _work(dev, L.lib.am_eigh_topk_work_bytes(D, P), "eigtop")
-        rc = L.lib.am_eigh_topk(L.t_ptr(A), D, P, L.t_ptr(evals), L.t_ptr(evecs), L.t_ptr(trace),
-                                L.t_ptr(work), L.stream_ptr(dev))
+        rc = L.lib.am_eigh_topk_signal(L.t_ptr(A), D, P, L.t_ptr(evals), L.t_ptr(evecs), L.t_ptr(trace),
+                                       L.t_ptr(work), L.t_ptr(started), int(started_value), L.stream_ptr(dev))
         if rc == L.AM_ECUDA and not _topk_state.get("disabled"):
             # e.g. a 16-CTA cluster cannot be scheduled on this part: use the device Jacobi solver
             # from now on (still a CUDA path; there is no CPU fallback)
@@ -376,6 +382,8 @@ def eigh_topk(A, P: int):
         elif rc != L.AM_OK:
             L.check(rc)
         if _topk_state.get("disabled"):
+            if started is not None:
+                started.fill_(int(started_value))
             evals_all, evecs_all = eigh_desc(A)
             return (evals_all[:P].contiguous(), evecs_all[:P].contiguous(),
                     torch.clamp(evals_all, min=0.0).sum().reshape(1))

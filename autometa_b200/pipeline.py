@@ -176,7 +176,7 @@ def _fit(packed, counts, stats, method, row_index, col_index, group, distributed
                 row_index=row_index, col_index=col_index, stats=tail, n_total=n_t, R=R, counts=counts)
 
 
-def _project(st, n_components, mark, eig_owner=None, eig_group=None):
+def _project(st, n_components, mark, eig_owner=None, eig_group=None, started=None, started_value=0):
     """Stage 2 — top-P eigenpairs of the covariance (N-independent, latency-bound) and the scores.
 
     ``eig_owner`` (a rank of ``eig_group``): only that rank solves the eigenproblem and broadcasts
@@ -190,13 +190,13 @@ def _project(st, n_components, mark, eig_owner=None, eig_group=None):
     dev = C.device
     P = min(n_components, Dout)
     if eig_owner is None:
-        evals, comps, total = _dev.eigh_topk(C, P)
+        evals, comps, total = _dev.eigh_topk(C, P, started, started_value)
     else:
         import torch.distributed as dist
 
         buf = torch.empty(P + P * Dout + 1, dtype=torch.float64, device=dev)
         if dist.get_rank(eig_group) == eig_owner:
-            evals, comps, total = _dev.eigh_topk(C, P)
+            evals, comps, total = _dev.eigh_topk(C, P, started, started_value)
             buf[:P] = evals
             buf[P : P + P * Dout] = comps.reshape(-1)
             buf[P + P * Dout :] = total.reshape(-1)
@@ -312,10 +312,17 @@ class FeatureStream:
         self.n_submitted = 0
         self.eig_group = None
         self.world = 1
+        self.rank = 0
+        # "the tridiagonalisation cluster of pass i is resident": stage 1 of pass i+1 waits for it (a stream-level
+        # wait on this word), because its first kernel fills every SM for its whole duration and the cluster —
+        # ready a few microseconds later, behind an event — would otherwise queue behind it
+        self.started = None
+        self.wait_value = 0
         if distributed and spread_eigh:
             import torch.distributed as dist
 
             self.world = dist.get_world_size(group)
+            self.rank = dist.get_rank(group)
             if self.world > 1:
                 ranks = list(range(dist.get_world_size())) if group is None else dist.get_process_group_ranks(group)
                 self.eig_group = dist.new_group(ranks=ranks)  # collective call: every rank constructs the stream
@@ -341,7 +348,12 @@ class FeatureStream:
         with torch.cuda.device(self.dev):
             cur = torch.cuda.current_stream(self.dev)
             self.sA.wait_stream(cur)  # inputs produced on the caller's stream
+            if self.started is None:
+                self.started = torch.zeros(1, dtype=torch.int32, device=self.dev)
+                torch.cuda.current_stream(self.dev).synchronize()
             with torch.cuda.stream(self.sA):
+                if self.wait_value:
+                    L.check(L.lib.am_stream_wait_geq(L.stream_ptr(self.dev), L.t_ptr(self.started), self.wait_value))
                 mark("start")
                 counts, present, row_sum = _dev.count_packed(packed, self.k)
                 mark("count")
@@ -352,10 +364,14 @@ class FeatureStream:
             self.sB.wait_event(evA)
             owner = (self.n_submitted % self.world) if self.eig_group is not None else None
             self.n_submitted += 1
+            solves_here = self.depth > 1 and (owner is None or owner == self.rank)
             with torch.cuda.stream(self.sB):
-                res = _project(st, self.P, mark, owner, self.eig_group)
+                res = _project(st, self.P, mark, owner, self.eig_group, self.started if solves_here else None,
+                               self.n_submitted)
                 evB = torch.cuda.Event()
                 evB.record(self.sB)
+            # the next pass's stage 1 is held until this pass's cluster is resident (only where it runs)
+            self.wait_value = self.n_submitted if solves_here else 0
             self.inflight.append((packed, st, res, evB, row_sum, present))
 
     def _retire(self):

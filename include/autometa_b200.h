@@ -290,6 +290,15 @@ int am_eigh(const double *d_A, int D, double *d_evals, double *d_evecs,
  * with the svd_flip sign; d_trace[1] (may be NULL) = sum of ALL eigenvalues (= trace), the
  * denominator of explained_variance_ratio_ (_pca.py:645-646). */
 int64_t am_eigh_topk_work_bytes(int D, int P);
+/* am_eigh_topk that also tells when its first kernel — the 16-CTA tridiagonalisation cluster — is RESIDENT:
+ * CTA 0 stores started_value to *d_started (device memory, 4-byte aligned) as its first action.  Paired with
+ * am_stream_wait_geq on another stream, it lets the caller start an SM-filling kernel only once the cluster has
+ * its SMs, so that the two run side by side instead of the cluster queueing behind the persistent kernel. */
+int am_eigh_topk_signal(const double *d_A, int D, int P, double *d_evals, double *d_evecs,
+                        double *d_trace, void *d_work, uint32_t *d_started, uint32_t started_value,
+                        void *stream);
+/* Hold `stream` until *d_flag >= value (cuStreamWaitValue32: a stream-level wait, no kernel spins). */
+int am_stream_wait_geq(void *stream, const uint32_t *d_flag, uint32_t value);
 int am_eigh_topk(const double *d_A, int D, int P, double *d_evals, double *d_evecs,
                  double *d_trace, void *d_work, void *stream);
 /* Tensor-core projection from the digit planes (tcgen05 kind::i8, K-major operands):
