@@ -176,34 +176,35 @@ def _fit(packed, counts, stats, method, row_index, col_index, group, distributed
                 row_index=row_index, col_index=col_index, stats=tail, n_total=n_t, R=R, counts=counts)
 
 
-def _project(st, n_components, mark, eig_owner=None, eig_group=None, started=None, started_value=0):
-    """Stage 2 — top-P eigenpairs of the covariance (N-independent, latency-bound) and the scores.
-
-    ``eig_owner`` (a rank of ``eig_group``): only that rank solves the eigenproblem and broadcasts
-    ``[eigenvalues | components | trace]`` (P + P D + 1 doubles, 0.2 MB); the others receive.  The covariance is
-    bit-identical on every rank after the all-reduce, so this is the same result as the replicated solve
-    — ``FeatureStream`` uses it to spread the eigensolves of the passes in flight over the GPUs."""
+def _eig(st, n_components, started=None, started_value=0, pack=False):
+    """Stage 2a — top-P eigenpairs of the covariance (N-independent, latency-bound).  ``pack``: also return them
+    as one buffer ``[eigenvalues | components | trace]`` (P + P D + 1 doubles, 0.2 MB) ready to be broadcast."""
     import torch
 
-    C, mu, planes, e, center, X = st["C"], st["mu"], st["planes"], st["e"], st["center"], st["X"]
-    n_out, Dout, side = st["n_out"], st["Dout"], st["side"]
-    dev = C.device
+    C, Dout = st["C"], st["Dout"]
     P = min(n_components, Dout)
-    if eig_owner is None:
-        evals, comps, total = _dev.eigh_topk(C, P, started, started_value)
-    else:
-        import torch.distributed as dist
+    evals, comps, total = _dev.eigh_topk(C, P, started, started_value)
+    if not pack:
+        return evals, comps, total
+    buf = torch.empty(P + P * Dout + 1, dtype=torch.float64, device=C.device)
+    buf[:P] = evals
+    buf[P : P + P * Dout] = comps.reshape(-1)
+    buf[P + P * Dout :] = total.reshape(-1)
+    return buf
 
-        buf = torch.empty(P + P * Dout + 1, dtype=torch.float64, device=dev)
-        if dist.get_rank(eig_group) == eig_owner:
-            evals, comps, total = _dev.eigh_topk(C, P, started, started_value)
-            buf[:P] = evals
-            buf[P : P + P * Dout] = comps.reshape(-1)
-            buf[P + P * Dout :] = total.reshape(-1)
-        dist.broadcast(buf, src=dist.get_global_rank(eig_group, eig_owner) if eig_group is not None else eig_owner,
-                       group=eig_group)
-        evals, comps, total = buf[:P], buf[P : P + P * Dout].view(P, Dout), buf[P + P * Dout :]
-    mark("eigh")
+
+def _unpack_eig(buf, P, Dout):
+    return buf[:P], buf[P : P + P * Dout].view(P, Dout), buf[P + P * Dout :]
+
+
+def _scores(st, evals, comps, total, mark):
+    """Stage 2b — the scores from the digit planes (or the fp64 rows) and the result record."""
+    import torch
+
+    mu, planes, e, center, X = st["mu"], st["planes"], st["e"], st["center"], st["X"]
+    n_out, Dout, side = st["n_out"], st["Dout"], st["side"]
+    dev = st["C"].device
+    P = comps.shape[0]
     evals = torch.clamp(evals, min=0.0)
     if n_out == 0:
         scores = torch.empty((0, P), dtype=torch.float64, device=dev)
@@ -220,6 +221,14 @@ def _project(st, n_components, mark, eig_owner=None, eig_group=None, started=Non
     return dict(scores=scores, explained_variance=evals, explained_variance_ratio=evals / total,
                 components=comps, mean=mu, row_index=st["row_index"], col_index=st["col_index"], normalized=X,
                 stats=st["stats"], n_total=st["n_total"])
+
+
+def _project(st, n_components, mark):
+    """Stage 2 on one stream: eigensolve, then scores (the serial pass; every rank solves the same, bit-identical
+    covariance, so no exchange is needed)."""
+    evals, comps, total = _eig(st, n_components)
+    mark("eigh")
+    return _scores(st, evals, comps, total, mark)
 
 
 def _fit_project(packed, counts, stats, method, n_components, row_index, col_index, group, distributed, mark,
@@ -285,11 +294,12 @@ class FeatureStream:
     """Throughput mode: assemblies (or partitions of one) featurised back to back with up to ``depth`` of them
     in flight on two streams.
 
-    A pass has two parts of very different shape: stage 1 (count -> normalise -> Gram; all the work that grows
-    with the assembly, every SM busy) and stage 2 (top-P eigenpairs of the 512 x 512 covariance + scores;
-    a latency-bound chain of small kernels, 16 SMs for most of its 1.2 ms).  Run one after the other the chip
-    idles through stage 2; here stage 1 of pass i+1 is queued on stream A while stage 2 of pass i runs on the
-    (higher-priority) stream B, so the eigensolve hides behind the next pass's counting.  Results are
+    A pass has parts of very different shape: stage 1 (count -> normalise -> Gram; all the work that grows
+    with the assembly, every SM busy), the eigensolve (top-P eigenpairs of the 512 x 512 covariance; a
+    latency-bound chain of small kernels, 16 SMs for most of its 1.2 ms) and the projection.  Run one after the
+    other the chip idles through the eigensolve; here stage 1 of pass i+1 is queued on stream A while the
+    eigensolve of pass i runs on stream B and its projection on stream C (both higher priority), so the
+    eigensolve hides behind the next pass's counting.  Results are
     identical to ``featurise`` (same kernels, same order within a pass); the optimistic am_clr tests are read
     back when a pass retires and the rare failing pass is redone by ``featurise``."""
 
@@ -327,8 +337,9 @@ class FeatureStream:
                 ranks = list(range(dist.get_world_size())) if group is None else dist.get_process_group_ranks(group)
                 self.eig_group = dist.new_group(ranks=ranks)  # collective call: every rank constructs the stream
         lo, hi = torch.cuda.Stream.priority_range()  # (lowest, highest): numerically hi <= lo
-        self.sA = torch.cuda.Stream(device=self.dev, priority=lo)
-        self.sB = torch.cuda.Stream(device=self.dev, priority=hi)
+        self.sA = torch.cuda.Stream(device=self.dev, priority=lo)   # stage 1: count -> normalise -> Gram
+        self.sB = torch.cuda.Stream(device=self.dev, priority=hi)   # this rank's eigensolves
+        self.sC = torch.cuda.Stream(device=self.dev, priority=hi)   # (broadcast +) projection, in pass order
         self.inflight = []
         self.done = []
 
@@ -361,17 +372,35 @@ class FeatureStream:
                           mark, False)
                 evA = torch.cuda.Event()
                 evA.record(self.sA)
-            self.sB.wait_event(evA)
             owner = (self.n_submitted % self.world) if self.eig_group is not None else None
             self.n_submitted += 1
-            solves_here = self.depth > 1 and (owner is None or owner == self.rank)
-            with torch.cuda.stream(self.sB):
-                res = _project(st, self.P, mark, owner, self.eig_group, self.started if solves_here else None,
-                               self.n_submitted)
+            solves_here = owner is None or owner == self.rank
+            P, Dout = min(self.P, st["Dout"]), st["Dout"]
+            eig = None
+            if solves_here:
+                # stream B holds nothing but this rank's own eigensolves, back to back: it never waits for a peer
+                self.sB.wait_event(evA)
+                with torch.cuda.stream(self.sB):
+                    eig = _eig(st, self.P, self.started if self.depth > 1 else None, self.n_submitted,
+                               pack=owner is not None)
+                    evE = torch.cuda.Event()
+                    evE.record(self.sB)
+                self.sC.wait_event(evE)
+            else:
+                self.sC.wait_event(evA)
+            with torch.cuda.stream(self.sC):
+                if owner is not None:
+                    import torch.distributed as dist
+
+                    buf = eig if solves_here else torch.empty(P + P * Dout + 1, dtype=torch.float64, device=self.dev)
+                    dist.broadcast(buf, src=dist.get_global_rank(self.eig_group, owner), group=self.eig_group)
+                    eig = _unpack_eig(buf, P, Dout)
+                mark("eigh")
+                res = _scores(st, eig[0], eig[1], eig[2], mark)
                 evB = torch.cuda.Event()
-                evB.record(self.sB)
+                evB.record(self.sC)
             # the next pass's stage 1 is held until this pass's cluster is resident (only where it runs)
-            self.wait_value = self.n_submitted if solves_here else 0
+            self.wait_value = self.n_submitted if (solves_here and self.depth > 1) else 0
             self.inflight.append((packed, st, res, evB, row_sum, present))
 
     def _retire(self):
