@@ -426,7 +426,7 @@ def main():
     ap.add_argument("--no-weak", action="store_true", help="N>1: skip the extra weak-scaling measurement")
     ap.add_argument("--norm", default=None, choices=["am_clr", "clr", "ilr"])
     ap.add_argument("--pipeline-depth", type=int, default=0,
-                    help="steps in flight in the timed region (0 = max(2, N + 1); 1 = strictly one step at a time)")
+                    help="steps in flight in the timed region (0 = max(3, N + 2); 1 = strictly one step at a time)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -479,7 +479,7 @@ def main():
     t_load = time.time()
     ms_serial, stage_ms, launches_serial, _ = time_steps(torch, dist, pipeline, L, packed, args.norm, args.steps,
                                                          args.warmup, distributed, dev)
-    depth = args.pipeline_depth if args.pipeline_depth > 0 else max(2, world + 1)
+    depth = args.pipeline_depth if args.pipeline_depth > 0 else max(3, world + 2)
     if depth > 1:
         ms_per_step, launches, tt0, tt1 = time_pipelined(torch, dist, pipeline, L, packed, args.norm, args.steps,
                                                          args.warmup, distributed, dev, depth)
@@ -642,8 +642,8 @@ def main():
                                + ("; the eigensolve of step i runs on rank i mod N and is broadcast (0.2 MB)"
                                   if (world > 1 and depth > 1) else ""),
                 "pipelining": (f"{depth} steps in flight (pipeline.FeatureStream): count/normalise/Gram of step i+1 on one "
-                               "stream while the eigensolve + projection of step i run on another; all K steps complete "
-                               "inside the timed region; `serial` = one step at a time") if depth > 1 else "none",
+                               "stream while the eigensolve of step i and its projection run on two others; all K "
+                               "steps complete inside the timed region; `serial` = one step at a time") if depth > 1 else "none",
                 "l2": "inputs larger than L2 (0.25 GB codes, 0.41 GB counts, 0.82 GB features per step at N=1); no flush "
                       "in the headline, see `l2_flush_check`",
             },
