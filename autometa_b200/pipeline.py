@@ -173,7 +173,8 @@ def _fit(packed, counts, stats, method, row_index, col_index, group, distributed
     mu = _dev.cov_finish(G, cs, c_fin, n_t)
     mark("gram")
     return dict(C=G, mu=mu, planes=planes, e=e, center=center, X=X, n_out=n_out, Dout=Dout, side=side,
-                row_index=row_index, col_index=col_index, stats=tail, n_total=n_t, R=R, counts=counts)
+                row_index=row_index, col_index=col_index, stats=tail, n_total=n_t, R=R, counts=counts,
+                n_and_stats=R[GG + D :])  # [row count | presence flags | all-NA rows]: one read-back
 
 
 def _eig(st, n_components, started=None, started_value=0, pack=False):
@@ -220,7 +221,7 @@ def _scores(st, evals, comps, total, mark):
     mark("project")
     return dict(scores=scores, explained_variance=evals, explained_variance_ratio=evals / total,
                 components=comps, mean=mu, row_index=st["row_index"], col_index=st["col_index"], normalized=X,
-                stats=st["stats"], n_total=st["n_total"])
+                stats=st["stats"], n_total=st["n_total"], n_and_stats=st["n_and_stats"])
 
 
 def _project(st, n_components, mark):
@@ -267,10 +268,10 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
         res = _fit_project(packed, counts, (present, row_sum), method, n_components, None, None, group,
                            distributed, mark, overlap)
         D = counts.shape[1]
-        st = res["stats"].cpu().numpy()  # the only host sync: after everything has been queued
+        back = res["n_and_stats"].cpu().numpy()  # the only host sync: after everything has been queued
+        n_total, st = float(back[0]), back[1:]
         present_g = st[:D] > 0
         cols_ok, rows_ok = bool(present_g.all()), bool(st[D] == 0)
-        n_total = float(res["n_total"].item()) if distributed else float(packed.n_contigs)
         if method != "am_clr":
             if n_total > 0 and not rows_ok:
                 raise ValueError("Input matrix cannot have rows with all zeros")
@@ -282,6 +283,7 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
         out = res
         out.pop("stats")
         out.pop("n_total")
+        out.pop("n_and_stats")
         X = out.pop("normalized")
         if keep:
             if distributed:
@@ -409,9 +411,9 @@ class FeatureStream:
         packed, st, res, evB, row_sum, present = self.inflight.pop(0)
         evB.synchronize()
         D = st["counts"].shape[1]
-        flags = res["stats"].cpu().numpy()
+        back = st["n_and_stats"].cpu().numpy()  # the one host read of the pass
+        n_total, flags = float(back[0]), back[1:]
         cols_ok, rows_ok = bool((flags[:D] > 0).all()), bool(flags[D] == 0)
-        n_total = float(res["n_total"].item()) if self.distributed else float(packed.n_contigs)
         if n_total > 0 and not (rows_ok and (cols_ok or self.method != "am_clr")):
             # rare: redo this pass on the general path (row / column gathers, or the clr / ilr error).  The
             # library's scratch buffers are shared per device: let the passes in flight finish first
@@ -421,6 +423,7 @@ class FeatureStream:
         else:
             res.pop("stats")
             res.pop("n_total")
+            res.pop("n_and_stats")
             X = res.pop("normalized")
             if self.keep:
                 res.update(counts=st["counts"], normalized=X, col_present=present, row_sum=row_sum)

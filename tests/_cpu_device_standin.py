@@ -120,7 +120,7 @@ def cov_finish(G, colsum, center, n_t):
     return mu.clone()
 
 
-def eigh_topk(C, P):
+def eigh_topk(C, P, started=None, started_value=0):
     if not np.all(np.isfinite(C.numpy())):
         D = C.shape[0]
         return torch.zeros(P, dtype=torch.float64), torch.zeros((P, D), dtype=torch.float64), torch.ones(1, dtype=torch.float64)
