@@ -217,5 +217,8 @@ extern "C" int am_cluster_metrics(const int64_t *d_labels, int64_t n_points, con
   AM_LAUNCHED("median_kernel");
   AM_CUDA(cudaMemcpyAsync(d_present, b.present, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
   AM_CUDA(cudaMemcpyAsync(d_single, b.single, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  // leave the WHOLE workspace zeroed (the marker table already is: marker_count_kernel clears what it reads), so
+  // that one zero-filled buffer can serve sweeps of any (n, M) without a per-sweep n x M memset
+  AM_CUDA(cudaMemsetAsync(b.cnt, 0, (size_t)((char *)b.table - (char *)b.cnt), st));
   return AM_OK;
 }

@@ -472,6 +472,24 @@ class EpsSweep:
         return self.labels[: self.n]
 
 
+_metrics_work_cache: Dict[int, "torch.Tensor"] = {}
+
+
+def _metrics_work(device, nbytes: int):
+    """The marker scratch of ``am_cluster_metrics`` is a dense [points x markers] table that the kernels leave
+    zeroed (every entry they touch is cleared again with atomicExch), so ONE zero-filled buffer per device is
+    allocated, grown when a larger sweep comes, and reused by every ``ClusterMetrics`` — ``get_clusters`` and the
+    taxon drivers build one per sweep, and a fresh n x M memset per call would scale with n * M although only
+    the non-zero markers are ever touched.  (Sweeps on one device run one after the other on one stream.)"""
+    import torch
+
+    t = _metrics_work_cache.get(device.index)
+    if t is None or t.numel() < nbytes:
+        t = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _metrics_work_cache[device.index] = t
+    return t
+
+
 class ClusterMetrics:
     """Device-side add_metrics + apply_binning_metrics_filter + median completeness for the sweep
     (reference binning/utilities.py:125-262, recursive_dbscan.py:180-192)."""
@@ -501,8 +519,7 @@ class ClusterMetrics:
             self.present = torch.empty(n1, dtype=torch.int32, device=device)
             self.single = torch.empty(n1, dtype=torch.int32, device=device)
             self.summary = torch.zeros(4, dtype=torch.float64, device=device)
-            self.work = torch.zeros(max(256, L.lib.am_metrics_work_bytes(self.n, self.M)), dtype=torch.uint8,
-                                    device=device)
+            self.work = _metrics_work(device, max(256, L.lib.am_metrics_work_bytes(self.n, self.M)))
 
     def compute(self, labels, n_clusters):
         """Queue the metrics of one eps; returns the device summary [n_clusters, median, n_pass]."""

@@ -344,6 +344,10 @@ class FeatureStream:
         self.sC = torch.cuda.Stream(device=self.dev, priority=hi)   # (broadcast +) projection, in pass order
         self.inflight = []
         self.done = []
+        # host-side accounting: seconds spent queueing passes (submit, without the waits) and waiting for the
+        # oldest pass in flight to finish (back-pressure): tells a launch-bound stream from a GPU-bound one
+        self.host_queue_s = 0.0
+        self.host_wait_s = 0.0
 
     #: SMs the statically split kernels of stage 1 (Gram, projection) leave to the tridiagonalisation cluster of
     #: the pass before (16 CTAs, one per SM): without it the Gram's last CTAs wait for the cluster to end and
@@ -353,7 +357,11 @@ class FeatureStream:
     def submit(self, packed: PackedAssembly, marks=None):
         import torch
 
+        import time
+
         mark = marks if marks is not None else (lambda name: None)
+        t_in = time.perf_counter()
+        w_in = self.host_wait_s
         if self.depth > 1 and L.lib.am_get_reserved_sms() != self.RESERVED_SMS:
             L.check(L.lib.am_set_reserved_sms(self.RESERVED_SMS))
         while len(self.inflight) >= self.depth:
@@ -404,12 +412,17 @@ class FeatureStream:
             # the next pass's stage 1 is held until this pass's cluster is resident (only where it runs)
             self.wait_value = self.n_submitted if (solves_here and self.depth > 1) else 0
             self.inflight.append((packed, st, res, evB, row_sum, present))
+        self.host_queue_s += (time.perf_counter() - t_in) - (self.host_wait_s - w_in)
 
     def _retire(self):
         import torch
 
+        import time
+
         packed, st, res, evB, row_sum, present = self.inflight.pop(0)
+        t_w = time.perf_counter()
         evB.synchronize()
+        self.host_wait_s += time.perf_counter() - t_w
         D = st["counts"].shape[1]
         back = st["n_and_stats"].cpu().numpy()  # the one host read of the pass
         n_total, flags = float(back[0]), back[1:]

@@ -387,6 +387,7 @@ def time_pipelined(torch, dist, pipeline, L, packed, norm, steps, warmup, distri
     torch.cuda.synchronize()
     l0 = L.launch_count()
     t0 = time.time()
+    fs.host_queue_s = fs.host_wait_s = 0.0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(steps):
@@ -402,8 +403,12 @@ def time_pipelined(torch, dist, pipeline, L, packed, norm, steps, warmup, distri
     tp = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    host = {"queue_ms_per_step": round(fs.host_queue_s / steps * 1e3, 4),
+            "wait_ms_per_step": round(fs.host_wait_s / steps * 1e3, 4),
+            "what": "rank 0's host time per step spent queueing work (Python + launches + NCCL enqueues) and waiting "
+                    "for the oldest step in flight; queue_ms ~ ms_per_step means the stream is launch-bound"}
     del fs
-    return float(tp.item()) / steps, launches, t0, t1
+    return float(tp.item()) / steps, launches, t0, t1, host
 
 
 def main():
@@ -481,10 +486,10 @@ def main():
                                                          args.warmup, distributed, dev)
     depth = args.pipeline_depth if args.pipeline_depth > 0 else max(3, world + 2)
     if depth > 1:
-        ms_per_step, launches, tt0, tt1 = time_pipelined(torch, dist, pipeline, L, packed, args.norm, args.steps,
-                                                         args.warmup, distributed, dev, depth)
+        ms_per_step, launches, tt0, tt1, host_acct = time_pipelined(torch, dist, pipeline, L, packed, args.norm,
+                                                                    args.steps, args.warmup, distributed, dev, depth)
     else:
-        ms_per_step, launches, tt0, tt1 = ms_serial, launches_serial, t_load, time.time()
+        ms_per_step, launches, tt0, tt1, host_acct = ms_serial, launches_serial, t_load, time.time(), None
     clocks = sampler.stop(tt0, tt1, t_load) if rank == 0 else None
     value = job_bp / (ms_per_step * 1e-3) / 1e9
     serial = {"value": job_bp / (ms_serial * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_serial,
@@ -511,7 +516,7 @@ def main():
         ms_ws, stage_w, _, _ = time_steps(torch, dist, pipeline, L, packed_w, args.norm, ws, 3, distributed, dev)
         ms_w = ms_ws
         if depth > 1:
-            ms_w, _, _, _ = time_pipelined(torch, dist, pipeline, L, packed_w, args.norm, ws, 3, distributed, dev, depth)
+            ms_w, _, _, _, _ = time_pipelined(torch, dist, pipeline, L, packed_w, args.norm, ws, 3, distributed, dev, depth)
         weak = {"value": world * asm_w.total_bp / (ms_w * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_w,
                 "serial_ms_per_step": ms_ws,
                 "per_gpu": f"{asm_w.n_contigs} contigs / {asm_w.total_bp / 1e9:.3f} Gbp",
@@ -652,7 +657,7 @@ def main():
             "n_independent_note": "top-50 eigenpairs of the 512x512 covariance (tridiagonalisation + bisection + inverse "
                                   "iteration + back-transformation): the same time whatever the assembly size, replicated "
                                   "on every rank; the longest stage of the step, not a bandwidth-bound one",
-            "l2_flush_check": flush_check, "serial": serial, "weak": weak,
+            "l2_flush_check": flush_check, "serial": serial, "host": host_acct, "weak": weak,
             "cpu_baseline": cpu, "e2e": e2e, "sweep": sweep,
             "gpu_launches": int(launches), "clocks": clocks,
         }

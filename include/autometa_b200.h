@@ -342,7 +342,8 @@ int am_iota_i32(int32_t *d_v, int64_t n, void *stream);
  *   outputs per cluster c < n_clusters: completeness, purity (NaN when nothing present),
  *   coverage / GC sigma (ddof 1, NaN for singletons), present / single-copy marker counts;
  *   d_summary[3] = {n_clusters, median completeness of passing clusters (-inf if none), n passing}.
- * d_work: am_metrics_work_bytes(n_points, M) bytes, zero-filled once by the caller. */
+ * d_work: am_metrics_work_bytes(n_points, M) bytes, zero-filled once by the caller; the call leaves it
+ * zero-filled again, so one buffer (of the largest size) can serve sweeps of any (n_points, M). */
 int64_t am_metrics_work_bytes(int64_t n_points, int n_markers);
 int am_cluster_metrics(const int64_t *d_labels, int64_t n_points, const int32_t *d_n_clusters,
                        const int32_t *d_marker_rows, const int32_t *d_marker_cols,
