@@ -82,6 +82,9 @@ _SIGS = {
     "am_stats_pack": (C.c_int, [_p, _i32, _p, _i64, _p, _p]),
     "am_gram_recenter": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p]),
     "am_table_stats": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p]),
+    "am_axpb_f64": (C.c_int, [_p, _i64, _f64, _f64, _p]),
+    "am_zero_async": (C.c_int, [_p, _i64, _p]),
+    "am_pca_finish": (C.c_int, [_p, _p, _i32, _p, _p]),
     "am_gram_work_bytes": (_i64, [_i32]),
     "am_gram": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
     "am_eigh_work_bytes": (_i64, [_i32]),

@@ -498,6 +498,25 @@ table_stats_kernel(const int32_t *__restrict__ counts, const int64_t *__restrict
   }
 }
 
+// Small fp64 vector helpers for the launch-lean pass (pipeline.FeatureStream queues a pass with ~15 C calls and
+// no tensor-library kernel in between; at 25k contigs per GPU the host-side cost of queueing, not the GPU, bounds
+// the stream): x[i] = x[i] * a + b, and the tail of the PCA fit — eigenvalues clamped at zero (_pca.py:630) and
+// explained_variance_ratio_ = eigenvalue / trace (:645-646).
+__global__ void axpb_kernel(double *__restrict__ x, int64_t n, double a, double b) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = fma(x[i], a, b);
+}
+
+__global__ void pca_finish_kernel(double *__restrict__ evals, const double *__restrict__ total, int P,
+                                  double *__restrict__ ratio) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) {
+    const double v = fmax(evals[i], 0.0);
+    evals[i] = v;
+    ratio[i] = v / total[0];
+  }
+}
+
 extern "C" int am_stats_pack(const int32_t *d_col_present, int ncols, const int32_t *d_row_sum, int64_t n_contigs,
                              double *d_out, void *stream) {
   if (!d_col_present || !d_out || ncols < 1 || n_contigs < 0 || (n_contigs > 0 && !d_row_sum))
@@ -531,5 +550,27 @@ extern "C" int am_table_stats(const int32_t *d_counts, const int64_t *d_row_inde
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_rows + 7) / 8, (int64_t)am::num_sms() * 8));
   table_stats_kernel<<<grid, 256, 0, st>>>(d_counts, d_row_index, n_rows, D, d_col_present, d_row_sum);
   AM_LAUNCHED("table_stats_kernel");
+  return AM_OK;
+}
+
+extern "C" int am_axpb_f64(double *d_x, int64_t n, double a, double b, void *stream) {
+  if (n < 0 || (n > 0 && !d_x)) return am::fail(AM_EINVAL, "am_axpb_f64: bad args");
+  if (n == 0) return AM_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 1024);
+  axpb_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, n, a, b);
+  AM_LAUNCHED("axpb_kernel");
+  return AM_OK;
+}
+
+extern "C" int am_zero_async(void *d_ptr, int64_t nbytes, void *stream) {
+  if (nbytes < 0 || (nbytes > 0 && !d_ptr)) return am::fail(AM_EINVAL, "am_zero_async: bad args");
+  if (nbytes) AM_CUDA(cudaMemsetAsync(d_ptr, 0, (size_t)nbytes, (cudaStream_t)stream));
+  return AM_OK;
+}
+
+extern "C" int am_pca_finish(double *d_evals, const double *d_total, int P, double *d_ratio, void *stream) {
+  if (P < 1 || !d_evals || !d_total || !d_ratio) return am::fail(AM_EINVAL, "am_pca_finish: bad args");
+  pca_finish_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_evals, d_total, P, d_ratio);
+  AM_LAUNCHED("pca_finish_kernel");
   return AM_OK;
 }

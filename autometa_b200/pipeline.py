@@ -292,6 +292,74 @@ def featurise(packed: PackedAssembly, k: int = 5, method: str = "am_clr", n_comp
         return out
 
 
+class _PassSlot:
+    """Every device buffer one pass of the k = 5 path needs for a given shard shape, allocated once and reused
+    every ``depth`` passes, with the raw pointers resolved once.  A pass is then queued with ~15 C calls and two
+    NCCL calls — no allocation, no tensor-library kernel, no stream context — which is what bounds small shards
+    (1/8 of C2 per GPU: 0.5 ms of GPU work per pass against 0.7 ms of host work through the general wrappers)."""
+
+    def __init__(self, dev, n: int, D: int, method: str, P: int, ns: int):
+        import torch
+
+        self.n, self.D, self.method, self.P, self.ns = n, D, method, P, ns
+        self.Dout = D - 1 if method == "ilr" else D
+        self.GG = self.Dout * self.Dout
+        f64, i32 = torch.float64, torch.int32
+        e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+        self.counts = e((n, D), i32)
+        self.present = e(D, i32)
+        self.row_sum = e(max(n, 1), i32)
+        self.R = e(self.GG + 2 * D + 2, f64)        # G | cs[D] | n | present[D] | all-NA rows
+        self.zb = e(2 * D, f64)                      # zeros[D] | centre (sample sums, then means)[D]
+        self.sample_out = e((max(ns, 1), D), f64)
+        self.e = e(D, i32)
+        self.sc = e(D, f64)
+        self.X = e((max(n, 1), D), f64)
+        self.planes = e(max(256, L.lib.am_planes_bytes(max(n, 1), D, 6)), torch.int8)
+        self.mu = e(D, f64)
+        self.eig = e(P + P * self.Dout + 1 + P, f64)  # eigenvalues | components | trace | ratio
+        self.scores = e((n, P), f64)
+        wb = lambda nbytes: e(max(256, int(nbytes)), torch.uint8)
+        self.w_norm = wb(L.lib.am_normalize_work_bytes(D))
+        self.w_colsum = wb(L.lib.am_colsum_work_bytes(D))
+        self.w_gram = wb(L.lib.am_gram_planes_work_bytes(max(n, 1), self.Dout, 6))
+        self.w_eig = wb(L.lib.am_eigh_topk_work_bytes(self.Dout, P))
+        self.w_proj = wb(L.lib.am_project_planes_work_bytes(self.Dout, 6))
+        p = lambda t: t.data_ptr()
+        GG, Dout = self.GG, self.Dout
+        self.p_counts, self.p_present, self.p_row_sum = p(self.counts), p(self.present), p(self.row_sum)
+        self.p_R = p(self.R)
+        self.p_cs = self.p_R + 8 * GG
+        self.p_nt = self.p_R + 8 * (GG + D)
+        self.p_tail = self.p_R + 8 * (GG + D + 1)
+        self.p_zeros = p(self.zb)
+        self.p_center = p(self.zb) + 8 * D
+        self.p_sample, self.p_e, self.p_sc, self.p_X, self.p_planes, self.p_mu = (
+            p(self.sample_out), p(self.e), p(self.sc), p(self.X), p(self.planes), p(self.mu))
+        self.p_evals = p(self.eig)
+        self.p_comps = self.p_evals + 8 * P
+        self.p_total = self.p_comps + 8 * P * Dout
+        self.p_ratio = self.p_total + 8
+        self.p_scores = p(self.scores)
+        self.p_w_norm, self.p_w_colsum, self.p_w_gram, self.p_w_eig, self.p_w_proj = (
+            p(self.w_norm), p(self.w_colsum), p(self.w_gram), p(self.w_eig), p(self.w_proj))
+        self.bcast = self.eig[: P + P * Dout + 1]
+        self.n_and_stats = self.R[GG + D :]
+
+    def result(self, keep: bool, clone: bool):
+        P, Dout = self.P, self.Dout
+        out = dict(scores=self.scores, explained_variance=self.eig[:P],
+                   explained_variance_ratio=self.eig[P + P * Dout + 1 :],
+                   components=self.eig[P : P + P * Dout].view(P, Dout), mean=self.mu[:Dout], row_index=None,
+                   col_index=None)
+        if keep:
+            out.update(counts=self.counts, normalized=self.X[: self.n, :Dout], col_present=self.present,
+                       row_sum=self.row_sum[: self.n])
+        if clone:  # the slot is reused `depth` passes later: results that outlive it are copies
+            out = {k2: (v.clone() if hasattr(v, "clone") else v) for k2, v in out.items()}
+        return out
+
+
 class FeatureStream:
     """Throughput mode: assemblies (or partitions of one) featurised back to back with up to ``depth`` of them
     in flight on two streams.
@@ -307,7 +375,7 @@ class FeatureStream:
 
     def __init__(self, device, k: int = 5, method: str = "am_clr", n_components: int = 50, group=None,
                  distributed: bool = False, depth: int = 2, keep: bool = False, spread_eigh: bool = True,
-                 on_result=None):
+                 on_result=None, lean: bool = True):
         """``spread_eigh`` (several GPUs): the eigensolve of pass i is done by rank i mod N only and broadcast,
         instead of being replicated on every rank — with N passes in flight each GPU solves one eigenproblem
         per N passes, which removes the replicated, N-independent 1.2 ms from every rank's critical path
@@ -344,10 +412,112 @@ class FeatureStream:
         self.sC = torch.cuda.Stream(device=self.dev, priority=hi)   # (broadcast +) projection, in pass order
         self.inflight = []
         self.done = []
+        self.lean = lean        # k = 5 passes queued from pre-allocated slots with raw C calls (_PassSlot)
+        self.slots = {}
+        self._events, self._ev_i = [], 0
         # host-side accounting: seconds spent queueing passes (submit, without the waits) and waiting for the
         # oldest pass in flight to finish (back-pressure): tells a launch-bound stream from a GPU-bound one
         self.host_queue_s = 0.0
         self.host_wait_s = 0.0
+
+    def _lean_ok(self, packed) -> bool:
+        return (self.lean and self.method in ("am_clr", "clr", "ilr") and self.k == 5 and self.P <= 64
+                and packed.n_contigs > 0)
+
+    def _submit_lean(self, packed):
+        """Queue one pass of the k = 5 path from pre-allocated slot buffers with raw C calls (see _PassSlot);
+        same kernels, same order, same results as ``_fit`` + ``_eig`` + ``_scores``."""
+        import torch
+
+        lib, dev = L.lib, self.dev
+        n, D = packed.n_contigs, 512
+        m = L.NORM_METHODS[self.method]
+        sample = _sample_rows(n, dev, packed._plans)
+        ns = int(sample.numel())
+        slot_i = self.n_submitted % self.depth
+        key = (n, self.method, self.P, ns)
+        slot = self.slots.get(slot_i)
+        if slot is None or slot.key != key:
+            slot = _PassSlot(dev, n, D, self.method, self.P, ns)
+            slot.key = key
+            self.slots[slot_i] = slot
+            torch.cuda.current_stream(dev).synchronize()
+        S = slot
+        plan = _dev.get_count_plan(packed, self.k)
+        bound = _bound_for(packed, self.method, D)
+        Dout, P = S.Dout, min(self.P, S.Dout)
+        sa, sb, sc = self.sA.cuda_stream, self.sB.cuda_stream, self.sC.cuda_stream
+        ck = L.check
+        self.sA.wait_stream(torch.cuda.current_stream(dev))  # inputs produced on the caller's stream
+        if self.wait_value:
+            ck(lib.am_stream_wait_geq(sa, L.t_ptr(self.started), self.wait_value))
+        # ---- stage 1 (stream A)
+        ck(lib.am_zero_async(S.p_R, S.R.numel() * 8, sa))
+        ck(lib.am_zero_async(S.p_zeros, S.zb.numel() * 8, sa))
+        ck(lib.am_zero_async(S.p_present, D * 4, sa))
+        ck(lib.am_count_kmers(L.t_ptr(packed.codes), L.t_ptr(packed.exc_bitmap), L.t_ptr(packed.exc_rank),
+                              L.t_ptr(packed.exc_mask), L.t_ptr(packed.starts), L.t_ptr(plan.items), plan.n_items,
+                              L.t_ptr(plan.multi), plan.n_multi, n, self.k, S.p_counts, S.p_present, S.p_row_sum,
+                              L.t_ptr(plan.work), sa))
+        ck(lib.am_stats_pack(S.p_present, D, S.p_row_sum, n, S.p_tail, sa))
+        if self.method == "ilr":  # the generic ilr kernel has no fused column sums
+            ck(lib.am_normalize(S.p_counts, ns, D, L.t_ptr(sample), None, D, m, S.p_sample, None, None, None, sa))
+            ck(lib.am_colsum(S.p_sample, ns, Dout, S.p_center, S.p_w_colsum, sa))
+        else:
+            ck(lib.am_normalize(S.p_counts, ns, D, L.t_ptr(sample), None, D, m, S.p_sample, S.p_center, None,
+                                S.p_w_norm, sa))
+        ck(lib.am_axpb_f64(S.p_center, D, 1.0 / ns, 0.0, sa))  # sample sums -> provisional centre
+        ck(lib.am_plane_scales(S.p_center, None, float(bound), D, 6, S.p_e, S.p_sc, sa))
+        ck(lib.am_normalize_planes(S.p_counts, n, D, None, m, S.p_X, S.p_cs, S.p_center, S.p_sc, 6, S.p_planes,
+                                   S.p_w_norm, sa))
+        ck(lib.am_axpb_f64(S.p_nt, 1, 0.0, float(n), sa))       # row count
+        ck(lib.am_gram_planes(S.p_planes, n, Dout, 6, S.p_e, S.p_R, S.p_w_gram, sa))
+        c_fin = S.p_center
+        if self.distributed:
+            ck(lib.am_gram_recenter(S.p_R, Dout, S.p_cs, S.p_center, None, S.p_nt, sa))
+            with torch.cuda.stream(self.sA):
+                _dist.allreduce_sum_([S.R], self.group)
+            c_fin = S.p_zeros  # the all-reduced Gram is about the origin
+        ck(lib.am_cov_finish(S.p_R, Dout, S.p_cs, c_fin, S.p_nt, S.p_mu, sa))
+        evA = self._event()
+        evA.record(self.sA)
+        # ---- stage 2a (stream B): this rank's eigensolves only
+        owner = (self.n_submitted % self.world) if self.eig_group is not None else None
+        self.n_submitted += 1
+        solves_here = owner is None or owner == self.rank
+        if solves_here:
+            self.sB.wait_event(evA)
+            ck(lib.am_eigh_topk_signal(S.p_R, Dout, P, S.p_evals, S.p_comps, S.p_total, S.p_w_eig,
+                                       L.t_ptr(self.started) if self.depth > 1 else None, self.n_submitted, sb))
+            evE = self._event()
+            evE.record(self.sB)
+            self.sC.wait_event(evE)
+        else:
+            self.sC.wait_event(evA)
+        # ---- stage 2b (stream C): (broadcast +) ratio, projection
+        if owner is not None:
+            import torch.distributed as dist
+
+            with torch.cuda.stream(self.sC):
+                dist.broadcast(S.bcast, src=dist.get_global_rank(self.eig_group, owner), group=self.eig_group)
+        ck(lib.am_pca_finish(S.p_evals, S.p_total, P, S.p_ratio, sc))
+        ck(lib.am_project_planes(S.p_planes, n, Dout, 6, S.p_e, S.p_center, S.p_mu, S.p_comps, P, S.p_scores,
+                                 S.p_w_proj, sc))
+        evB = self._event()
+        evB.record(self.sC)
+        self.wait_value = self.n_submitted if (solves_here and self.depth > 1) else 0
+        self.inflight.append((packed, S, None, evB, None, None))
+
+    def _event(self):
+        import torch
+
+        # a small ring of reusable events (creating one costs more than recording it)
+        if len(self._events) < 6 * self.depth + 6:
+            ev = torch.cuda.Event()
+            self._events.append(ev)
+            return ev
+        self._ev_i = (self._ev_i + 1) % len(self._events)
+        return self._events[self._ev_i]
 
     #: SMs the statically split kernels of stage 1 (Gram, projection) leave to the tridiagonalisation cluster of
     #: the pass before (16 CTAs, one per SM): without it the Gram's last CTAs wait for the cluster to end and
@@ -364,6 +534,17 @@ class FeatureStream:
         w_in = self.host_wait_s
         if self.depth > 1 and L.lib.am_get_reserved_sms() != self.RESERVED_SMS:
             L.check(L.lib.am_set_reserved_sms(self.RESERVED_SMS))
+        if self.started is None:
+            with torch.cuda.device(self.dev):
+                self.started = torch.zeros(1, dtype=torch.int32, device=self.dev)
+                torch.cuda.current_stream(self.dev).synchronize()
+        if marks is None and self._lean_ok(packed):
+            while len(self.inflight) >= self.depth:
+                self._retire()
+            with L.on_device(self.dev):
+                self._submit_lean(packed)
+            self.host_queue_s += (time.perf_counter() - t_in) - (self.host_wait_s - w_in)
+            return
         while len(self.inflight) >= self.depth:
             self._retire()
         with torch.cuda.device(self.dev):
@@ -423,8 +604,9 @@ class FeatureStream:
         t_w = time.perf_counter()
         evB.synchronize()
         self.host_wait_s += time.perf_counter() - t_w
-        D = st["counts"].shape[1]
-        back = st["n_and_stats"].cpu().numpy()  # the one host read of the pass
+        lean = isinstance(st, _PassSlot)
+        D = st.D if lean else st["counts"].shape[1]
+        back = (st.n_and_stats if lean else st["n_and_stats"]).cpu().numpy()  # the one host read of the pass
         n_total, flags = float(back[0]), back[1:]
         cols_ok, rows_ok = bool((flags[:D] > 0).all()), bool(flags[D] == 0)
         if n_total > 0 and not (rows_ok and (cols_ok or self.method != "am_clr")):
@@ -433,6 +615,8 @@ class FeatureStream:
             with torch.cuda.device(self.dev):
                 torch.cuda.synchronize(self.dev)
                 res = featurise(packed, self.k, self.method, self.P, self.group, self.distributed, keep=self.keep)
+        elif lean:
+            res = st.result(self.keep, clone=self.on_result is None)
         else:
             res.pop("stats")
             res.pop("n_total")

@@ -251,6 +251,12 @@ int am_gram_recenter(double *d_G, int D, const double *d_colsum, const double *d
  * table that arrived as TSV (large_data_mode.py:454-470 subsets counts per taxon before normalising). */
 int am_table_stats(const int32_t *d_counts, const int64_t *d_row_index, int64_t n_rows, int D,
                    int32_t *d_col_present, int32_t *d_row_sum, void *stream);
+/* Helpers of the launch-lean pass (pipeline.FeatureStream): x = x * a + b on an fp64 vector; an async memset;
+ * the tail of the PCA fit — eigenvalues clamped at zero in place (_pca.py:630) and
+ * ratio[i] = eigenvalue[i] / total[0] (_pca.py:645-646). */
+int am_axpb_f64(double *d_x, int64_t n, double a, double b, void *stream);
+int am_zero_async(void *d_ptr, int64_t nbytes, void *stream);
+int am_pca_finish(double *d_evals, const double *d_total, int P, double *d_ratio, void *stream);
 int64_t am_gram_work_bytes(int D);
 int am_gram(const double *d_X, int64_t n_rows, int D, const double *d_mu,
             double *d_G, void *d_work, void *stream);
