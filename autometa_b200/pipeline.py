@@ -19,13 +19,14 @@ from .assembly import HostAssembly, PackedAssembly, pack_device_arrays, pack_pla
 
 
 def _sample_rows(n_out: int, dev, cache: dict):
-    """Strided row sample (<= 2048 rows) for the provisional centre; cached per (n_out, device)."""
+    """Strided row sample (n/32 rows, between 256 and 2048) for the provisional centre; cached per (n_out, device).
+    The centre only has to be near the mean: the Gram correction n (mu - c)(mu - c)^T is 1/ns of G."""
     import torch
 
     key = ("sample", n_out, dev.index)
     t = cache.get(key)
     if t is None:
-        ns = min(n_out, 2048)
+        ns = min(n_out, max(256, min(2048, n_out // 32)))
         t = torch.div(torch.arange(ns, device=dev, dtype=torch.int64) * n_out, ns, rounding_mode="floor")
         cache[key] = t
     return t
