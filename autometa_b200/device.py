@@ -41,17 +41,9 @@ def column_lut(k: int) -> np.ndarray:
 class CountPlan:
     """Device copy of the count work list for one (assembly, k)."""
 
-    def __init__(self, packed: PackedAssembly, k: int, max_item_bases: int = 0):
+    def __init__(self, packed: PackedAssembly, k: int, max_item_bases: int = 32768):
         import torch
 
-        if max_item_bases <= 0:
-            # a work item is counted by ONE warp, so the kernel cannot end before its longest item does
-            # (32 kbp = 16 tiles ~ 80 us on a loaded SM).  Small shards get shorter items: about 4 items per
-            # resident warp (148 SMs x 48 warps), between 4096 and 32768 windows, a multiple of the tile.
-            per_warp = int(packed.lengths.astype(np.int64).sum()) // (148 * 48 * 4) if packed.n_contigs else 0
-            max_item_bases = 4096
-            while max_item_bases * 2 <= min(per_warp, 32768):
-                max_item_bases *= 2
         items, multi = count_plan(packed.lengths, k, max_item_bases)
         if len(items) > 1:
             # longest work items first: warps claim items from an atomic counter, so the tail of the kernel is
