@@ -698,8 +698,9 @@ class HostFeaturiser:
     def describe(self) -> str:
         if self.host_format == "packed":
             return ("pinned host 2-bit codes + exception masks (threaded host packer am_pack_host, 0.25 B/bp) -> H2D "
-                    "-> count -> normalise -> PCA -> D2H scores; back-to-back steps, the H2D copy of step i+1 "
-                    "overlaps the compute of step i")
+                    "-> count -> normalise -> PCA -> D2H scores; back-to-back steps through FeatureStream: the H2D "
+                    "copy of step i+1 on a copy stream, up to 3 steps in flight on the compute streams, the scores "
+                    "of each step read back as it retires")
         return ("pinned host ASCII (1 B/bp) -> H2D -> am_pack_device -> count -> normalise -> PCA -> D2H scores; "
                 "back-to-back steps, the H2D copy of step i+1 overlaps the compute of step i (PCIe-bound)")
 
@@ -714,6 +715,59 @@ class HostFeaturiser:
         with torch.cuda.device(self.dev):
             self._upload(0)
             return self._compute(self.bufs[0], group, distributed)
+
+    def run_stream(self, n_steps: int, group=None, distributed: bool = False, depth: int = 3):
+        """``n_steps`` assemblies back to back through ``FeatureStream`` (packed host format): the H2D copy of step
+        i+1 runs on a copy stream while steps i, i-1, ... are in flight on the compute streams (the eigensolve of one
+        beside the counting of the next; on several GPUs one eigensolve per N steps per GPU), and the scores of
+        every step are read back to pinned host memory as the step retires.  Every step copies its own input from
+        pinned host memory and returns its own scores; nothing is shared between steps but the allocations.
+        Returns the last step's host results."""
+        import torch
+
+        if self.host_format != "packed":
+            return self.run_many(n_steps, group, distributed)
+        with torch.cuda.device(self.dev):
+            nbuf = depth + 1
+            while len(self.bufs) < nbuf:
+                self.bufs.append([torch.empty_like(b) for b in self.bufs[0]])
+            if getattr(self, "copy_stream", None) is None:
+                self.copy_stream = torch.cuda.Stream(device=self.dev)
+            evs = [torch.cuda.Event() for _ in range(nbuf)]
+            cur = torch.cuda.current_stream(self.dev)
+            if self.h_scores is None:
+                self.run(group, distributed)  # sizes the pinned result buffers
+
+            def collect(res):
+                # runs when a step retires (its device work is complete): D2H of its scores on the caller's stream
+                self.h_scores.copy_(res["scores"], non_blocking=True)
+                self.h_ev.copy_(res["explained_variance"], non_blocking=True)
+
+            fs = FeatureStream(self.dev, self.k, self.method, self.P, group=group, distributed=distributed,
+                               depth=depth, on_result=collect)
+            packed = [self._packed(b) for b in self.bufs]
+            for p in packed:
+                if self._plans:
+                    p._plans = self._plans
+
+            def upload(i):
+                slot = i % nbuf
+                # slot's previous user (step i - nbuf) has retired: FeatureStream keeps at most `depth` in flight
+                with torch.cuda.stream(self.copy_stream):
+                    self._upload(slot)
+                    evs[slot].record(self.copy_stream)
+
+            upload(0)
+            for i in range(n_steps):
+                cur.wait_event(evs[i % nbuf])
+                fs.submit(packed[i % nbuf])
+                self._plans = packed[i % nbuf]._plans
+                if i + 1 < n_steps:
+                    upload(i + 1)  # its slot's previous user, step i - depth, retired inside submit(i)
+            fs.drain()
+            cur.synchronize()
+            self.d2h_bytes = self.h_scores.numel() * 8 + self.h_ev.numel() * 8
+        return self.h_scores, self.h_ev
 
     def run_many(self, n_steps: int, group=None, distributed: bool = False):
         """``n_steps`` assemblies back to back with double buffering: the H2D copy of step i+1 runs on

@@ -824,6 +824,23 @@ def test_feature_stream_equals_serial_featurise(torch_cuda):
             assert torch_cuda.equal(g[key], ref[key]), key
 
 
+def test_host_featuriser_paths_agree(torch_cuda):
+    """End-to-end entries from pinned host buffers: packed and ASCII host formats, one call at a time (run),
+    double-buffered (run_many) and through FeatureStream (run_stream) all return the scores of the
+    device-resident pass."""
+    from autometa_b200 import assembly as A, pipeline, synth
+
+    asm = synth.make_assembly(5600, 5600 * 3300, seed=71)
+    ref = pipeline.featurise(A.pack_to_device(asm, device="cuda:0", on_device=True), 5, "am_clr", 50)
+    ref_s, ref_ev = ref["scores"].cpu().numpy(), ref["explained_variance"].cpu().numpy()
+    for fmt in ("packed", "ascii"):
+        hf = pipeline.HostFeaturiser(asm, device="cuda:0", host_format=fmt)
+        for call in (lambda: hf.run(), lambda: hf.run_many(3), lambda: hf.run_stream(5)):
+            s, ev = call()
+            assert np.array_equal(s.numpy(), ref_s) and np.array_equal(ev.numpy(), ref_ev), fmt
+        assert hf.h2d_bytes > 0 and hf.d2h_bytes == ref_s.nbytes + ref_ev.nbytes
+
+
 # ----------------------------------------------------------------------------- embed() through its own call site
 def test_embed_pca_stage_matches_reference_embed_call(torch_cuda, golden_pca, tmp_path, monkeypatch):
     """The reference's embed() was run (tests/golden/make_golden.py) with a stub ``tsne.bh_sne`` that returns
