@@ -377,11 +377,17 @@ def eigh_topk(A, P: int, started=None, started_value: int = 0):
         rc = L.lib.am_eigh_topk_signal(L.t_ptr(A), D, P, L.t_ptr(evals), L.t_ptr(evecs), L.t_ptr(trace),
                                        L.t_ptr(work), L.t_ptr(started), int(started_value), L.stream_ptr(dev))
         if rc == L.AM_ECUDA and not _topk_state.get("disabled"):
-            # e.g. a 16-CTA cluster cannot be scheduled on this part: use the device Jacobi solver
-            # from now on (still a CUDA path; there is no CPU fallback)
+            # e.g. a 16-CTA cluster cannot be scheduled on this part.  The device Jacobi solver (am_eigh) gives the
+            # same eigenpairs 65x slower (82 ms against 1.25 ms at D = 512): a silent switch would be a performance
+            # cliff, so it has to be asked for (still a CUDA path; there is no CPU fallback)
+            import os
             import warnings
 
-            warnings.warn("am_eigh_topk unavailable (%s); using am_eigh" % L.lib.am_last_error().decode(errors="replace"))
+            msg = L.lib.am_last_error().decode(errors="replace")
+            if os.environ.get("AUTOMETA_B200_ALLOW_JACOBI", "") != "1":
+                raise L.AutometaB200Error(rc, "am_eigh_topk (cluster tridiagonalisation) is unavailable on this device: "
+                                          + msg + "; set AUTOMETA_B200_ALLOW_JACOBI=1 to use the 65x slower am_eigh")
+            warnings.warn("am_eigh_topk unavailable (%s); using am_eigh (AUTOMETA_B200_ALLOW_JACOBI=1)" % msg)
             _topk_state["disabled"] = True
         elif rc != L.AM_OK:
             L.check(rc)

@@ -743,8 +743,14 @@ class HostFeaturiser:
                 self.h_scores.copy_(res["scores"], non_blocking=True)
                 self.h_ev.copy_(res["explained_variance"], non_blocking=True)
 
-            fs = FeatureStream(self.dev, self.k, self.method, self.P, group=group, distributed=distributed,
-                               depth=depth, on_result=collect)
+            key = (id(group), distributed, depth)
+            if getattr(self, "_fs_key", None) != key:
+                # built once per featuriser: with several GPUs it owns a communicator (a collective to create)
+                self._fs = FeatureStream(self.dev, self.k, self.method, self.P, group=group, distributed=distributed,
+                                         depth=depth)
+                self._fs_key = key
+            fs = self._fs
+            fs.on_result = collect
             packed = [self._packed(b) for b in self.bufs]
             for p in packed:
                 if self._plans:
