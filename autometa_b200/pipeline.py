@@ -399,6 +399,7 @@ class FeatureStream:
         # ready a few microseconds later, behind an event — would otherwise queue behind it
         self.started = None
         self.wait_value = 0
+        self.use_wait = True
         if distributed and spread_eigh:
             import torch.distributed as dist
 
@@ -450,8 +451,8 @@ class FeatureStream:
         sa, sb, sc = self.sA.cuda_stream, self.sB.cuda_stream, self.sC.cuda_stream
         ck = L.check
         self.sA.wait_stream(torch.cuda.current_stream(dev))  # inputs produced on the caller's stream
-        if self.wait_value:
-            ck(lib.am_stream_wait_geq(sa, L.t_ptr(self.started), self.wait_value))
+        if self.wait_value and self.use_wait:
+            self._hold_stage1(sa)
         # ---- stage 1 (stream A)
         ck(lib.am_zero_async(S.p_R, S.R.numel() * 8, sa))
         ck(lib.am_zero_async(S.p_zeros, S.zb.numel() * 8, sa))
@@ -509,6 +510,17 @@ class FeatureStream:
         self.wait_value = self.n_submitted if (solves_here and self.depth > 1) else 0
         self.inflight.append((packed, S, None, evB, None, None))
 
+    def _hold_stage1(self, raw_stream):
+        """Stream-level wait until the previous pass's tridiagonalisation cluster is resident.  A scheduling aid
+        only: where the driver refuses stream memory operations the stream simply runs without it."""
+        rc = L.lib.am_stream_wait_geq(raw_stream, L.t_ptr(self.started), self.wait_value)
+        if rc != L.AM_OK:
+            import warnings
+
+            warnings.warn("stream memory wait unavailable (%s): throughput mode runs without the start-order hold"
+                          % L.lib.am_last_error().decode(errors="replace"))
+            self.use_wait = False
+
     def _event(self):
         import torch
 
@@ -555,8 +567,8 @@ class FeatureStream:
                 self.started = torch.zeros(1, dtype=torch.int32, device=self.dev)
                 torch.cuda.current_stream(self.dev).synchronize()
             with torch.cuda.stream(self.sA):
-                if self.wait_value:
-                    L.check(L.lib.am_stream_wait_geq(L.stream_ptr(self.dev), L.t_ptr(self.started), self.wait_value))
+                if self.wait_value and self.use_wait:
+                    self._hold_stage1(L.stream_ptr(self.dev))
                 mark("start")
                 counts, present, row_sum = _dev.count_packed(packed, self.k)
                 mark("count")
