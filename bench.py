@@ -44,6 +44,7 @@ K = 5
 NCOMP = 50
 # the same string in both arms (the driver compares `config.workload` of the two lines)
 WORKLOADS = {
+    "c1": "C1: 5-mer count + am_clr + PCA(50), 10k contigs / 50 Mbp seeded synthetic assembly",
     "c2": "C2: 5-mer count + am_clr + PCA(50), 200k contigs / 1 Gbp seeded synthetic assembly",
     "c5": "C5: 5-mer count + ilr + PCA(50), 1M contigs / 5 Gbp seeded synthetic assembly (large-data mode)",
 }
@@ -417,9 +418,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c2", "c5"],
-                    help="c2: BASELINE.json configs[1]/[2] (200k contigs / 1 Gbp, am_clr); c5: configs[4] "
-                         "(1M contigs / 5 Gbp, ilr, sharded over the ranks)")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c5"],
+                    help="c2: BASELINE.json configs[1]/[2] (200k contigs / 1 Gbp, am_clr); c1: configs[0] (10k contigs / "
+                         "50 Mbp, the reference's CPU-runnable case: L2-resident, a parity config rather than a roofline "
+                         "one); c5: configs[4] (1M contigs / 5 Gbp, ilr, sharded over the ranks)")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="N>1 default: strong (the same assembly sharded by bp, BASELINE.json configs[2]); the weak "
                          "figure is then measured too and reported under `weak`")
@@ -438,9 +440,9 @@ def main():
         return
     c5 = args.config == "c5"
     if args.contigs is None:
-        args.contigs = 1_000_000 if c5 else N_CONTIGS
+        args.contigs = 1_000_000 if c5 else (10_000 if args.config == "c1" else N_CONTIGS)
     if args.bp is None:
-        args.bp = 5_000_000_000 if c5 else TOTAL_BP
+        args.bp = 5_000_000_000 if c5 else (50_000_000 if args.config == "c1" else TOTAL_BP)
     if args.norm is None:
         args.norm = "ilr" if c5 else "am_clr"
 
@@ -627,10 +629,10 @@ def main():
             "serial_frac": round(comp_bytes / (ms_serial * 1e-3) / 1e9 / hbm, 4),
         }
         cpu = None
-        if not args.no_cpu_baseline and world == 1 and not c5:  # reported once, on rank 0 at N=1
+        if not args.no_cpu_baseline and world == 1 and args.config == "c2":  # reported once, on rank 0 at N=1
             cpu = cpu_baseline(asm, os.cpu_count() or 1)
         sweep = None
-        if not args.no_sweep and world == 1 and not c5:  # the 200k-point sweep fits one GPU: replicas only
+        if not args.no_sweep and world == 1 and args.config == "c2":  # the 200k-point sweep fits one GPU: replicas only
             sweep = sweep_bench(dev, torch, cpu=not args.no_cpu_baseline)
         line = {
             "metric": METRIC if not c5 else METRIC.replace("am_clr", args.norm), "value": value, "unit": UNIT,
