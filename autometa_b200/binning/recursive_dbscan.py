@@ -11,7 +11,10 @@ sweep keeps ONE union-find forest on the device and only adds merges as eps grow
 The callers of the sweep are mirrored on top of it: ``get_clusters``
 (:440-545, re-sweeps the leftovers until nothing more is recovered) and
 ``taxon_guided_binning`` (:548-705, the same per taxon from superkingdom down to
-species).  Only ``method="dbscan"`` is on the device; HDBSCAN is out of scope.
+species).  Only ``method="dbscan"`` is on the device; HDBSCAN is out of scope
+(``NotImplementedError``).  The eps step takes at most 4 clustering features (the
+columns containing ``x_`` plus ``coverage``: ``embed_dimensions`` <= 3), more raise
+``ValueError``; the reference's default is 2 + coverage.
 """
 from __future__ import annotations
 

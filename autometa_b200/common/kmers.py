@@ -16,6 +16,13 @@ function          reference                              kernel
 ================  =====================================  ======================
 
 There is no CPU fallback: without a CUDA device these functions raise.
+
+Where this module is narrower than, or differs from, the reference (INTEGRATION.md 3b has the reasons):
+``count`` takes ``size`` 1..7 only (larger k: ``AutometaB200Error``, "k must be in 1..7") and returns nullable
+``Int32`` columns instead of object columns (same values, same ``pd.NA``, same TSV bytes); the PCA stage of
+``embed`` always computes the exact leading eigenpairs, also for the table sizes (500 < N < 10 D) at which
+sklearn's ``svd_solver="auto"`` takes the randomized branch — there the scores agree with the reference's only to
+the randomized solver's own accuracy and the shared ``RandomState`` is not advanced by the PCA.
 """
 from __future__ import annotations
 
