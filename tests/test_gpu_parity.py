@@ -382,6 +382,71 @@ def test_eigh_topk_direct(torch_cuda):
     assert not D._topk_state.get("disabled"), "am_eigh_topk fell back to the Jacobi solver on this GPU"
 
 
+def test_small_entry_points_against_numpy(torch_cuda):
+    """The small C entries the sharded / streamed / large-data-mode passes are built from, each against numpy:
+    am_table_stats, am_stats_pack, am_gram_recenter (+ am_cov_finish), am_axpb_f64, am_pca_finish."""
+    import torch
+
+    from autometa_b200 import _lib as L
+    from autometa_b200 import device as D
+
+    rng = np.random.default_rng(4)
+    dev = torch.device("cuda", 0)
+    st = L.stream_ptr(dev)
+    # am_table_stats: presence and row sums of a row subset, D not a multiple of 32 and > 1024
+    for Dc in (136, 512, 2080):
+        cnt = rng.poisson(0.6, size=(300, Dc)).astype(np.int32)
+        cnt[:, 5] = 0
+        cnt[17] = 0
+        rows = np.sort(rng.choice(300, size=120, replace=False)).astype(np.int64)
+        d_cnt, d_rows = torch.from_numpy(cnt).to(dev), torch.from_numpy(rows).to(dev)
+        present = torch.empty(Dc, dtype=torch.int32, device=dev)
+        row_sum = torch.empty(len(rows), dtype=torch.int32, device=dev)
+        L.check(L.lib.am_table_stats(L.t_ptr(d_cnt), L.t_ptr(d_rows), len(rows), Dc, L.t_ptr(present), L.t_ptr(row_sum), st))
+        assert np.array_equal(present.cpu().numpy(), (cnt[rows].sum(axis=0) > 0).astype(np.int32))
+        assert np.array_equal(row_sum.cpu().numpy(), cnt[rows].sum(axis=1))
+        L.check(L.lib.am_table_stats(L.t_ptr(d_cnt), None, 300, Dc, L.t_ptr(present), L.t_ptr(row_sum[:1].new_empty(300)), st))
+        # am_stats_pack: the SUM-reducible form
+        out = torch.full((Dc + 1,), -1.0, dtype=torch.float64, device=dev)
+        rs_all = torch.from_numpy(cnt.sum(axis=1).astype(np.int32)).to(dev)
+        pr_all = torch.from_numpy((cnt.sum(axis=0) > 0).astype(np.int32)).to(dev)
+        D.stats_pack(pr_all, rs_all, 300, out)
+        got = out.cpu().numpy()
+        assert np.array_equal(got[:Dc], (cnt.sum(axis=0) > 0).astype(np.float64))
+        assert got[Dc] == float((cnt.sum(axis=1) == 0).sum())
+    # am_gram_recenter + am_cov_finish: Gram about c_old -> Gram about c_new -> covariance
+    n, Dg = 500, 40
+    X = rng.normal(size=(n, Dg)) * rng.uniform(0.5, 3.0, size=Dg) + rng.normal(size=Dg) * 5
+    c_old, c_new = X[:50].mean(axis=0), rng.normal(size=Dg)
+    G = torch.from_numpy((X - c_old).T @ (X - c_old)).to(dev)
+    cs = torch.from_numpy(X.sum(axis=0)).to(dev)
+    n_t = torch.tensor([float(n)], dtype=torch.float64, device=dev)
+    D.gram_recenter(G, cs, torch.from_numpy(c_old).to(dev), torch.from_numpy(c_new).to(dev), n_t)
+    ref = (X - c_new).T @ (X - c_new)
+    assert np.max(np.abs(G.cpu().numpy() - ref)) <= 1e-12 * np.max(np.abs(ref))
+    D.gram_recenter(G, cs, torch.from_numpy(c_new).to(dev), None, n_t)  # ... about the origin
+    assert np.max(np.abs(G.cpu().numpy() - X.T @ X)) <= 1e-12 * np.max(np.abs(X.T @ X))
+    mu = D.cov_finish(G, cs, torch.zeros(Dg, dtype=torch.float64, device=dev), n_t)
+    np.testing.assert_allclose(mu.cpu().numpy(), X.mean(axis=0), rtol=1e-14)
+    C = np.cov(X, rowvar=False)
+    assert np.max(np.abs(G.cpu().numpy() - C)) <= 1e-10 * np.max(np.abs(C))  # X^T X - n mu mu^T: sklearn's own form
+    # am_axpb_f64, am_pca_finish
+    v = torch.from_numpy(rng.normal(size=1000)).to(dev)
+    v0 = v.cpu().numpy().copy()
+    L.check(L.lib.am_axpb_f64(L.t_ptr(v), 1000, 0.25, -3.0, st))
+    np.testing.assert_array_equal(v.cpu().numpy(), np.array([np.float64(x) * 0.25 - 3.0 for x in v0]))  # fma: exact here
+    ev = torch.tensor([5.0, 2.0, -1e-18, 0.5], dtype=torch.float64, device=dev)
+    tot = torch.tensor([10.0], dtype=torch.float64, device=dev)
+    ratio = torch.empty(4, dtype=torch.float64, device=dev)
+    L.check(L.lib.am_pca_finish(L.t_ptr(ev), L.t_ptr(tot), 4, L.t_ptr(ratio), st))
+    assert ev.cpu().tolist() == [5.0, 2.0, 0.0, 0.5] and ratio.cpu().tolist() == [0.5, 0.2, 0.0, 0.05]
+    # reserved SMs round trip
+    L.check(L.lib.am_set_reserved_sms(16))
+    assert L.lib.am_get_reserved_sms() == 16
+    L.check(L.lib.am_set_reserved_sms(0))
+    assert L.lib.am_set_reserved_sms(-1) != 0
+
+
 # ---------------------------------------------------------------------------- DBSCAN
 def _sweep_table():
     from autometa_b200 import synth
