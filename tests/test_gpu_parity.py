@@ -405,7 +405,10 @@ def test_small_entry_points_against_numpy(torch_cuda):
         L.check(L.lib.am_table_stats(L.t_ptr(d_cnt), L.t_ptr(d_rows), len(rows), Dc, L.t_ptr(present), L.t_ptr(row_sum), st))
         assert np.array_equal(present.cpu().numpy(), (cnt[rows].sum(axis=0) > 0).astype(np.int32))
         assert np.array_equal(row_sum.cpu().numpy(), cnt[rows].sum(axis=1))
-        L.check(L.lib.am_table_stats(L.t_ptr(d_cnt), None, 300, Dc, L.t_ptr(present), L.t_ptr(row_sum[:1].new_empty(300)), st))
+        rs_full = torch.empty(300, dtype=torch.int32, device=dev)
+        L.check(L.lib.am_table_stats(L.t_ptr(d_cnt), None, 300, Dc, L.t_ptr(present), L.t_ptr(rs_full), st))  # all rows
+        assert np.array_equal(rs_full.cpu().numpy(), cnt.sum(axis=1))
+        assert np.array_equal(present.cpu().numpy(), (cnt.sum(axis=0) > 0).astype(np.int32))
         # am_stats_pack: the SUM-reducible form
         out = torch.full((Dc + 1,), -1.0, dtype=torch.float64, device=dev)
         rs_all = torch.from_numpy(cnt.sum(axis=1).astype(np.int32)).to(dev)
