@@ -514,7 +514,9 @@ gram_i8_reduce_kernel(const double *__restrict__ part, GramI8Params p, int n_par
 // ------------------------------------------------------------------ host side
 inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
-void gram_i8_shape(int64_t n_rows, int D, int S, GramI8Params *p) {
+// `sms`: the CTAs the launch will use, so that the work items are a whole number of waves.  More SMs never
+// give fewer row chunks, so buffers sized with num_sms() fit a launch under any SM reservation.
+void gram_i8_shape(int64_t n_rows, int D, int S, GramI8Params *p, int sms) {
   p->S = S;
   p->n_rows = (int)n_rows;
   p->TI = (D + GI_M - 1) / GI_M;
@@ -522,7 +524,6 @@ void gram_i8_shape(int64_t n_rows, int D, int S, GramI8Params *p) {
   int nt = 0;
   for (int I = 0; I < p->TI; ++I) nt += std::max(0, p->TJ - 2 * I);
   p->n_tiles = nt;
-  const int sms = am::num_sms();
   // row chunks: enough work items for ~5 waves of persistent CTAs, chunk <= 16384 rows (int32
   // headroom: S pairs x rows x 2^14 < 2^31), >= 512 rows
   int64_t want_items = (int64_t)sms * 5;
@@ -595,7 +596,7 @@ extern "C" int am_quantize_planes(const double *d_X, int64_t n_rows, int D, cons
 extern "C" int64_t am_gram_planes_work_bytes(int64_t n_rows, int D, int S) {
   if (n_rows < 1 || D < 1 || S < 2 || S > GI_MAXS) return 0;
   GramI8Params p;
-  gram_i8_shape(n_rows, D, S, &p);
+  gram_i8_shape(n_rows, D, S, &p, am::num_sms());  // upper bound over every reservation
   return align256((int64_t)2 * p.n_chunks * p.n_tiles * GI_M * GI_N * 8);  // x2: the CTA-pair kernel writes two partials
 }
 
@@ -609,7 +610,7 @@ extern "C" int am_gram_planes(const int8_t *d_planes, int64_t n_rows, int D, int
   if (!encode) return am::fail(AM_ECUDA, "am_gram_planes: cuTensorMapEncodeTiled entry point unavailable");
   cudaStream_t st = (cudaStream_t)stream;
   GramI8Params p;
-  gram_i8_shape(n_rows, D, S, &p);
+  gram_i8_shape(n_rows, D, S, &p, am::grid_sms());
   const int Dp = plane_pitch(D);
   double *part = (double *)d_work;
   CUtensorMap tmA, tmB;
