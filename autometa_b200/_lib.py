@@ -103,7 +103,40 @@ _SIGS = {
     "am_metrics_work_bytes": (_i64, [_i64, _i32]),
     "am_cluster_metrics": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _i32, _p, _p, _f64, _f64, _f64, _f64,
                                      _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "am_eps_grid": (C.c_int, [_f64, _p, _p, _i32, _p]),
+    "am_eps_union_dyn": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p]),
+    "am_sweep_args_size": (_i64, []),
+    "am_sweep_ctl_bytes": (_i64, [_i64, _i32]),
+    "am_sweep_init": (C.c_int, [_p, _p]),
+    "am_sweep_steps": (C.c_int, [_p, _i32, _p, _p]),
+    "am_sweep_graph_create": (C.c_int, [_p, _p, _p]),
+    "am_sweep_graph_launch": (C.c_int, [_p, _p, _i32, _p, _p]),
+    "am_sweep_graph_destroy": (C.c_int, [_p]),
+    "am_sweep_advance_host": (C.c_int, [_p, _p, _i32, _i32, _f64]),
 }
+
+#: indices into the loop state of the device-resident sweep (include/autometa_b200.h, AM_SWEEP_*)
+SWEEP_CTL_WORDS = 32
+(SWEEP_EPS, SWEEP_STEP, SWEEP_BEST, SWEEP_DONE, SWEEP_NSTEPS, SWEEP_BEST_STEP, SWEEP_BEST_NC, SWEEP_LAST_NC,
+ SWEEP_LAST_MED, SWEEP_TAKE, SWEEP_INV_CELL, SWEEP_EPS2, SWEEP_SPAN) = range(13)
+SWEEP_BEST_EPS = 16
+
+
+class SweepArgs(C.Structure):
+    """``am_sweep_args`` (include/autometa_b200.h), field for field."""
+
+    _fields_ = [
+        ("d_X", _p), ("n_points", _i64), ("F", C.c_int32), ("n_markers", C.c_int32),
+        ("h_min", _f64 * 4), ("h_max", _f64 * 4),
+        ("d_parent", _p), ("d_dbscan_work", _p), ("d_labels", _p), ("d_n_clusters", _p),
+        ("d_marker_rows", _p), ("d_marker_cols", _p), ("d_marker_vals", _p), ("nnz", _i64),
+        ("d_coverage", _p), ("d_gc", _p), ("cutoffs", _f64 * 4),
+        ("d_completeness", _p), ("d_purity", _p), ("d_cov_std", _p), ("d_gc_std", _p),
+        ("d_present", _p), ("d_single", _p), ("d_summary", _p), ("d_metrics_work", _p), ("d_ctl", _p),
+        ("d_best_labels", _p), ("d_best_completeness", _p), ("d_best_purity", _p), ("d_best_cov_std", _p),
+        ("d_best_gc_std", _p), ("d_best_present", _p), ("d_best_single", _p),
+        ("trace_cap", C.c_int32), ("reserved", C.c_int32),
+    ]
 
 EXPORTS = tuple(_SIGS)
 
@@ -111,6 +144,11 @@ for _name, (_res, _args) in _SIGS.items():
     _fn = getattr(lib, _name)  # AttributeError here = header/library mismatch: fail loudly
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+if lib.am_sweep_args_size() != C.sizeof(SweepArgs):  # header / binding mismatch: fail loudly
+    raise ImportError("am_sweep_args: the library's struct is %d bytes, the binding's %d"
+                      % (lib.am_sweep_args_size(), C.sizeof(SweepArgs)))
 
 
 def check(rc: int) -> None:

@@ -34,7 +34,7 @@ from .. import pipeline as _pipe
 from .. import tsv as _tsv
 from ..common import kmers
 from ..common.exceptions import BinningError, TableFormatError
-from .recursive_dbscan import get_clusters
+from .recursive_dbscan import get_clusters, get_clusters_many
 from .utilities import reindex_bin_names, zero_pad_bin_names
 
 logger = logging.getLogger(__name__)
@@ -367,7 +367,8 @@ def cluster_by_taxon_partitioning(
         scores = batch.run(plan) if plan else {}
         rank_embedding = get_kmer_embedding(counts.loc[rank_counts_index], cache_fpath=rank_cache,
                                             pca_scores=scores.get("__rank__"), **embed_args)
-        # ---- per taxon: manifold step + sweep, in the reference's order
+        # ---- per taxon: manifold step (host, in the reference's order) ...
+        jobs = []  # (name, frame to sweep | None for a taxon that is only cached)
         for name, rank_df, taxon_cache in taxa:
             if name == resume_name:
                 resumed = True
@@ -381,7 +382,7 @@ def cluster_by_taxon_partitioning(
             if n > max_partition_size:
                 logger.debug(f"{name} > max_partition_size ({n:,}>{max_partition_size:,}). skipping [and caching embedding]")
                 get_kmer_embedding(taxon_counts, cache_fpath=taxon_cache, pca_scores=scores.get(name), **embed_args)
-                binning_checkpoints[name] = pd.NA
+                jobs.append((name, None))
                 continue
             if n >= min_contigs:
                 taxon_embedding = get_kmer_embedding(taxon_counts, cache_fpath=taxon_cache, pca_scores=scores.get(name),
@@ -392,11 +393,20 @@ def cluster_by_taxon_partitioning(
                 logger.debug(f"using {rank} embedding for {name}. shape={taxon_embedding.shape}")
             rank_df = pd.merge(rank_df, taxon_embedding, how="left", left_index=True, right_index=True)
             logger.debug(f"Examining taxonomy: {rank} : {name} : {rank_df.shape}")
-            binned = get_clusters(
-                main=rank_df, markers_df=markers, completeness=completeness, purity=purity,
-                coverage_stddev=coverage_stddev, gc_content_stddev=gc_content_stddev, method=method,
-                n_jobs=n_jobs, verbose=verbose,
-            )
+            jobs.append((name, rank_df))
+        # ---- ... then the sweeps of all the rank's taxa in flight together on the device (the taxa of a rank
+        # are disjoint, so no sweep changes another's input) ...
+        binned_frames = iter(get_clusters_many(
+            [df for _, df in jobs if df is not None], markers_df=markers, completeness=completeness, purity=purity,
+            coverage_stddev=coverage_stddev, gc_content_stddev=gc_content_stddev, method=method, n_jobs=n_jobs,
+            verbose=verbose, device=device,
+        ))
+        # ---- ... and the bookkeeping (bin names, checkpoints) taxon by taxon in the reference's order
+        for name, rank_df in jobs:
+            if rank_df is None:
+                binning_checkpoints[name] = pd.NA
+                continue
+            binned = next(binned_frames)
             clustered = binned.loc[binned["cluster"].notnull()]
             if clustered.empty:
                 continue

@@ -49,7 +49,9 @@ _DROPCOLS = ["cluster", "purity", "completeness", "coverage_stddev", "gc_content
 def _feature_matrix(df: pd.DataFrame) -> np.ndarray:
     # recursive_dbscan.py:105-107: every column containing "x_" plus "coverage", in frame order
     cols = [col for col in df.columns if "x_" in col or col == "coverage"]
-    return np.ascontiguousarray(df.loc[:, cols].to_numpy(dtype=np.float64))
+    if not cols or not df.columns.is_unique:
+        return np.ascontiguousarray(df.loc[:, cols].to_numpy(dtype=np.float64))
+    return np.ascontiguousarray(np.stack([df[col].to_numpy(dtype=np.float64) for col in cols], axis=1))
 
 
 def _upload(X: np.ndarray, device=None):
@@ -87,6 +89,79 @@ def run_dbscan(
     return pd.merge(df, clusters, how="left", left_index=True, right_index=True)
 
 
+#: how a sweep is driven: "device" (default) = the loop state lives on the GPU (``device.DeviceSweep``,
+#: csrc/am_sweep.cu), the host queues batches of graph replays; "host" = one synchronisation per eps with the
+#: schedule in Python (the round-1 loop, kept as a cross-check of the device controller — both are CUDA paths)
+SWEEP_MODES = ("device", "host")
+
+#: device memory the sweeps in flight may hold together (bytes), and the most sweeps in flight
+_IN_FLIGHT_BYTES = 4 << 30
+_IN_FLIGHT_MAX = 16
+
+_streams = {}
+
+
+def _stream_pool(dev, k: int):
+    """``k`` streams of the device's pool (created on first use): the sweeps in flight get one each."""
+    import torch
+
+    pool = _streams.setdefault(dev.index, [])
+    while len(pool) < k:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:k]
+
+
+def _drive(starters, limit: int = 1):
+    """Run generator-style jobs to completion, at most ``limit`` in flight.  ``starters[i](slot)`` returns a
+    generator that yields an object with ``ready()`` / ``wait()`` each time it has queued device work and needs
+    it finished before it can go on; its return value is the job's result.  With one job this is a plain loop;
+    with several, the host-side work of one (pandas frames, queueing) overlaps the device work of the others."""
+    results = [None] * len(starters)
+    live = {}  # slot -> (job index, generator, what it waits for)
+    nxt = 0
+    free = list(range(max(1, limit)))[::-1]
+
+    def advance(slot, i, gen):
+        try:
+            live[slot] = (i, gen, next(gen))
+        except StopIteration as stop:
+            results[i] = stop.value
+            live.pop(slot, None)
+            free.append(slot)
+
+    while nxt < len(starters) or live:
+        while free and nxt < len(starters):
+            slot = free.pop()
+            advance(slot, nxt, starters[nxt](slot))
+            nxt += 1
+        progressed = False
+        for slot in list(live):
+            i, gen, w = live[slot]
+            if w is None or w.ready():
+                advance(slot, i, gen)
+                progressed = True
+        if not progressed and live:
+            w = next(iter(live.values()))[2]
+            if w is not None:
+                w.wait()
+    return results
+
+
+def _in_flight(n_rows, n_markers: int) -> int:
+    """How many sweeps of up to ``n_rows`` points may be in flight within the memory budget."""
+    per = max(1, int(n_rows)) * (4 * max(1, int(n_markers)) + 256)
+    return int(max(1, min(_IN_FLIGHT_MAX, _IN_FLIGHT_BYTES // per)))
+
+
+def _sweep_mode() -> str:
+    import os
+
+    mode = os.environ.get("AUTOMETA_B200_SWEEP", "device")
+    if mode not in SWEEP_MODES:
+        raise ValueError(f"AUTOMETA_B200_SWEEP must be one of {SWEEP_MODES}, got {mode!r}")
+    return mode
+
+
 def recursive_dbscan(
     table: pd.DataFrame,
     markers_df: pd.DataFrame,
@@ -104,38 +179,92 @@ def recursive_dbscan(
     stop at <= 1 cluster (or median == 0 ten times).  Returns
     ``(clustered_df, unclustered_df)``.
     """
+    cut = (completeness_cutoff, purity_cutoff, coverage_stddev_cutoff, gc_content_stddev_cutoff)
+    return _drive([lambda slot: _recursive_dbscan_gen(table, markers_df, cut, verbose, device, None)])[0]
+
+
+def _recursive_dbscan_gen(table, markers_df, cut, verbose, device, stream):
+    """``recursive_dbscan`` as a generator (see ``_drive``): yields each time a batch of eps steps has been
+    queued on the device."""
     n_samples = table.shape[0]
     if n_samples <= 1 or "coverage" not in table.columns or "gc_content" not in table.columns:
-        return _recursive_dbscan_frames(
-            table, markers_df, completeness_cutoff, purity_cutoff, coverage_stddev_cutoff,
-            gc_content_stddev_cutoff, verbose, device,
-        )
+        return _recursive_dbscan_frames(table, markers_df, *cut, verbose, device)
     # run_dbscan's side effects and checks (:95-103), once
     table.drop(columns=_DROPCOLS, inplace=True, errors="ignore")
     if np.any(table.isnull()):
         raise TableFormatError(f"df is missing {table.isnull().sum().sum()} kmer/coverage annotations")
     X = _feature_matrix(table)
-    sweep = _dev.EpsSweep(_upload(X, device))
+    if X.shape[1] < 1 or X.shape[1] > 4:
+        raise ValueError(f"the GPU eps step supports 1..4 clustering features, got {X.shape[1]}")
+    dev = L.require_cuda(device)
     coverage = table["coverage"].to_numpy(dtype=np.float64)
     gc = table["gc_content"].to_numpy(dtype=np.float64)
     rows, cols, vals = markers_coo(markers_df, table.index)
     n_ref = markers_df.shape[1]
-    dev = sweep.dev
-    metrics = _dev.ClusterMetrics(
-        n_samples, rows, cols, vals, n_ref, coverage, gc,
-        (completeness_cutoff, purity_cutoff, coverage_stddev_cutoff, gc_content_stddev_cutoff), dev,
-    )
+    if _sweep_mode() == "host":
+        labels, m, best_median = _sweep_hostloop(X, coverage, gc, rows, cols, vals, n_ref, cut, dev, verbose)
+    else:
+        # The loop (schedule, best-eps rule, termination :189-215) runs on the device; the host queues
+        # batches of steps and looks at one word per batch.
+        if stream is None:
+            stream = _stream_pool(dev, 1)[0]
+        run = _dev.DeviceSweep(X, coverage, gc, rows, cols, vals, n_ref, cut, dev, stream=stream,
+                               trace_cap=4096 if verbose else 0)
+        while True:
+            run.launch()
+            yield run
+            if run.poll():
+                break
+        labels, m, best_median, _, trace = run.result()
+        run.close()
+        if verbose and trace is not None:
+            zero_rounds = 0
+            for k, (eps, n_clusters, median, best) in enumerate(trace):
+                zero_rounds += int(median == 0)
+                if zero_rounds >= 10:  # the reference leaves the loop before it logs this eps (:208-214)
+                    break
+                logger.debug(
+                    f"EPS: {eps:3.2f} Clusters: {int(n_clusters):,}"
+                    f" Completeness: Median={median:4.2f} Best={best:4.2f}"
+                )
+    # the frame add_metrics returns (utilities.py:173-206): the table without earlier metric columns, then
+    # ``cluster`` and the six metrics; built in one concat, and split by the passing mask of the CLUSTERS
+    # (= apply_binning_metrics_filter on the rows, :257-262, and its complement by index)
+    stale = [c for c in METRICS if c in table.columns]
+    base = table.drop(columns=stale) if stale else table
+    extra = pd.DataFrame({"cluster": labels, **{name: m[name][labels] for name in METRICS}}, index=table.index)
+    best_df = pd.concat([base, extra], axis=1)
+    if table.index.is_unique:
+        passing = passing_mask(m, *cut)[labels]
+        clustered_df = best_df[passing]
+        unclustered_df = best_df[~passing]
+    else:
+        clustered_df = apply_binning_metrics_filter(
+            df=best_df,
+            completeness_cutoff=cut[0],
+            purity_cutoff=cut[1],
+            coverage_stddev_cutoff=cut[2],
+            gc_content_stddev_cutoff=cut[3],
+        )
+        unclustered_df = best_df.loc[~best_df.index.isin(clustered_df.index)]
+    if verbose:
+        logger.debug(f"Best completeness median: {best_median:4.2f}")
+    logger.debug(f"clustered: {clustered_df.shape[0]:,} unclustered: {unclustered_df.shape[0]:,}")
+    return clustered_df, unclustered_df
 
-    # The loop keeps labels and metrics on the device; per eps only the 3-number summary
-    # (cluster count, median completeness of passing clusters, number passing) comes back,
-    # because the eps schedule and the best-eps rule are host control flow (:189-215).
+
+def _sweep_hostloop(X, coverage, gc, rows, cols, vals, n_ref, cut, dev, verbose):
+    """The sweep with the schedule on the host: labels and metrics stay on the device, per eps only the
+    3-number summary (cluster count, median completeness of passing clusters, number passing) comes back."""
+    import torch
+
+    n_samples = X.shape[0]
+    sweep = _dev.EpsSweep(_upload(X, dev))
+    metrics = _dev.ClusterMetrics(n_samples, rows, cols, vals, n_ref, coverage, gc, cut, dev)
     eps, step = 0.3, 0.1
     clustering_rounds = {0: 0}
     n_clusters = float("inf")
     best_median = float("-inf")
-    best = None  # (labels, metrics) on the host, fetched when an eps becomes the best so far
-    import torch
-
     best_labels_d = torch.empty(n_samples, dtype=torch.int64, device=dev)
     best_keep = None
     while n_clusters > 1:
@@ -167,24 +296,7 @@ def recursive_dbscan(
     m = {k2: v.cpu().numpy() for k2, v in best_keep.items()}
     for k2 in ("present_marker_count", "single_copy_marker_count"):
         m[k2] = m[k2].astype(np.int64)
-    best = (best_labels_d.cpu().numpy(), m)
-    labels, m = best
-    best_df = table.copy()
-    best_df["cluster"] = labels
-    for name in METRICS:
-        best_df[name] = m[name][labels]
-    clustered_df = apply_binning_metrics_filter(
-        df=best_df,
-        completeness_cutoff=completeness_cutoff,
-        purity_cutoff=purity_cutoff,
-        coverage_stddev_cutoff=coverage_stddev_cutoff,
-        gc_content_stddev_cutoff=gc_content_stddev_cutoff,
-    )
-    unclustered_df = best_df.loc[~best_df.index.isin(clustered_df.index)]
-    if verbose:
-        logger.debug(f"Best completeness median: {best_median:4.2f}")
-    logger.debug(f"clustered: {clustered_df.shape[0]:,} unclustered: {unclustered_df.shape[0]:,}")
-    return clustered_df, unclustered_df
+    return best_labels_d.cpu().numpy(), m, best_median
 
 
 def _recursive_dbscan_frames(table, markers_df, completeness_cutoff, purity_cutoff,
@@ -239,24 +351,54 @@ def get_clusters(
     """Sweep, keep the passing clusters, sweep the leftovers again ... until a round recovers
     nothing or nothing is left (reference recursive_dbscan.py:440-545).  Returns ``main`` with
     ``cluster`` (``bin_NN`` / ``pd.NA``) and the four metric columns."""
+    return get_clusters_many([main], markers_df, completeness, purity, coverage_stddev, gc_content_stddev, method,
+                             n_jobs=n_jobs, verbose=verbose, device=device)[0]
+
+
+def get_clusters_many(
+    mains: List[pd.DataFrame],
+    markers_df: pd.DataFrame,
+    completeness: float,
+    purity: float,
+    coverage_stddev: float,
+    gc_content_stddev: float,
+    method: str,
+    n_jobs: int = -1,
+    verbose: bool = False,
+    device=None,
+) -> List[pd.DataFrame]:
+    """``get_clusters`` of several independent contig tables (the taxa of one rank: SURVEY 8f-3), their
+    sweeps in flight together on the device — each on its own stream, each a chain of CUDA-graph replays
+    (``device.DeviceSweep``), so the small sweeps of large-data mode are bound neither by one host
+    synchronisation per eps nor by one sweep's launch latency.  Results are those of ``get_clusters`` on each
+    table, in order."""
     if method not in ("dbscan", "hdbscan"):
         raise ValueError(f"Method: {method} not a choice. choose between dict_keys(['dbscan', 'hdbscan'])")
     if method != "dbscan":
         raise NotImplementedError("only method='dbscan' runs on the device; HDBSCAN is out of scope (DESIGN.md 9)")
+    if not mains:
+        return []
+    cut = (completeness, purity, coverage_stddev, gc_content_stddev)
+    limit = 1
+    pool = [None]
+    if _sweep_mode() == "device":
+        dev = L.require_cuda(device)
+        if len(mains) > 1:
+            limit = min(len(mains), _in_flight(max(m.shape[0] for m in mains), markers_df.shape[1]))
+        pool = _stream_pool(dev, limit)
+    starters = [
+        (lambda slot, main=main: _get_clusters_gen(main, markers_df, cut, verbose, device, pool[slot]))
+        for main in mains
+    ]
+    return _drive(starters, limit)
+
+
+def _get_clusters_gen(main, markers_df, cut, verbose, device, stream):
     n_bins = 0
     rounds = []
     while True:
-        clustered_df, unclustered_df = recursive_dbscan(
-            table=main,
-            markers_df=markers_df,
-            completeness_cutoff=completeness,
-            purity_cutoff=purity,
-            coverage_stddev_cutoff=coverage_stddev,
-            gc_content_stddev_cutoff=gc_content_stddev,
-            verbose=verbose,
-            n_jobs=n_jobs,
-            device=device,
-        )
+        clustered_df, unclustered_df = yield from _recursive_dbscan_gen(main, markers_df, cut, verbose, device,
+                                                                        stream)
         if clustered_df.empty:  # nothing recovered: the rest stays unbinned
             rounds.append(unclustered_df.assign(cluster=pd.NA))
             break
@@ -304,6 +446,9 @@ def taxon_guided_binning(
         by_taxon = main.loc[main[rank] != "unclassified"].groupby(rank)
         sizes = by_taxon[rank].count()
         logger.info(f"Examining {rank}: {sizes.index.nunique():,} unique taxa ({sizes.sum():,} contigs)")
+        # a contig has one taxon per rank, so the taxa of a rank are independent problems (bins found in
+        # one never remove contigs from another): their sweeps are queued together (get_clusters_many)
+        todos = []
         for taxon, members in by_taxon:
             if members.empty:
                 continue
@@ -313,11 +458,12 @@ def taxon_guided_binning(
             if todo.empty:
                 continue
             logger.debug(f"Examining taxonomy: {rank} : {taxon} : {todo.shape}")
-            clusters_df = get_clusters(
-                main=todo, markers_df=markers, completeness=completeness, purity=purity,
-                coverage_stddev=coverage_stddev, gc_content_stddev=gc_content_stddev, method=method,
-                n_jobs=n_jobs, verbose=verbose, device=device,
-            )
+            todos.append(todo)
+        results = get_clusters_many(
+            todos, markers_df=markers, completeness=completeness, purity=purity, coverage_stddev=coverage_stddev,
+            gc_content_stddev=gc_content_stddev, method=method, n_jobs=n_jobs, verbose=verbose, device=device,
+        )
+        for clusters_df in results:
             clustered = clusters_df.loc[clusters_df["cluster"].notnull()]
             if clustered.empty:
                 continue

@@ -79,9 +79,59 @@ def passing_mask(m: Dict[str, np.ndarray], completeness_cutoff, purity_cutoff, c
         )
 
 
+class _MarkerTable:
+    """The non-zero entries of a contig x marker count table in CSR form, built once per table: the sweeps of
+    a binning run (hundreds of taxa, several rounds each) all restrict the SAME marker table to their own
+    contigs, and converting the whole frame each time costs more than the sweep itself."""
+
+    def __init__(self, markers_df: pd.DataFrame):
+        vals = markers_df.to_numpy(dtype=np.float64, na_value=0.0)
+        vals = np.nan_to_num(vals, nan=0.0)
+        r, c = np.nonzero(vals)
+        self.index = markers_df.index
+        self.shape = markers_df.shape
+        self.indptr = np.searchsorted(r, np.arange(markers_df.shape[0] + 1)).astype(np.int64)
+        self.cols = c.astype(np.int64)
+        self.vals = vals[r, c]
+
+    def coo(self, index: pd.Index):
+        mrow = self.index.get_indexer(index)  # row of every contig of the table in the marker table, or -1
+        have = np.flatnonzero(mrow >= 0)
+        starts = self.indptr[mrow[have]]
+        lens = self.indptr[mrow[have] + 1] - starts
+        total = int(lens.sum())
+        if total == 0:
+            z = np.zeros(0, dtype=np.int64)
+            return z, z.copy(), np.zeros(0, dtype=np.float64)
+        rows = np.repeat(have, lens)
+        first = np.cumsum(lens) - lens  # position of each contig's first entry in the output
+        offs = np.repeat(starts - first, lens) + np.arange(total, dtype=np.int64)
+        return rows.astype(np.int64), self.cols[offs], self.vals[offs]
+
+
+_marker_tables: Dict[int, tuple] = {}
+
+
+def _marker_table(markers_df: pd.DataFrame) -> "_MarkerTable":
+    import weakref
+
+    key = id(markers_df)
+    hit = _marker_tables.get(key)
+    if hit is not None and hit[0]() is markers_df and hit[1].shape == markers_df.shape:
+        return hit[1]
+    table = _MarkerTable(markers_df)
+    for k in [k for k, (ref, _) in _marker_tables.items() if ref() is None]:
+        del _marker_tables[k]
+    _marker_tables[key] = (weakref.ref(markers_df), table)
+    return table
+
+
 def markers_coo(markers_df: pd.DataFrame, index: pd.Index):
     """Non-zero entries of ``markers_df`` restricted/aligned to ``index`` (contigs
-    absent from the marker table count as zero, as the outer join + sum does)."""
+    absent from the marker table count as zero, as the outer join + sum does), as
+    ``(row in index, marker column, count)``."""
+    if markers_df.index.is_unique:
+        return _marker_table(markers_df).coo(index)
     pos = index.get_indexer(markers_df.index)
     ok = pos >= 0
     vals = markers_df.to_numpy(dtype=np.float64, na_value=0.0)[ok]

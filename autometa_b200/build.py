@@ -26,6 +26,7 @@ SOURCES = [
     "am_eigtop.cu",
     "am_dbscan.cu",
     "am_metrics.cu",
+    "am_sweep.cu",
 ]
 NVCC_FLAGS = [
     "-gencode",

@@ -60,6 +60,45 @@ inline int grid_sms() {
   return n < 2 ? 2 : n;
 }
 
+// IEEE double operations that the compiler may not contract into an FMA, on either side of the boundary:
+// the eps schedule of the sweep (Python float arithmetic in the reference) has to come out bit-identical
+// whether the host or a device kernel advances it.
+__host__ __device__ __forceinline__ double mul_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  volatile double r = a * b;
+  return r;
+#endif
+}
+__host__ __device__ __forceinline__ double add_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dadd_rn(a, b);
+#else
+  volatile double r = a + b;
+  return r;
+#endif
+}
+__host__ __device__ __forceinline__ double div_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __ddiv_rn(a, b);
+#else
+  volatile double r = a / b;
+  return r;
+#endif
+}
+
+// Cell list of one eps step (am_dbscan.cu): cell edge slightly above eps so that |a-b| <= eps implies cell
+// indices differ by <= 1 even after rounding; the cell count per axis is capped so indices stay well inside
+// the int range.  out2 = {1 / cell edge, eps^2}.
+__host__ __device__ inline void eps_grid(double eps, const double *span, int F, double *out2) {
+  double cell = mul_rn(eps, 1.0 + 1.0 / 1048576.0);
+  for (int d = 0; d < F; ++d)
+    if (div_rn(span[d], cell) > 1.0e9) cell = div_rn(span[d], 1.0e9);
+  out2[0] = div_rn(1.0, cell);
+  out2[1] = mul_rn(eps, eps);
+}
+
 // reverse complement of an MSB-first base-4 code with A=0,T=1,C=2,G=3
 inline uint32_t revcomp_code(uint32_t code, int k) {
   uint32_t rc = 0;

@@ -21,6 +21,11 @@ namespace {
 
 constexpr int MAXF = 4;
 constexpr unsigned FULL = 0xffffffffu;
+// tables up to this many points take eps_union_warp_kernel (a warp per point), larger ones eps_union_kernel
+// (a thread per point).  Measured on B200: the warp form wins at every size — 2000 points 103 -> ~10 us per
+// step, 200k points (C4) 23.3 -> 13.1 ms for the 48-eps grid — so the thread form is only reachable through
+// the measurement knob AM_EPS_WARP_MAX.
+constexpr int WARP_PER_POINT_MAX = 0x7fffffff;
 
 struct GridParams {
   double mn[MAXF];
@@ -43,10 +48,14 @@ __device__ __forceinline__ void cell_of(const double *x, const GridParams &gp, i
   for (int d = 0; d < gp.F; ++d) c[d] = (int)floor((x[d] - gp.mn[d]) * gp.inv_cell);
 }
 
+// `dyn` (device, may be null): {1 / cell edge, eps^2} of the step, read from memory instead of the launch
+// parameters so that ONE captured launch sequence serves every eps of a sweep (am_sweep.cu)
 __global__ void bucket_count_kernel(const double *__restrict__ X, int n, GridParams gp,
+                                    const double *__restrict__ dyn,
                                     unsigned *__restrict__ bucket_of, unsigned *__restrict__ counts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (dyn) gp.inv_cell = dyn[0];
   double x[MAXF];
   int c[MAXF];
   for (int d = 0; d < gp.F; ++d) x[d] = __ldg(X + (int64_t)i * gp.F + d);
@@ -107,12 +116,17 @@ __global__ void bucket_roots_kernel(int n, const unsigned *__restrict__ bucket_o
 
 // one thread per point (in bucket-sorted order)
 __global__ void __launch_bounds__(128)
-eps_union_kernel(int n, GridParams gp, double eps2, const unsigned *__restrict__ bucket_start,
+eps_union_kernel(int n, GridParams gp, double eps2, const double *__restrict__ dyn,
+                 const unsigned *__restrict__ bucket_start,
                  const int *__restrict__ sorted_idx, const double *__restrict__ sorted_x,
                  const int *__restrict__ rmin_inv, const int *__restrict__ rmax,
                  const int *__restrict__ sorted_root, int *__restrict__ parent) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= n) return;
+  if (dyn) {
+    gp.inv_cell = dyn[0];
+    eps2 = dyn[1];
+  }
   const int F = gp.F;
   double x[MAXF];
   int c[MAXF];
@@ -153,6 +167,79 @@ eps_union_kernel(int n, GridParams gp, double eps2, const unsigned *__restrict__
         dist = __dadd_rn(dist, __dmul_rn(tmp, tmp));
       }
       if (dist <= eps2) uf_union(parent, me, other);
+    }
+  }
+}
+
+// One WARP per point (the production form).  With one thread per point every thread walks its 3^F cells one
+// after the other — ~50 dependent global loads — so the pass is pure latency: 100 us for a 2000-point table
+// (16 CTAs on an otherwise empty GPU), and at 200k points only ~10 warps per scheduler with nothing to overlap
+// their stalls (ncu: issue active 29 %, long-scoreboard stalls on top).  Here the lanes look up the 3^F cells
+// at once (hash, the uniform-root test, the bucket bounds), then the warp goes through the cells that are
+// left, 32 candidates at a time.  Same tests, same unions, same forest as eps_union_kernel.
+__global__ void __launch_bounds__(256)
+eps_union_warp_kernel(int n, GridParams gp, double eps2, const double *__restrict__ dyn,
+                      const unsigned *__restrict__ bucket_start, const int *__restrict__ sorted_idx,
+                      const double *__restrict__ sorted_x, const int *__restrict__ rmin_inv,
+                      const int *__restrict__ rmax, const int *__restrict__ sorted_root, int *__restrict__ parent) {
+  const int lane = threadIdx.x & 31;
+  const int pos = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (pos >= n) return;  // the whole warp leaves together
+  if (dyn) {
+    gp.inv_cell = dyn[0];
+    eps2 = dyn[1];
+  }
+  const int F = gp.F;
+  double x[MAXF];
+  int c[MAXF];
+  for (int d = 0; d < F; ++d) x[d] = sorted_x[(int64_t)d * n + pos];
+  cell_of(x, gp, c);
+  const int me = sorted_idx[pos];
+  const int myroot0 = *((volatile int *)(parent + me));
+  int ncomb = 1;
+  for (int d = 0; d < F; ++d) ncomb *= 3;
+  for (int base = 0; base < ncomb; base += 32) {
+    const int comb = base + lane;
+    bool act = comb < ncomb;
+    unsigned b = 0xffffffffu, beg = 0, end = 0;
+    if (act) {
+      int cc[MAXF];
+      int t = comb;
+      for (int d = 0; d < F; ++d) {
+        cc[d] = c[d] + (t % 3) - 1;
+        t /= 3;
+      }
+      b = hash_cell(cc, F, gp.nbuckets_mask);
+    }
+    // a bucket reached through several cells (hash collisions) is scanned once per round of 32 cells; a
+    // second scan in a later round (F = 4) would only repeat unions that are already done
+    const unsigned same = __match_any_sync(FULL, b);
+    if (act && (__ffs(same) - 1) != lane) act = false;
+    if (act) {
+      if (__ldg(rmax + b) == myroot0 && 0x7fffffff - __ldg(rmin_inv + b) == myroot0) {
+        act = false;  // nothing to merge
+      } else {
+        beg = bucket_start[b];
+        end = bucket_start[b + 1];
+        act = end > beg;
+      }
+    }
+    unsigned todo = __ballot_sync(FULL, act);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const unsigned cb = __shfl_sync(FULL, beg, src), ce = __shfl_sync(FULL, end, src);
+      for (unsigned j = cb + lane; j < ce; j += 32) {
+        if (__ldg(sorted_root + j) == myroot0) continue;
+        const int other = sorted_idx[j];
+        if (other >= me) continue;  // each unordered pair once, from its larger row
+        double dist = 0.0;
+        for (int d = 0; d < F; ++d) {
+          const double tmp = __dsub_rn(x[d], sorted_x[(int64_t)d * n + j]);
+          dist = __dadd_rn(dist, __dmul_rn(tmp, tmp));
+        }
+        if (dist <= eps2) uf_union(parent, me, other);
+      }
     }
   }
 }
@@ -269,36 +356,22 @@ extern "C" int am_iota_i32(int32_t *d_v, int64_t n, void *stream) {
   return AM_OK;
 }
 
-extern "C" int am_eps_union(const double *d_X, int64_t n_points, int F, double eps,
-                            const double *h_min, const double *h_max, int32_t *d_parent,
-                            void *d_work, void *stream) {
-  if (F < 1 || F > MAXF) return am::fail(AM_EINVAL, "am_eps_union: F must be in 1..4");
-  if (n_points < 0 || n_points > 0x7fffffff) return am::fail(AM_EINVAL, "am_eps_union: bad n_points");
-  if (!(eps > 0.0)) return am::fail(AM_EINVAL, "am_eps_union: eps must be > 0");
-  if (n_points == 0) return AM_OK;
-  if (!d_X || !h_min || !h_max || !d_parent || !d_work) return am::fail(AM_EINVAL, "am_eps_union: null pointer");
-  cudaStream_t st = (cudaStream_t)stream;
+// the launch sequence of one eps step; `dyn` null: cell edge / eps^2 from (inv_cell, eps2)
+static int eps_union_launch(const double *d_X, int64_t n_points, int F, const double *h_min, double inv_cell,
+                            double eps2, const double *d_dyn, int32_t *d_parent, void *d_work, cudaStream_t st) {
   const int n = (int)n_points;
   Work w;
   carve(d_work, n_points, &w);
   const unsigned nb = pick_buckets(n_points);
   GridParams gp;
-  // cell edge slightly above eps so that |a-b| <= eps implies cell indices differ by <= 1
-  // even after rounding; cap the cell count per axis so indices stay well inside int range
-  double cell = eps * (1.0 + 1.0 / 1048576.0);
-  for (int d = 0; d < F; ++d) {
-    const double span = h_max[d] - h_min[d];
-    if (!(span >= 0.0)) return am::fail(AM_EINVAL, "am_eps_union: bad bounds (NaN?)");
-    if (span / cell > 1.0e9) cell = span / 1.0e9;
-  }
   for (int d = 0; d < MAXF; ++d) gp.mn[d] = d < F ? h_min[d] : 0.0;
-  gp.inv_cell = 1.0 / cell;
+  gp.inv_cell = inv_cell;
   gp.F = F;
   gp.nbuckets_mask = nb - 1;
-  AM_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)nb * 4, st));
-  AM_CUDA(cudaMemsetAsync(w.fill, 0, (size_t)nb * 4, st));
+  // counts | fill are adjacent in the workspace (nb * 4 is a multiple of the 256-byte carving unit)
+  AM_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)((char *)(w.fill + nb) - (char *)w.counts), st));
   const int blocks = (n + 255) / 256;
-  bucket_count_kernel<<<blocks, 256, 0, st>>>(d_X, n, gp, w.bucket_of, w.counts);
+  bucket_count_kernel<<<blocks, 256, 0, st>>>(d_X, n, gp, d_dyn, w.bucket_of, w.counts);
   AM_LAUNCHED("bucket_count_kernel");
   am::g_launches.fetch_add(am::exclusive_scan(w.counts, w.bucket_start, (int)nb, w.scan_tmp, st) - 1);
   AM_LAUNCHED("exclusive_scan");
@@ -309,10 +382,56 @@ extern "C" int am_eps_union(const double *d_X, int64_t n_points, int F, double e
   AM_CUDA(cudaMemsetAsync(w.rmax, 0xFF, (size_t)nb * 4, st));
   bucket_roots_kernel<<<blocks, 256, 0, st>>>(n, w.bucket_of, d_parent, w.rmin_inv, w.rmax);
   AM_LAUNCHED("bucket_roots_kernel");
-  eps_union_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, gp, eps * eps, w.bucket_start, w.sorted_idx,
-                                                    w.sorted_x, w.rmin_inv, w.rmax, w.sorted_root, d_parent);
-  AM_LAUNCHED("eps_union_kernel");
+  static const int warp_max = [] {
+    const char *v = getenv("AM_EPS_WARP_MAX");  // measurement knob
+    return v ? atoi(v) : WARP_PER_POINT_MAX;
+  }();
+  if (n <= warp_max) {
+    eps_union_warp_kernel<<<(unsigned)(((int64_t)n + 7) / 8), 256, 0, st>>>(n, gp, eps2, d_dyn, w.bucket_start, w.sorted_idx,
+                                                       w.sorted_x, w.rmin_inv, w.rmax, w.sorted_root, d_parent);
+    AM_LAUNCHED("eps_union_warp_kernel");
+  } else {
+    eps_union_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, gp, eps2, d_dyn, w.bucket_start, w.sorted_idx,
+                                                      w.sorted_x, w.rmin_inv, w.rmax, w.sorted_root, d_parent);
+    AM_LAUNCHED("eps_union_kernel");
+  }
   return AM_OK;
+}
+
+extern "C" int am_eps_grid(double eps, const double *h_min, const double *h_max, int F, double *out2) {
+  if (F < 1 || F > MAXF) return am::fail(AM_EINVAL, "am_eps_grid: F must be in 1..4");
+  if (!(eps > 0.0)) return am::fail(AM_EINVAL, "am_eps_grid: eps must be > 0");
+  if (!h_min || !h_max || !out2) return am::fail(AM_EINVAL, "am_eps_grid: null pointer");
+  double span[MAXF];
+  for (int d = 0; d < F; ++d) {
+    span[d] = h_max[d] - h_min[d];
+    if (!(span[d] >= 0.0)) return am::fail(AM_EINVAL, "am_eps_grid: bad bounds (NaN?)");
+  }
+  am::eps_grid(eps, span, F, out2);
+  return AM_OK;
+}
+
+extern "C" int am_eps_union(const double *d_X, int64_t n_points, int F, double eps,
+                            const double *h_min, const double *h_max, int32_t *d_parent,
+                            void *d_work, void *stream) {
+  if (F < 1 || F > MAXF) return am::fail(AM_EINVAL, "am_eps_union: F must be in 1..4");
+  if (n_points < 0 || n_points > 0x7fffffff) return am::fail(AM_EINVAL, "am_eps_union: bad n_points");
+  if (!(eps > 0.0)) return am::fail(AM_EINVAL, "am_eps_union: eps must be > 0");
+  if (n_points == 0) return AM_OK;
+  if (!d_X || !h_min || !h_max || !d_parent || !d_work) return am::fail(AM_EINVAL, "am_eps_union: null pointer");
+  double g[2];
+  const int rc = am_eps_grid(eps, h_min, h_max, F, g);
+  if (rc) return rc;
+  return eps_union_launch(d_X, n_points, F, h_min, g[0], g[1], nullptr, d_parent, d_work, (cudaStream_t)stream);
+}
+
+extern "C" int am_eps_union_dyn(const double *d_X, int64_t n_points, int F, const double *h_min,
+                                const double *d_dyn, int32_t *d_parent, void *d_work, void *stream) {
+  if (F < 1 || F > MAXF) return am::fail(AM_EINVAL, "am_eps_union_dyn: F must be in 1..4");
+  if (n_points < 0 || n_points > 0x7fffffff) return am::fail(AM_EINVAL, "am_eps_union_dyn: bad n_points");
+  if (n_points == 0) return AM_OK;
+  if (!d_X || !h_min || !d_dyn || !d_parent || !d_work) return am::fail(AM_EINVAL, "am_eps_union_dyn: null pointer");
+  return eps_union_launch(d_X, n_points, F, h_min, 0.0, 0.0, d_dyn, d_parent, d_work, (cudaStream_t)stream);
 }
 
 extern "C" int am_labels_from_parent(int32_t *d_parent, int64_t n_points, int64_t *d_labels,

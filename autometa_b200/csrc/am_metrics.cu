@@ -127,9 +127,12 @@ __global__ void finalize_kernel(const int *__restrict__ n_clusters, int M, const
                                 const int *__restrict__ present, const int *__restrict__ single, double cc,
                                 double pc, double cs, double gs, double *__restrict__ completeness,
                                 double *__restrict__ purity, double *__restrict__ cov_std,
-                                double *__restrict__ gc_std, int *hist) {
+                                double *__restrict__ gc_std, int *__restrict__ present_out,
+                                int *__restrict__ single_out, int *hist) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= *n_clusters) return;
+  present_out[c] = present[c];
+  single_out[c] = single[c];
   const double comp = __dmul_rn(__ddiv_rn((double)present[c], (double)M), 100.0);
   const double pur = __dmul_rn(__ddiv_rn((double)single[c], (double)present[c]), 100.0);  // 0/0 -> NaN like pandas
   const double k1 = (double)cnt[c] - 1.0;
@@ -195,7 +198,7 @@ extern "C" int am_cluster_metrics(const int64_t *d_labels, int64_t n_points, con
   const int n = (int)n_points, M = n_markers;
   MetricsBufs b;
   carve_metrics(d_work, n_points, M, &b);
-  AM_CUDA(cudaMemsetAsync(b.cnt, 0, (size_t)((char *)b.table - (char *)b.cnt), st));
+  // no memset here: the caller zero-filled d_work once and every call leaves it zeroed (below)
   const int blocks = (n + 255) / 256;
   point_sums_kernel<<<blocks, 256, 0, st>>>(d_labels, n, d_coverage, d_gc, b.cnt, b.s_cov, b.s_gc);
   AM_LAUNCHED("point_sums_kernel");
@@ -211,12 +214,10 @@ extern "C" int am_cluster_metrics(const int64_t *d_labels, int64_t n_points, con
   finalize_kernel<<<blocks, 256, 0, st>>>(d_n_clusters, M, b.cnt, b.ss_cov, b.ss_gc, b.present, b.single,
                                           completeness_cutoff, purity_cutoff, coverage_stddev_cutoff,
                                           gc_content_stddev_cutoff, d_completeness, d_purity, d_cov_std, d_gc_std,
-                                          b.hist);
+                                          d_present, d_single, b.hist);
   AM_LAUNCHED("finalize_kernel");
   median_kernel<<<1, 32, 0, st>>>(b.hist, M, d_n_clusters, d_summary);
   AM_LAUNCHED("median_kernel");
-  AM_CUDA(cudaMemcpyAsync(d_present, b.present, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-  AM_CUDA(cudaMemcpyAsync(d_single, b.single, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
   // leave the WHOLE workspace zeroed (the marker table already is: marker_count_kernel clears what it reads), so
   // that one zero-filled buffer can serve sweeps of any (n, M) without a per-sweep n x M memset
   AM_CUDA(cudaMemsetAsync(b.cnt, 0, (size_t)((char *)b.table - (char *)b.cnt), st));

@@ -559,3 +559,148 @@ class ClusterMetrics:
             present_marker_count=self.present[:k].cpu().numpy().astype(np.int64),
             single_copy_marker_count=self.single[:k].cpu().numpy().astype(np.int64),
         )
+
+
+class DeviceSweep:
+    """The whole eps sweep of ``recursive_dbscan`` (reference recursive_dbscan.py:172-215) resident on the
+    device (``csrc/am_sweep.cu``): eps step, labels, metrics, the loop's decisions (best eps so far, step x 10,
+    termination) and the copy of the best labels / metrics all run as device work; one step is captured into a
+    CUDA graph and replayed.  The host queues batches of steps on the sweep's OWN stream and reads one word per
+    batch, so several sweeps (the taxa of a rank) can be in flight at once.
+
+    ``launch(steps)`` queues; ``ready()`` / ``wait()`` tell when the batch has run; ``poll()`` -> has the sweep
+    ended; ``result()`` -> labels and metrics of the best eps on the host."""
+
+    #: steps queued per batch (a batch may overshoot the end of the sweep: extra steps change nothing)
+    BATCH = 16
+
+    def __init__(self, X: np.ndarray, coverage: np.ndarray, gc: np.ndarray, marker_rows, marker_cols, marker_vals,
+                 n_ref_markers: int, cutoffs, device, stream=None, trace_cap: int = 0, graph: bool = True):
+        import ctypes as C
+
+        import torch
+
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        self.n, self.F = X.shape
+        if self.n < 1:
+            raise ValueError("DeviceSweep needs at least one point")
+        if not 1 <= self.F <= 4:
+            raise ValueError(f"the GPU eps step supports 1..4 clustering features, got {self.F}")
+        self.dev = device
+        self.M = int(n_ref_markers)
+        self.trace_cap = int(trace_cap)
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=device)
+        n = self.n
+        with torch.cuda.device(device), torch.cuda.stream(self.stream):
+            up = lambda a, dt: torch.from_numpy(np.array(a, dtype=dt, order="C", copy=True)).to(device)
+            e = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
+            self.X = up(X, np.float64)
+            self.cov = up(coverage, np.float64)
+            self.gc = up(gc, np.float64)
+            self.nnz = int(len(marker_rows))
+            self.rows = up(marker_rows if self.nnz else np.zeros(1), np.int32)
+            self.cols = up(marker_cols if self.nnz else np.zeros(1), np.int32)
+            self.vals = up(marker_vals if self.nnz else np.zeros(1), np.int32)
+            self.parent = e(n, torch.int32)
+            self.labels = e(n, torch.int64)
+            self.n_clusters = e(1, torch.int32)
+            self.summary = e(4, torch.float64)
+            self.cur = [e(n, torch.float64) for _ in range(4)] + [e(n, torch.int32) for _ in range(2)]
+            self.best_labels = e(n, torch.int64)
+            self.best = [e(n, torch.float64) for _ in range(4)] + [e(n, torch.int32) for _ in range(2)]
+            self.w_dbscan = e(max(256, L.lib.am_dbscan_work_bytes(n)), torch.uint8)
+            # private marker scratch (zero-filled once): concurrent sweeps cannot share the per-device one
+            self.w_metrics = torch.zeros(max(256, L.lib.am_metrics_work_bytes(n, self.M)), dtype=torch.uint8,
+                                         device=device)
+            self.ctl = e(max(256, L.lib.am_sweep_ctl_bytes(n, self.trace_cap)), torch.uint8)
+            self.h_ctl = torch.zeros(L.SWEEP_CTL_WORDS, dtype=torch.float64).pin_memory()
+            a = L.SweepArgs()
+            a.d_X, a.n_points, a.F, a.n_markers = self.X.data_ptr(), n, self.F, self.M
+            mn, mx = X.min(axis=0), X.max(axis=0)
+            for d in range(self.F):
+                a.h_min[d], a.h_max[d] = float(mn[d]), float(mx[d])
+            a.d_parent, a.d_dbscan_work = self.parent.data_ptr(), self.w_dbscan.data_ptr()
+            a.d_labels, a.d_n_clusters = self.labels.data_ptr(), self.n_clusters.data_ptr()
+            a.d_marker_rows, a.d_marker_cols, a.d_marker_vals = (self.rows.data_ptr(), self.cols.data_ptr(),
+                                                                 self.vals.data_ptr())
+            a.nnz = self.nnz
+            a.d_coverage, a.d_gc = self.cov.data_ptr(), self.gc.data_ptr()
+            for i, c in enumerate(cutoffs):
+                a.cutoffs[i] = float(c)
+            (a.d_completeness, a.d_purity, a.d_cov_std, a.d_gc_std, a.d_present,
+             a.d_single) = [t.data_ptr() for t in self.cur]
+            a.d_summary, a.d_metrics_work, a.d_ctl = (self.summary.data_ptr(), self.w_metrics.data_ptr(),
+                                                      self.ctl.data_ptr())
+            a.d_best_labels = self.best_labels.data_ptr()
+            (a.d_best_completeness, a.d_best_purity, a.d_best_cov_std, a.d_best_gc_std, a.d_best_present,
+             a.d_best_single) = [t.data_ptr() for t in self.best]
+            a.trace_cap = self.trace_cap
+            self.args = a
+            self._argp = C.addressof(a)
+            st = self.stream.cuda_stream
+            L.check(L.lib.am_sweep_init(self._argp, st))
+            self.graph = None
+            if graph:
+                g = C.c_void_p()
+                L.check(L.lib.am_sweep_graph_create(self._argp, st, C.addressof(g)))
+                self.graph = g.value
+        self.event = torch.cuda.Event()
+        self.steps_queued = 0
+
+    def launch(self, steps: int = 0) -> None:
+        """Queue ``steps`` eps steps and the copy of the loop state to pinned host memory."""
+        steps = int(steps) or self.BATCH
+        st = self.stream.cuda_stream
+        if self.graph:
+            L.check(L.lib.am_sweep_graph_launch(self.graph, self._argp, steps, self.h_ctl.data_ptr(), st))
+        else:
+            L.check(L.lib.am_sweep_steps(self._argp, steps, self.h_ctl.data_ptr(), st))
+        self.event.record(self.stream)
+        self.steps_queued += steps
+
+    def ready(self) -> bool:
+        return self.event.query()
+
+    def wait(self) -> None:
+        self.event.synchronize()
+
+    def poll(self) -> bool:
+        """After the batch has run: True once the sweep has ended."""
+        return bool(self.h_ctl[L.SWEEP_DONE].item() != 0.0)
+
+    def state(self) -> np.ndarray:
+        return self.h_ctl.numpy().copy()
+
+    def result(self):
+        """``(labels int64[n], per-cluster metrics dict, best median, n_clusters at the best eps, trace)`` —
+        labels is None when no step was ever kept (cannot happen: the first step's median >= -inf)."""
+        import torch
+
+        self.wait()
+        ctl = self.state()
+        nc = int(ctl[L.SWEEP_BEST_NC])
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
+            labels = self.best_labels.cpu().numpy()
+            names = ("completeness", "purity", "coverage_stddev", "gc_content_stddev", "present_marker_count",
+                     "single_copy_marker_count")
+            m = {k: t[:nc].cpu().numpy() for k, t in zip(names, self.best)}
+            trace = None
+            if self.trace_cap:
+                k = min(int(ctl[L.SWEEP_NSTEPS]), self.trace_cap)
+                off = (L.SWEEP_CTL_WORDS * 8 + 255) // 256 * 256 + ((self.n + 1) * 4 + 255) // 256 * 256
+                trace = self.ctl[off : off + k * 32].cpu().numpy().view(np.float64).reshape(k, 4)
+        for k2 in ("present_marker_count", "single_copy_marker_count"):
+            m[k2] = m[k2].astype(np.int64)
+        return labels, m, float(ctl[L.SWEEP_BEST]), nc, trace
+
+    def close(self) -> None:
+        if self.graph:
+            self.wait()
+            L.check(L.lib.am_sweep_graph_destroy(self.graph))
+            self.graph = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

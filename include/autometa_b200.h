@@ -345,7 +345,7 @@ int am_iota_i32(int32_t *d_v, int64_t n, void *stream);
  * as used inside the sweep (recursive_dbscan.py:180-192).
  *   d_labels[n_points] int64 (0-based, from am_labels_from_parent), d_n_clusters int32[1];
  *   contig x marker counts in COO form (rows index points), n_markers = reference marker count M;
- *   outputs per cluster c < n_clusters: completeness, purity (NaN when nothing present),
+ *   outputs per cluster c < n_clusters (entries beyond are left untouched): completeness, purity (NaN when nothing present),
  *   coverage / GC sigma (ddof 1, NaN for singletons), present / single-copy marker counts;
  *   d_summary[3] = {n_clusters, median completeness of passing clusters (-inf if none), n passing}.
  * d_work: am_metrics_work_bytes(n_points, M) bytes, zero-filled once by the caller; the call leaves it
@@ -359,6 +359,92 @@ int am_cluster_metrics(const int64_t *d_labels, int64_t n_points, const int32_t 
                        double gc_content_stddev_cutoff, double *d_completeness, double *d_purity,
                        double *d_cov_std, double *d_gc_std, int32_t *d_present, int32_t *d_single,
                        double *d_summary, void *d_work, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * The eps step with its grid read from device memory, and the grid of an eps on the host.
+ *   am_eps_grid       out2 = {1 / cell edge, eps * eps} for the bounding box [h_min, h_max] — the two
+ *                     eps-dependent values of a step (what am_eps_union derives from its `eps` argument)
+ *   am_eps_union_dyn  am_eps_union with those two doubles read from d_dyn[2] when the kernels run, so the
+ *                     same launch sequence (or its captured graph) serves every eps of a sweep */
+int am_eps_grid(double eps, const double *h_min, const double *h_max, int F, double *out2);
+int am_eps_union_dyn(const double *d_X, int64_t n_points, int F, const double *h_min /*F*/,
+                     const double *d_dyn /*2*/, int32_t *d_parent, void *d_work, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * The WHOLE eps sweep of recursive_dbscan (autometa/binning/recursive_dbscan.py:172-215) resident on the
+ * device: besides the step itself (am_eps_union_dyn -> am_labels_from_parent -> am_cluster_metrics) a
+ * one-thread controller kernel advances the loop state exactly as the reference's Python does —
+ *     take = median >= best_median (:194-196);  clustering_rounds[n_clusters] += 1 (:199-202);
+ *     > 10 -> step *= 10 (:204-205);  median == 0 -> clustering_rounds[0] += 1 (:206-207);
+ *     clustering_rounds[0] >= 10 -> stop (:208-209);  eps += step (:215);  n_clusters <= 1 -> stop (:179)
+ * (IEEE double add / multiply without contraction = Python float arithmetic) — writes the next step's grid
+ * to where am_eps_union_dyn reads it, and a copy kernel keeps the labels and per-cluster metrics of the best
+ * eps so far.  The host therefore neither reads anything back per eps nor decides anything: it queues steps
+ * (one captured CUDA graph per step, replayed) and looks at the `done` word once per batch.  Steps queued
+ * after the sweep has ended change nothing (the state is frozen and the step at an unchanged eps is
+ * idempotent), so batches may overshoot.
+ *
+ * All buffers belong to the caller (device unless named h_*):
+ *   d_ctl            am_sweep_ctl_bytes(n_points, trace_cap) bytes: AM_SWEEP_CTL_WORDS doubles of loop state
+ *                    (indices AM_SWEEP_*), then int32 clustering_rounds[n_points + 1], then the trace,
+ *                    trace_cap x 4 doubles {eps, n_clusters, median, best_median} per executed step
+ *   d_metrics_work   am_metrics_work_bytes, zero-filled once; d_dbscan_work am_dbscan_work_bytes
+ *   d_* / d_best_*   the per-cluster outputs of am_cluster_metrics for the current / the best eps
+ * am_sweep_init resets the state (eps 0.3, step 0.1, best -inf, forest = identity).  am_sweep_steps queues
+ * `repeats` steps as plain launches; am_sweep_graph_create captures one step on `stream` (which must not be
+ * the legacy default stream) into an executable graph, am_sweep_graph_launch replays it `repeats` times.
+ * Both then copy the AM_SWEEP_CTL_WORDS state doubles to h_ctl (pinned) on the same stream when h_ctl is
+ * not null. */
+#define AM_SWEEP_CTL_WORDS 32
+#define AM_SWEEP_EPS 0        /* eps of the next step to run                       */
+#define AM_SWEEP_STEP 1       /* current increment                                 */
+#define AM_SWEEP_BEST 2       /* best median completeness so far (-inf: none yet)  */
+#define AM_SWEEP_DONE 3       /* 1 once the loop has ended                         */
+#define AM_SWEEP_NSTEPS 4     /* steps executed                                    */
+#define AM_SWEEP_BEST_STEP 5  /* 0-based step the kept labels come from (-1: none) */
+#define AM_SWEEP_BEST_NC 6    /* number of clusters at that step                   */
+#define AM_SWEEP_LAST_NC 7
+#define AM_SWEEP_LAST_MED 8
+#define AM_SWEEP_TAKE 9       /* 1 while the current step is the new best          */
+#define AM_SWEEP_INV_CELL 10  /* d_dyn of am_eps_union_dyn: {1 / cell, eps^2}      */
+#define AM_SWEEP_EPS2 11
+#define AM_SWEEP_SPAN 12      /* 4 doubles: h_max - h_min                          */
+#define AM_SWEEP_BEST_EPS 16  /* eps of the kept step                              */
+typedef struct am_sweep_args {
+  const double *d_X;            /* [n_points x F] row-major */
+  int64_t n_points;
+  int32_t F;
+  int32_t n_markers;            /* reference marker count M */
+  double h_min[4], h_max[4];    /* bounding box of X */
+  int32_t *d_parent;            /* [n_points] forest */
+  void *d_dbscan_work;
+  int64_t *d_labels;            /* [n_points] current step */
+  int32_t *d_n_clusters;        /* [1] */
+  const int32_t *d_marker_rows, *d_marker_cols, *d_marker_vals;
+  int64_t nnz;
+  const double *d_coverage, *d_gc;
+  double cutoffs[4];            /* completeness, purity, coverage sigma, GC sigma */
+  double *d_completeness, *d_purity, *d_cov_std, *d_gc_std;
+  int32_t *d_present, *d_single;
+  double *d_summary;            /* [4] */
+  void *d_metrics_work;
+  void *d_ctl;
+  int64_t *d_best_labels;
+  double *d_best_completeness, *d_best_purity, *d_best_cov_std, *d_best_gc_std;
+  int32_t *d_best_present, *d_best_single;
+  int32_t trace_cap;
+  int32_t reserved;
+} am_sweep_args;
+int64_t am_sweep_args_size(void); /* sizeof(am_sweep_args): lets a binding check its struct layout */
+int64_t am_sweep_ctl_bytes(int64_t n_points, int trace_cap);
+int am_sweep_init(const am_sweep_args *a, void *stream);
+int am_sweep_steps(const am_sweep_args *a, int repeats, double *h_ctl, void *stream);
+int am_sweep_graph_create(const am_sweep_args *a, void *stream, void **graph_out);
+int am_sweep_graph_launch(void *graph, const am_sweep_args *a, int repeats, double *h_ctl, void *stream);
+int am_sweep_graph_destroy(void *graph);
+/* The controller's state machine on the host, for tests: advances ctl / rounds by one step with the given
+ * outcome (n_clusters, median) exactly as the device kernel does; returns 1 when the step is the new best. */
+int am_sweep_advance_host(double *ctl, int32_t *rounds, int F, int n_clusters, double median);
 
 /* ---------------------------------------------------------------------------
  * Host-side TSV I/O of the k-mer tables, all host threads.

@@ -493,6 +493,118 @@ def test_recursive_dbscan_matches_reference_golden(torch_cuda, golden_dbscan):
     assert np.array_equal(unclustered["cluster"].to_numpy(), golden_dbscan["unclustered_cluster"])
 
 
+def _frames_equal(a, b):
+    assert a.index.tolist() == b.index.tolist() and a.columns.tolist() == b.columns.tolist()
+    for c in a.columns:
+        x, y = a[c].to_numpy(), b[c].to_numpy()
+        if x.dtype.kind == "f" or y.dtype.kind == "f":
+            # the sigma columns are sums of fp64 atomics: the last ulp depends on the order the adds retire in
+            assert np.allclose(x.astype(float), y.astype(float), rtol=1e-12, atol=0, equal_nan=True), c
+        else:
+            assert [None if pd.isna(v) else v for v in x] == [None if pd.isna(v) else v for v in y], c
+
+
+def test_device_resident_sweep_equals_host_driven_loop(torch_cuda, monkeypatch):
+    """The sweep with its loop state on the device (controller kernel + CUDA-graph replays, csrc/am_sweep.cu)
+    against the same sweep with one read-back per eps and the schedule in Python: same best eps, same step
+    count, identical labels, counts and completeness / purity (sigma to 1e-12); graph replays == plain launches; extra steps past the end change
+    nothing."""
+    import torch
+
+    from autometa_b200 import _lib as L
+    from autometa_b200 import device as D
+    from autometa_b200 import synth
+    from autometa_b200.binning import recursive_dbscan as R
+    from autometa_b200.binning.utilities import markers_coo
+
+    dev = torch.device("cuda", 0)
+    for n, k, seed in ((3000, 12, 11), (700, 5, 4), (2, 1, 1), (60, 3, 9)):
+        table, markers = synth.make_sweep_input(n_points=n, n_clusters=k, n_markers=40, seed=seed)
+        cut = (20.0, 90.0, 25.0, 5.0)
+        X = R._feature_matrix(table)
+        cov, gc = table["coverage"].to_numpy(), table["gc_content"].to_numpy()
+        rows, cols, vals = markers_coo(markers, table.index)
+        want_labels, want_m, want_best = R._sweep_hostloop(X, cov, gc, rows, cols, vals, markers.shape[1], cut, dev, False)
+        states = []
+        for graph in (True, False):
+            run = D.DeviceSweep(X, cov, gc, rows, cols, vals, markers.shape[1], cut, dev, trace_cap=512, graph=graph)
+            batches = 0
+            while True:
+                run.launch(7)
+                run.wait()
+                batches += 1
+                if run.poll():
+                    break
+            run.launch(5)  # past the end: frozen
+            run.wait()
+            labels, m, best, nc, trace = run.result()
+            st = run.state()
+            run.close()
+            assert np.array_equal(labels, want_labels), (n, graph)
+            assert best == want_best and nc == len(want_m["completeness"])
+            for key in want_m:  # sigma: sums of fp64 atomics, last-ulp order dependence; the rest is exact
+                if key.endswith("stddev"):
+                    assert np.allclose(m[key], want_m[key], rtol=1e-12, atol=0, equal_nan=True), (n, graph, key)
+                else:
+                    assert np.array_equal(m[key], want_m[key], equal_nan=True), (n, graph, key)
+            n_steps = int(st[L.SWEEP_NSTEPS])
+            assert trace.shape == (n_steps, 4) and n_steps <= 7 * batches
+            # the eps of every step = the reference's schedule replayed on the outcomes the steps produced
+            eps, step, rounds = 0.3, 0.1, {0: 0}
+            for t_eps, t_nc, t_med, _ in trace:
+                assert t_eps == eps
+                rounds[int(t_nc)] = rounds.get(int(t_nc), 0) + 1
+                if rounds[int(t_nc)] > 10:
+                    step *= 10
+                if t_med == 0:
+                    rounds[0] += 1
+                eps += step
+            assert trace[int(st[L.SWEEP_BEST_STEP]), 0] == st[L.SWEEP_BEST_EPS]
+            assert trace[-1, 3] == best
+            states.append((n_steps, st[L.SWEEP_BEST_EPS], st[L.SWEEP_EPS], st[L.SWEEP_STEP]))
+        assert states[0] == states[1]
+    # the API in both modes (frames as the reference builds them)
+    table, markers = _sweep_table()
+    a = R.recursive_dbscan(table.copy(), markers, 20.0, 90.0, 25.0, 5.0, verbose=True)
+    monkeypatch.setenv("AUTOMETA_B200_SWEEP", "host")
+    b = R.recursive_dbscan(table.copy(), markers, 20.0, 90.0, 25.0, 5.0)
+    monkeypatch.delenv("AUTOMETA_B200_SWEEP")
+    _frames_equal(a[0], b[0])
+    _frames_equal(a[1], b[1])
+    launches = L.launch_count()
+    R.recursive_dbscan(table.copy(), markers, 20.0, 90.0, 25.0, 5.0)
+    assert L.launch_count() - launches >= 16 * 15  # replays are counted as the kernels they launch
+
+
+def test_get_clusters_many_equals_one_at_a_time(torch_cuda):
+    """Sweeps in flight together (own streams, own scratch) give the frames of one-at-a-time calls."""
+    from autometa_b200 import synth
+    from autometa_b200.binning import recursive_dbscan as R
+
+    tables = []
+    markers = None
+    for i, (n, k) in enumerate(((1500, 9), (400, 4), (1, 1), (2500, 15), (90, 3), (800, 6), (1200, 7))):
+        t, m = synth.make_sweep_input(n_points=n, n_clusters=k, n_markers=40, seed=21 + i)
+        t.index = pd.Index([f"T{i}_{c}" for c in t.index], name="contig")
+        m.index = pd.Index([f"T{i}_{c}" for c in m.index], name="contig")
+        tables.append(t)
+        markers = m if markers is None else pd.concat([markers, m])
+    one = [R.get_clusters(t.copy(), markers, 20.0, 90.0, 25.0, 5.0, method="dbscan") for t in tables]
+    many = R.get_clusters_many([t.copy() for t in tables], markers, 20.0, 90.0, 25.0, 5.0, method="dbscan")
+    assert len(many) == len(one)
+    for a, b in zip(one, many):
+        _frames_equal(a, b)
+    old = R._IN_FLIGHT_MAX
+    try:
+        R._IN_FLIGHT_MAX = 2  # slots (streams) reused by later jobs
+        few = R.get_clusters_many([t.copy() for t in tables], markers, 20.0, 90.0, 25.0, 5.0, method="dbscan")
+    finally:
+        R._IN_FLIGHT_MAX = old
+    for a, b in zip(one, few):
+        _frames_equal(a, b)
+    assert R.get_clusters_many([], markers, 20.0, 90.0, 25.0, 5.0, method="dbscan") == []
+
+
 def test_sweep_incremental_equals_fresh_and_oracle(torch_cuda):
     import torch
 

@@ -442,3 +442,149 @@ def test_ldm_checkpoint_round_trip(tmp_path):
         assert head[0].strip() == "#-- Parameters --#" and head[12].strip() == "#-- Runtime Variables --#"
         assert head[10].startswith("# min-partition-size: 51 (max([pca_dimensions + 1, embed_dimensions + 1])")
         assert head[13].strip() == "# rank: class" and head[14].strip() == "# name: Bacilli"
+
+
+# ----------------------------------------------------------------------------- device-resident sweep (host side)
+def _reference_loop(outcomes):
+    """The loop body of the reference after the metrics (recursive_dbscan.py:172-215), fed with the
+    (n_clusters, median) a step produced; returns the per-step (eps, take, step, done)."""
+    eps, step = 0.3, 0.1
+    clustering_rounds = {0: 0}
+    best_median = float("-inf")
+    out = []
+    for n_clusters, median_completeness in outcomes:
+        this_eps = eps
+        take = median_completeness >= best_median
+        if take:
+            best_median = median_completeness
+        if n_clusters in clustering_rounds:
+            clustering_rounds[n_clusters] += 1
+        else:
+            clustering_rounds[n_clusters] = 1
+        if clustering_rounds[n_clusters] > 10:
+            step *= 10
+        if median_completeness == 0:
+            clustering_rounds[0] += 1
+        done = False
+        if clustering_rounds[0] >= 10:
+            done = True
+        else:
+            eps += step
+            done = not (n_clusters > 1)
+        out.append((this_eps, take, step, done, best_median, eps))
+        if done:
+            break
+    return out
+
+
+@pytest.mark.parametrize("case", ["plateaus", "zero_medians", "single_cluster_at_once", "random"])
+def test_sweep_controller_advances_like_the_reference_loop(case):
+    """am_sweep_advance_host runs the same code as the device controller kernel (csrc/am_sweep.cu)."""
+    from autometa_b200 import _lib as L
+
+    rng = np.random.default_rng(5)
+    if case == "plateaus":      # the same cluster count > 10 times -> step x 10, twice; ends at one cluster
+        outcomes = [(50, float("-inf"))] * 3 + [(40, 12.5)] * 14 + [(7, 30.0)] * 12 + [(3, 30.0), (2, 10.0), (1, 0.5)]
+    elif case == "zero_medians":  # median == 0 ten times -> break (and counts towards clustering_rounds[0])
+        outcomes = [(90 - i, 0.0) for i in range(30)]
+    elif case == "single_cluster_at_once":
+        outcomes = [(1, float("-inf"))]
+    else:
+        ncs = np.maximum(1, 200 - np.cumsum(rng.integers(0, 6, size=400)))
+        meds = rng.choice([float("-inf"), 0.0, 10.0, 20.0, 35.5], size=400)
+        outcomes = list(zip(ncs.tolist(), meds.tolist()))
+    want = _reference_loop(outcomes)
+    n_max = max(nc for nc, _ in outcomes)
+    ctl = np.zeros(L.SWEEP_CTL_WORDS, dtype=np.float64)
+    ctl[L.SWEEP_EPS], ctl[L.SWEEP_STEP], ctl[L.SWEEP_BEST], ctl[L.SWEEP_BEST_STEP] = 0.3, 0.1, -np.inf, -1.0
+    span = np.array([200.0, 150.0, 500.0, 0.0])
+    ctl[L.SWEEP_SPAN : L.SWEEP_SPAN + 4] = span
+    rounds = np.zeros(n_max + 1, dtype=np.int32)
+    mn, g = np.zeros(4), np.zeros(2)
+    for k, (nc, med) in enumerate(outcomes):
+        eps_before = ctl[L.SWEEP_EPS]
+        take = L.lib.am_sweep_advance_host(L.np_ptr(ctl), L.np_ptr(rounds), 3, int(nc), float(med))
+        w_eps, w_take, w_step, w_done, w_best, w_next = want[k]
+        assert eps_before == w_eps                      # bit-identical float accumulation
+        assert take == int(w_take) and ctl[L.SWEEP_TAKE] == float(w_take)
+        assert ctl[L.SWEEP_STEP] == w_step and ctl[L.SWEEP_BEST] == w_best
+        assert ctl[L.SWEEP_EPS] == w_next and bool(ctl[L.SWEEP_DONE]) == w_done
+        assert ctl[L.SWEEP_NSTEPS] == k + 1
+        if w_done:
+            break
+        # the grid the next step reads = am_eps_grid of the next eps
+        L.check(L.lib.am_eps_grid(float(w_next), L.np_ptr(mn), L.np_ptr(span), 3, L.np_ptr(g)))
+        assert ctl[L.SWEEP_INV_CELL] == g[0] and ctl[L.SWEEP_EPS2] == g[1]
+    assert k + 1 == len(want) and want[-1][3]
+    # frozen afterwards: further steps change nothing
+    before = ctl.copy()
+    assert L.lib.am_sweep_advance_host(L.np_ptr(ctl), L.np_ptr(rounds), 3, 5, 50.0) == 0
+    before[L.SWEEP_TAKE] = 0.0
+    assert np.array_equal(ctl, before)
+
+
+def test_sweep_controller_first_48_eps_are_the_reference_schedule():
+    from autometa_b200 import _lib as L
+
+    ctl = np.zeros(L.SWEEP_CTL_WORDS, dtype=np.float64)
+    ctl[L.SWEEP_EPS], ctl[L.SWEEP_STEP], ctl[L.SWEEP_BEST] = 0.3, 0.1, -np.inf
+    rounds = np.zeros(1000, dtype=np.int32)
+    got = []
+    for k in range(48):
+        got.append(ctl[L.SWEEP_EPS])
+        L.lib.am_sweep_advance_host(L.np_ptr(ctl), L.np_ptr(rounds), 2, 900 - k, 10.0)
+    assert got == O.eps_schedule(48)
+    assert got[5] == 0.7999999999999999 and got[47] == 4.999999999999998  # SURVEY appendix A.7
+
+
+def test_eps_grid_matches_the_step_formula():
+    from autometa_b200 import _lib as L
+
+    mn = np.array([-3.0, 0.0, 1.0, 0.0])
+    mx = np.array([5.0, 2.0e12, 1.0, 0.0])
+    g = np.zeros(2)
+    for eps in (0.3, 0.7999999999999999, 5.0, 1e3):
+        L.check(L.lib.am_eps_grid(eps, L.np_ptr(mn), L.np_ptr(mx), 3, L.np_ptr(g)))
+        cell = eps * (1.0 + 1.0 / 1048576.0)
+        for d in range(3):
+            if (mx[d] - mn[d]) / cell > 1.0e9:
+                cell = (mx[d] - mn[d]) / 1.0e9
+        assert g[0] == 1.0 / cell and g[1] == eps * eps
+    assert L.lib.am_eps_grid(0.0, L.np_ptr(mn), L.np_ptr(mx), 3, L.np_ptr(g)) == L.AM_EINVAL
+    assert L.lib.am_eps_grid(1.0, L.np_ptr(mx), L.np_ptr(mn), 3, L.np_ptr(g)) == L.AM_EINVAL
+    assert L.lib.am_sweep_ctl_bytes(1000, 0) >= 32 * 8 + 1001 * 4
+    assert L.lib.am_sweep_ctl_bytes(1000, 64) - L.lib.am_sweep_ctl_bytes(1000, 0) == 64 * 32
+
+
+def test_sweep_driver_keeps_order_and_limit():
+    """_drive: results in job order, never more than ``limit`` jobs in flight, slots reused."""
+    from autometa_b200.binning import recursive_dbscan as R
+
+    class Wait:
+        def __init__(self, polls):
+            self.polls = polls
+
+        def ready(self):
+            self.polls -= 1
+            return self.polls <= 0
+
+        def wait(self):
+            self.polls = 0
+
+    live, peak, slots_seen = set(), [0], []
+
+    def job(i, slot, n_yields):
+        live.add(i)
+        slots_seen.append(slot)
+        peak[0] = max(peak[0], len(live))
+        for y in range(n_yields):
+            yield Wait(polls=(i * 7 + y) % 4)
+        live.discard(i)
+        return ("result", i)
+
+    starters = [(lambda slot, i=i: job(i, slot, n_yields=(i * 3) % 5)) for i in range(11)]
+    assert R._drive(starters, limit=3) == [("result", i) for i in range(11)]
+    assert peak[0] == 3 and set(slots_seen) == {0, 1, 2}
+    assert R._drive(starters[:2], limit=1) == [("result", 0), ("result", 1)]
+    assert R._drive([], limit=4) == []
+    assert R._in_flight(10_000, 140) == 16 and R._in_flight(2_000_000, 140) >= 1
