@@ -177,6 +177,7 @@ eps_union_kernel(int n, GridParams gp, double eps2, const double *__restrict__ d
 // their stalls (ncu: issue active 29 %, long-scoreboard stalls on top).  Here the lanes look up the 3^F cells
 // at once (hash, the uniform-root test, the bucket bounds), then the warp goes through the cells that are
 // left, 32 candidates at a time.  Same tests, same unions, same forest as eps_union_kernel.
+template <int F>
 __global__ void __launch_bounds__(256)
 eps_union_warp_kernel(int n, GridParams gp, double eps2, const double *__restrict__ dyn,
                       const unsigned *__restrict__ bucket_start, const int *__restrict__ sorted_idx,
@@ -189,40 +190,44 @@ eps_union_warp_kernel(int n, GridParams gp, double eps2, const double *__restric
     gp.inv_cell = dyn[0];
     eps2 = dyn[1];
   }
-  const int F = gp.F;
-  double x[MAXF];
-  int c[MAXF];
+  // F is a template parameter: the per-feature loops unroll and x / c / cc live in registers (with a run-time
+  // F they were indexed stack arrays — half of the kernel's instructions were local loads and stores)
+  double x[F];
+  int c[F];
+#pragma unroll
   for (int d = 0; d < F; ++d) x[d] = sorted_x[(int64_t)d * n + pos];
-  cell_of(x, gp, c);
+#pragma unroll
+  for (int d = 0; d < F; ++d) c[d] = (int)floor((x[d] - gp.mn[d]) * gp.inv_cell);
   const int me = sorted_idx[pos];
   const int myroot0 = *((volatile int *)(parent + me));
-  int ncomb = 1;
-  for (int d = 0; d < F; ++d) ncomb *= 3;
-  for (int base = 0; base < ncomb; base += 32) {
+  constexpr int NCOMB = F == 1 ? 3 : F == 2 ? 9 : F == 3 ? 27 : 81;
+  for (int base = 0; base < NCOMB; base += 32) {
     const int comb = base + lane;
-    bool act = comb < ncomb;
+    bool act = comb < NCOMB;
     unsigned b = 0xffffffffu, beg = 0, end = 0;
     if (act) {
-      int cc[MAXF];
       int t = comb;
+      unsigned h = 0x9E3779B9u;  // hash_cell, unrolled
+#pragma unroll
       for (int d = 0; d < F; ++d) {
-        cc[d] = c[d] + (t % 3) - 1;
+        const int ccd = c[d] + (t % 3) - 1;
         t /= 3;
+        h ^= (unsigned)ccd + 0x9E3779B9u + (h << 6) + (h >> 2);
+        h *= 0x85EBCA6Bu;
+        h ^= h >> 13;
       }
-      b = hash_cell(cc, F, gp.nbuckets_mask);
+      b = h & gp.nbuckets_mask;
     }
     // a bucket reached through several cells (hash collisions) is scanned once per round of 32 cells; a
     // second scan in a later round (F = 4) would only repeat unions that are already done
     const unsigned same = __match_any_sync(FULL, b);
     if (act && (__ffs(same) - 1) != lane) act = false;
     if (act) {
-      if (__ldg(rmax + b) == myroot0 && 0x7fffffff - __ldg(rmin_inv + b) == myroot0) {
-        act = false;  // nothing to merge
-      } else {
-        beg = bucket_start[b];
-        end = bucket_start[b + 1];
-        act = end > beg;
-      }
+      // all four words of the bucket in flight together (one latency, not two)
+      const int hi = __ldg(rmax + b), lo_inv = __ldg(rmin_inv + b);
+      beg = __ldg(bucket_start + b);
+      end = __ldg(bucket_start + b + 1);
+      act = end > beg && !(hi == myroot0 && 0x7fffffff - lo_inv == myroot0);  // else: nothing to merge
     }
     unsigned todo = __ballot_sync(FULL, act);
     while (todo) {
@@ -230,12 +235,13 @@ eps_union_warp_kernel(int n, GridParams gp, double eps2, const double *__restric
       todo &= todo - 1;
       const unsigned cb = __shfl_sync(FULL, beg, src), ce = __shfl_sync(FULL, end, src);
       for (unsigned j = cb + lane; j < ce; j += 32) {
-        if (__ldg(sorted_root + j) == myroot0) continue;
-        const int other = sorted_idx[j];
-        if (other >= me) continue;  // each unordered pair once, from its larger row
+        const int root_j = __ldg(sorted_root + j), other = __ldg(sorted_idx + j);
+        if (root_j == myroot0) continue;  // already in my component when the step began
+        if (other >= me) continue;        // each unordered pair once, from its larger row
         double dist = 0.0;
+#pragma unroll
         for (int d = 0; d < F; ++d) {
-          const double tmp = __dsub_rn(x[d], sorted_x[(int64_t)d * n + j]);
+          const double tmp = __dsub_rn(x[d], __ldg(sorted_x + (int64_t)d * n + j));
           dist = __dadd_rn(dist, __dmul_rn(tmp, tmp));
         }
         if (dist <= eps2) uf_union(parent, me, other);
@@ -387,8 +393,17 @@ static int eps_union_launch(const double *d_X, int64_t n_points, int F, const do
     return v ? atoi(v) : WARP_PER_POINT_MAX;
   }();
   if (n <= warp_max) {
-    eps_union_warp_kernel<<<(unsigned)(((int64_t)n + 7) / 8), 256, 0, st>>>(n, gp, eps2, d_dyn, w.bucket_start, w.sorted_idx,
-                                                       w.sorted_x, w.rmin_inv, w.rmax, w.sorted_root, d_parent);
+    const unsigned wblocks = (unsigned)(((int64_t)n + 7) / 8);
+#define AM_WARP_UNION(FF)                                                                                      \
+  eps_union_warp_kernel<FF><<<wblocks, 256, 0, st>>>(n, gp, eps2, d_dyn, w.bucket_start, w.sorted_idx, w.sorted_x, \
+                                                     w.rmin_inv, w.rmax, w.sorted_root, d_parent)
+    switch (F) {
+      case 1: AM_WARP_UNION(1); break;
+      case 2: AM_WARP_UNION(2); break;
+      case 3: AM_WARP_UNION(3); break;
+      default: AM_WARP_UNION(4); break;
+    }
+#undef AM_WARP_UNION
     AM_LAUNCHED("eps_union_warp_kernel");
   } else {
     eps_union_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, gp, eps2, d_dyn, w.bucket_start, w.sorted_idx,

@@ -10,7 +10,7 @@ from autometa_b200.binning.utilities import markers_coo
 
 dev = torch.device("cuda", 0)
 out = {}
-sizes = (2000,) if os.environ.get("NCU") else (500, 2000, 10000, 200000)
+sizes = (int(os.environ.get("N", 2000)),) if os.environ.get("NCU") else (500, 2000, 10000, 200000)
 for n in sizes:
     table, markers = synth.make_sweep_input(n_points=n, n_clusters=max(3, n // 400), n_markers=40, seed=7)
     X = R._feature_matrix(table)
