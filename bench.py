@@ -236,7 +236,8 @@ def sweep_bench(dev, torch, cpu=True, reps=3):
         "n_points": n, "n_eps": len(grid), "clusters_at_last_eps": ncl[0], "gpu_launches": int(L0),
         "algorithmic_bytes_per_eps": 8 * 3 * n + 8 * n,
         "achieved_GBps_algorithmic": (8 * 3 * n + 8 * n) * len(grid) / t / 1e9,
-        "note": "latency/ALU-bound (6.4 MB per eps is HBM-trivial); incremental union-find forest across eps",
+        "note": "latency/instruction-bound (6.4 MB per eps is HBM-trivial); incremental union-find forest across "
+                "eps; neighbour pass = one warp per point over a hashed cell list (eps_union_warp_kernel)",
     }
     # the same sweep through the reference-facing API (recursive_dbscan.py:114-234 semantics: eps
     # schedule until one cluster remains, per-eps metrics + cutoff filter + best-eps rule), host
@@ -252,7 +253,9 @@ def sweep_bench(dev, torch, cpu=True, reps=3):
         cl, un = R.recursive_dbscan(tb, markers, 20.0, 95.0, 25.0, 5.0)
         out["api"] = {"value": time.perf_counter() - t0, "unit": "s",
                       "call": "recursive_dbscan(table, markers_df, 20, 95, 25, 5) incl. DataFrame in/out, all eps "
-                              "until one cluster remains, device-side add_metrics/filter/median",
+                              "until one cluster remains; eps step, add_metrics / filter / median AND the loop's "
+                              "decisions (best eps, step x 10, termination) on the device: one captured CUDA graph "
+                              "per step, replayed in batches of 16, one word read back per batch (csrc/am_sweep.cu)",
                       "clustered": int(cl.shape[0]), "unclustered": int(un.shape[0])}
     except Exception as exc:  # keep the bench line even if the API leg fails
         out["api"] = {"error": repr(exc)}
