@@ -306,6 +306,11 @@ int launch_count(const uint32_t *d_codes, const uint32_t *d_bitmap, const uint32
   int occ = 0;
   AM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
   if (occ < 1) return am::fail(AM_ECUDA, "count kernel does not fit on an SM");
+  static const int occ_cap = [] {
+    const char *v = getenv("AM_COUNT_OCC");  // measurement knob: resident CTAs per SM the grid is sized for
+    return v ? atoi(v) : 0;
+  }();
+  if (occ_cap > 0 && occ_cap < occ) occ = occ_cap;
   int64_t grid = (int64_t)am::num_sms() * occ;
   const int64_t need = (n_items + WARPS - 1) / WARPS;
   if (grid > need) grid = need;
