@@ -133,10 +133,13 @@ project_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_expect_tx(fb, stage_bytes);
           const uint32_t sa = base + (uint32_t)stage * stage_bytes;
           const uint32_t sb = sa + PJ_NP * PJ_A_BYTES;
-          for (int s = 0; s < PJ_NP; ++s) {
-            tma_load_3d(sa + (uint32_t)s * PJ_A_BYTES, &tmA, ks * PJ_BK, tile * PJ_M, s, fb);
-            tma_load_3d(sb + (uint32_t)s * PJ_B_BYTES, &tmB, ks * PJ_BK, 0, s, fb);
-          }
+          // one box per operand covers all PJ_NP staged planes (third box dimension): 2 TMA issues per stage
+          // instead of 10 from this one thread; the planes land back to back, [plane][row][64 B], as before
+          // CTAs start on different column strips (the int32 sums are exact, so the order over K does not
+          // matter): all 148 CTAs otherwise read the same 64-byte column offset of their rows at the same time
+          const int kc = (ks + (int)blockIdx.x) % p.n_ksteps;
+          tma_load_3d(sa, &tmA, kc * PJ_BK, tile * PJ_M, 0, fb);
+          tma_load_3d(sb, &tmB, kc * PJ_BK, 0, 0, fb);
           if (++stage == PJ_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -212,37 +215,62 @@ project_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(bar_accf, acc_phase);
       tc_fence_after();
       const int64_t row = (int64_t)tile * PJ_M + q * 32 + lane;
-      for (int c = 0; c < PJ_N / 16; ++c) {
-        double g[16];
+      // Phase A: the accumulators leave TMEM — all five weights of a 16-column block behind ONE wait, combined
+      // into fp64 in registers (64 doubles per thread) — and TMEM is handed back at once, so the next tile's
+      // MMAs start while phase B (scaling, stores) is still running.  (With scaling and stores before the
+      // hand-back the whole epilogue sat between two tiles' MMAs: 5 accumulators = 320 of the 512 TMEM columns
+      // leave no room for a second set.)
+      double g[PJ_N];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) g[j] = 0.0;
-        double wd = 1.0;
-        for (int d = 0; d < p.n_acc; ++d) {
-          uint32_t v[16];
+      for (int c = 0; c < PJ_N / 16; ++c) {
+        uint32_t v[PJ_NP][16];
+#pragma unroll
+        for (int d = 0; d < PJ_NP; ++d) {
           const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * PJ_N + c * 16);
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              : "=r"(v[d][0]), "=r"(v[d][1]), "=r"(v[d][2]), "=r"(v[d][3]), "=r"(v[d][4]), "=r"(v[d][5]),
+                "=r"(v[d][6]), "=r"(v[d][7]), "=r"(v[d][8]), "=r"(v[d][9]), "=r"(v[d][10]), "=r"(v[d][11]),
+                "=r"(v[d][12]), "=r"(v[d][13]), "=r"(v[d][14]), "=r"(v[d][15])
               : "r"(ta));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 16; ++j) g[j] = fma((double)(int32_t)v[j], wd, g[j]);
-          wd *= 1.0 / 256.0;
         }
-        if (row < p.n_rows) {
-          double *o = scores + row * p.P;
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int pc = c * 16 + j;
-            if (pc < p.P) o[pc] = ldexp(g[j], s_f[pc] - 12) - s_b[pc];
+        for (int j = 0; j < 16; ++j) {
+          // same order of operations as before (d = 0 first, weights 256^-d): bit-identical scores
+          double acc = 0.0, wd = 1.0;
+#pragma unroll
+          for (int d = 0; d < PJ_NP; ++d) {
+            acc = fma((double)(int32_t)v[d][j], wd, acc);
+            wd *= 1.0 / 256.0;
           }
+          g[c * 16 + j] = acc;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acce);
       acc_phase ^= 1u;
+      // Phase B: off the MMA warp's critical path
+      if (row < p.n_rows) {
+        double *o = scores + row * p.P;  // 16-byte aligned when P is even (row pitch 8 P bytes)
+        const bool vec = (p.P & 1) == 0;
+#pragma unroll
+        for (int pc = 0; pc < PJ_N; pc += 2) {
+          if (pc + 1 < p.P) {
+            const double a = ldexp(g[pc], s_f[pc] - 12) - s_b[pc];
+            const double b = ldexp(g[pc + 1], s_f[pc + 1] - 12) - s_b[pc + 1];
+            if (vec) {
+              *reinterpret_cast<double2 *>(o + pc) = make_double2(a, b);
+            } else {
+              o[pc] = a;
+              o[pc + 1] = b;
+            }
+          } else if (pc < p.P) {
+            o[pc] = ldexp(g[pc], s_f[pc] - 12) - s_b[pc];
+          }
+        }
+      }
     }
   }
   tc_fence_before();
@@ -318,8 +346,8 @@ extern "C" int am_project_planes(const int8_t *d_planes, int64_t n_rows, int D, 
     cuuint64_t gdimB[3] = {(cuuint64_t)D, (cuuint64_t)PJ_N, (cuuint64_t)PJ_S};
     cuuint64_t gstrB[2] = {(cuuint64_t)Dp, (cuuint64_t)Dp * (cuuint64_t)PJ_N};
     cuuint32_t estr[3] = {1, 1, 1};
-    cuuint32_t boxA[3] = {PJ_BK, PJ_M, 1};
-    cuuint32_t boxB[3] = {PJ_BK, PJ_N, 1};
+    cuuint32_t boxA[3] = {PJ_BK, PJ_M, PJ_NP};  // planes 0 .. PJ_W in one box
+    cuuint32_t boxB[3] = {PJ_BK, PJ_N, PJ_NP};
     CUresult r1 = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)d_planes, gdimA, gstrA, boxA, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

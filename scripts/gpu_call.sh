@@ -22,9 +22,11 @@ if [ "$2" != "short" ]; then
 python scripts/dev_plane_sweep.py > $O/${TAG}_plane_sweep.log 2>&1; echo "planes rc=$?"; cat $O/${TAG}_plane_sweep.log | tail -20
 python scripts/time_api.py > $O/${TAG}_api.log 2>&1; echo "api rc=$?"; cat $O/${TAG}_api.log | tail -4
 fi
-# ncu: eps_union at eps 0.3 / 2.0 / 5.0 (launches 0, 17, 47 of the sweep)
+python scripts/time_sweep_batch.py > $O/${TAG}_sweep_batch.json 2> $O/${TAG}_sweep_batch.err; echo "sweep batch rc=$?"; cat $O/${TAG}_sweep_batch.json
+python scripts/dev_sweep_step_time.py > $O/${TAG}_sweep_step_time.json 2>> $O/${TAG}_sweep_batch.err; cat $O/${TAG}_sweep_step_time.json
+# ncu: the neighbour kernel (eps_union_warp_kernel) at eps 0.3 / 2.0 / 5.0 (launches 0, 17, 47 of the sweep)
 python scripts/dev_sweep_once.py > $O/${TAG}_sweep_plain.log 2>&1 && for s in 0 17 47; do
-  ncu --set full --clock-control none -k regex:eps_union_kernel -s $s -c 1 -o $O/eps_$s python scripts/dev_sweep_once.py > $O/${TAG}_ncu_eps_$s.log 2>&1
+  ncu --set full --clock-control none -k regex:eps_union_warp_kernel -s $s -c 1 -o $O/eps_$s python scripts/dev_sweep_once.py > $O/${TAG}_ncu_eps_$s.log 2>&1
   ncu -i $O/eps_$s.ncu-rep --page raw --csv > $O/${TAG}_eps_union_launch${s}_raw.csv 2>/dev/null; rm -f $O/eps_$s.ncu-rep
 done; echo "ncu eps rc=$?"
 # ncu: launch list of a short bench, and full sets of the count kernel and the tridiagonalisation

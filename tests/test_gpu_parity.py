@@ -632,6 +632,34 @@ def test_sweep_incremental_equals_fresh_and_oracle(torch_cuda):
     assert prev_n == 1
 
 
+@pytest.mark.parametrize("F", [1, 2, 4])
+def test_eps_step_other_feature_counts(torch_cuda, F):
+    """The neighbour kernel is instantiated per feature count (3^F cells per point: 3 / 9 / 81, the last in three
+    rounds of 32 lanes); F = 3 is what every other test runs.  Labels against the oracle and against sklearn,
+    through EpsSweep and through run_dbscan (x_1 .. x_{F-1} + coverage)."""
+    import torch
+    from sklearn.cluster import DBSCAN
+
+    from autometa_b200 import device as D
+    from autometa_b200.binning import recursive_dbscan as R
+
+    rng = np.random.default_rng(40 + F)
+    n, k = 4000, 25
+    centres = rng.uniform(-30, 30, size=(k, F))
+    X = np.ascontiguousarray(centres[rng.integers(0, k, size=n)] + rng.normal(0, 0.8, size=(n, F)))
+    X[:50] = X[50:100]  # exact duplicates
+    sweep = D.EpsSweep(torch.from_numpy(X).cuda())
+    for eps in (0.05, 0.3, 0.7999999999999999, 1.5, 4.0, 200.0):
+        lab = sweep.step(eps).cpu().numpy()
+        assert np.array_equal(lab, O.dbscan_labels(X, eps)), (F, eps)
+        ref = DBSCAN(eps=eps, min_samples=1).fit(X).labels_
+        assert np.array_equal(lab, ref.astype(np.int64)), (F, eps)
+    cols = [f"x_{i + 1}" for i in range(F - 1)] + ["coverage"]
+    df = pd.DataFrame(X, columns=cols, index=pd.Index([f"c{i}" for i in range(n)], name="contig"))
+    out = R.run_dbscan(df.copy(), eps=0.7)
+    assert np.array_equal(out["cluster"].to_numpy(), DBSCAN(eps=0.7, min_samples=1).fit(X).labels_)
+
+
 def test_sweep_full_size_c4(torch_cuda):
     """C4: 200k points, the reference's 48-value eps grid; the label vector is identical to sklearn's
     (what recursive_dbscan.py:109 executes) at EVERY eps of the grid."""
