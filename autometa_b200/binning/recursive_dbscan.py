@@ -7,11 +7,15 @@ schedule, tie rule and termination; the clustering itself runs on the GPU
 ``DBSCAN(min_samples=1)``: every point is a core point, there are no border or
 noise points, and each eps is the connected components of the eps-graph — so the
 sweep keeps ONE union-find forest on the device and only adds merges as eps grows.
+The sweep's loop state (eps, step, best median so far, ``clustering_rounds``, termination)
+lives on the device too (``device.DeviceSweep``, csrc/am_sweep.cu): one step is a CUDA
+graph, the host queues batches of replays and reads one word per batch.
 
 The callers of the sweep are mirrored on top of it: ``get_clusters``
 (:440-545, re-sweeps the leftovers until nothing more is recovered) and
 ``taxon_guided_binning`` (:548-705, the same per taxon from superkingdom down to
-species).  Only ``method="dbscan"`` is on the device; HDBSCAN is out of scope
+species); ``get_clusters_many`` runs the independent ``get_clusters`` problems of one rank's
+taxa with their sweeps in flight together.  Only ``method="dbscan"`` is on the device; HDBSCAN is out of scope
 (``NotImplementedError``).  The eps step takes at most 4 clustering features (the
 columns containing ``x_`` plus ``coverage``: ``embed_dimensions`` <= 3), more raise
 ``ValueError``; the reference's default is 2 + coverage.
