@@ -259,6 +259,44 @@ def sweep_bench(dev, torch, cpu=True, reps=3):
                       "clustered": int(cl.shape[0]), "unclustered": int(un.shape[0])}
     except Exception as exc:  # keep the bench line even if the API leg fails
         out["api"] = {"error": repr(exc)}
+    # the callers' shape of the same work (large-data mode): many small get_clusters problems — the
+    # taxa of one rank — one at a time against in flight together (get_clusters_many)
+    try:
+        import pandas as pd
+
+        from autometa_b200.binning import recursive_dbscan as R
+
+        parts, per = 32, 2000
+        tables, mk = [], []
+        for i in range(parts):
+            t, m = synth.make_sweep_input(n_points=per, n_clusters=6, n_markers=40, seed=100 + i)
+            t.index = pd.Index([f"T{i}_{c}" for c in t.index], name="contig")
+            m.index = pd.Index([f"T{i}_{c}" for c in m.index], name="contig")
+            tables.append(t)
+            mk.append(m)
+        mk = pd.concat(mk)
+        cut = (20.0, 90.0, 25.0, 5.0)
+        R.get_clusters_many([t.copy() for t in tables[:8]], mk, *cut, method="dbscan")  # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        one = [R.get_clusters(t.copy(), mk, *cut, method="dbscan") for t in tables]
+        torch.cuda.synchronize()
+        t_one = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        many = R.get_clusters_many([t.copy() for t in tables], mk, *cut, method="dbscan")
+        torch.cuda.synchronize()
+        t_many = time.perf_counter() - t0
+        same = all(a["cluster"].fillna("").tolist() == b["cluster"].fillna("").tolist() for a, b in zip(one, many))
+        out["taxa_batch"] = {
+            "what": f"get_clusters on {parts} tables of {per} contigs (DataFrames in and out, all rounds): one call "
+                    "after the other / get_clusters_many (sweeps in flight together, each a chain of CUDA-graph "
+                    "replays on its own stream)",
+            "one_at_a_time_s": t_one, "in_flight_together_s": t_many,
+            "ms_per_table": {"one_at_a_time": t_one / parts * 1e3, "in_flight_together": t_many / parts * 1e3},
+            "bins": int(sum(x["cluster"].nunique() for x in many)), "same_bins": bool(same),
+        }
+    except Exception as exc:
+        out["taxa_batch"] = {"error": repr(exc)}
     if cpu:
         # reference arm of the same metric: what recursive_dbscan.py:109 executes, on the host cores,
         # at 4 of the 48 eps values (bounded sample), scaled to the grid

@@ -588,3 +588,36 @@ def test_sweep_driver_keeps_order_and_limit():
     assert R._drive(starters[:2], limit=1) == [("result", 0), ("result", 1)]
     assert R._drive([], limit=4) == []
     assert R._in_flight(10_000, 140) == 16 and R._in_flight(2_000_000, 140) >= 1
+
+
+def test_markers_coo_cached_table_equals_direct_conversion():
+    """markers_coo goes through a CSR table built once per marker frame; the entries must be those of the
+    direct conversion (restrict the frame to the table's contigs, take the non-zeros), for any subset / order
+    of contigs, contigs without markers, NaN cells and an empty selection."""
+    from autometa_b200.binning import utilities as U
+
+    rng = np.random.default_rng(3)
+    ids = np.array([f"c{i}" for i in range(500)], dtype=object)
+    vals = rng.integers(0, 3, size=(300, 17)).astype(float) * (rng.random((300, 17)) < 0.2)
+    vals[5, 3] = np.nan
+    markers = pd.DataFrame(vals, index=pd.Index(rng.permutation(ids)[:300], name="contig"),
+                           columns=[f"PF{m}" for m in range(17)])
+
+    def direct(index):
+        pos = index.get_indexer(markers.index)
+        ok = pos >= 0
+        v = np.nan_to_num(markers.to_numpy(dtype=np.float64, na_value=0.0)[ok], nan=0.0)
+        r, c = np.nonzero(v)
+        return sorted(zip(pos[ok][r].tolist(), c.tolist(), v[r, c].tolist()))
+
+    for sel in (ids, rng.permutation(ids)[:120], ids[:1], np.array(["zzz"], dtype=object), ids[:0]):
+        index = pd.Index(sel, name="contig")
+        r, c, v = U.markers_coo(markers, index)
+        assert r.dtype == np.int64 and c.dtype == np.int64
+        assert sorted(zip(r.tolist(), c.tolist(), v.tolist())) == direct(index)
+    assert U._marker_table(markers) is U._marker_table(markers)          # built once per frame
+    other = markers.copy()
+    assert U._marker_table(other) is not U._marker_table(markers)
+    dup = pd.concat([markers.iloc[:3], markers.iloc[:3]])                  # non-unique index: the direct path
+    r, c, v = U.markers_coo(dup, pd.Index(ids, name="contig"))
+    assert len(r) == 2 * int((np.nan_to_num(markers.iloc[:3].to_numpy()) != 0).sum())
