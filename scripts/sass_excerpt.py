@@ -16,7 +16,7 @@ for line in sass.splitlines():
         stats[cur] = collections.Counter()
         lines[cur] = 0
         continue
-    if cur and re.search(r'/\*[0-9a-f]{4}\*/', line):
+    if cur and re.search(r'/\*[0-9a-f]{4,}\*/', line):
         lines[cur] += 1
         for t in pat.findall(line):
             stats[cur][t] += 1
