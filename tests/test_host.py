@@ -621,3 +621,35 @@ def test_markers_coo_cached_table_equals_direct_conversion():
     dup = pd.concat([markers.iloc[:3], markers.iloc[:3]])                  # non-unique index: the direct path
     r, c, v = U.markers_coo(dup, pd.Index(ids, name="contig"))
     assert len(r) == 2 * int((np.nan_to_num(markers.iloc[:3].to_numpy()) != 0).sum())
+
+
+def _check_binning_frame(df, g, prefix):
+    assert df.index.tolist() == g[f"{prefix}_index"].tolist()
+    assert df.columns.tolist() == g[f"{prefix}_columns"].tolist()
+    got = np.array(["" if pd.isna(c) else str(c) for c in df["cluster"]])
+    assert np.array_equal(got, g[f"{prefix}_cluster"])
+    for m in ["completeness", "purity", "coverage_stddev", "gc_content_stddev"]:
+        a = pd.to_numeric(df[m], errors="coerce").to_numpy(dtype=np.float64, na_value=np.nan)
+        assert np.allclose(a, g[f"{prefix}_{m}"], rtol=1e-12, atol=0, equal_nan=True), m
+
+
+def test_binning_drivers_host_logic_against_reference_golden(monkeypatch, golden_binning):
+    """get_clusters / get_clusters_many / taxon_guided_binning with the device sweep replaced by the numpy oracle
+    (tests/_cpu_sweep_standin.py): everything the host does around a sweep — frames, rounds on the leftovers, bin
+    names, sweeps in flight together, the walk over ranks and taxa — against the frames the unmodified reference
+    produced (tests/golden/binning_golden.npz).  The same goldens pin the real device path in the GPU suite."""
+    import _cpu_sweep_standin as S
+    from autometa_b200 import synth
+    from autometa_b200.binning import recursive_dbscan as R
+
+    S.install(monkeypatch)
+    table, markers = synth.make_sweep_input(n_points=1500, n_clusters=9, n_markers=40, seed=21)
+    df = R.get_clusters(table.copy(), markers, 20.0, 90.0, 25.0, 5.0, method="dbscan")
+    _check_binning_frame(df, golden_binning, "get_clusters")
+    df0 = R.get_clusters(table.iloc[:40].copy(), markers, 99.0, 99.0, 0.001, 0.001, method="dbscan")
+    _check_binning_frame(df0, golden_binning, "get_clusters_none")
+    both = R.get_clusters_many([table.copy(), table.iloc[:40].copy()], markers, 20.0, 90.0, 25.0, 5.0, method="dbscan")
+    _check_binning_frame(both[0], golden_binning, "get_clusters")
+    tax = synth.add_taxonomy(table, seed=3)
+    dft = R.taxon_guided_binning(tax.copy(), markers, 20.0, 90.0, 25.0, 5.0, method="dbscan")
+    _check_binning_frame(dft, golden_binning, "taxon")
