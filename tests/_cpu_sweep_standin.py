@@ -76,3 +76,37 @@ def install(monkeypatch):
     monkeypatch.setattr(D, "DeviceSweep", OracleSweep)
     monkeypatch.setattr(R.L, "require_cuda", lambda device=None: torch.device("cpu"))
     monkeypatch.setattr(R, "_stream_pool", lambda dev, k: [None] * k)
+
+
+class OraclePartitionPCA:
+    """CPU stand-in for ``large_data_mode.PartitionPCA`` (tests only): am_clr + exact PCA of the numpy oracle per
+    partition, rows in the count table's order."""
+
+    def __init__(self, counts, norm_method, pca_dimensions, device=None, n_streams=8):
+        assert norm_method == "am_clr"
+        self.counts, self.P = counts, int(pca_dimensions)
+
+    def run(self, partitions):
+        import pandas as pd
+
+        out = {}
+        for key, index in partitions.items():
+            sub = self.counts.loc[self.counts.index.isin(index)]
+            X, row_keep, _ = O.am_clr(sub.to_numpy(dtype=np.float64))
+            out[key] = pd.DataFrame(O.pca_cov_eigh(X, self.P)["scores"], index=sub.index[row_keep])
+        return out
+
+
+def install_ldm(monkeypatch):
+    """``install`` + the batched normalise / PCA of large-data mode and the ``tsne`` stub the reference's golden
+    run used (returns the first d columns it is handed)."""
+    import sys
+    import types
+
+    from autometa_b200.binning import large_data_mode as M
+
+    install(monkeypatch)
+    monkeypatch.setattr(M, "PartitionPCA", OraclePartitionPCA)
+    stub = types.ModuleType("tsne")
+    stub.bh_sne = lambda data, d, **kw: np.ascontiguousarray(data[:, :d])
+    monkeypatch.setitem(sys.modules, "tsne", stub)

@@ -653,3 +653,29 @@ def test_binning_drivers_host_logic_against_reference_golden(monkeypatch, golden
     tax = synth.add_taxonomy(table, seed=3)
     dft = R.taxon_guided_binning(tax.copy(), markers, 20.0, 90.0, 25.0, 5.0, method="dbscan")
     _check_binning_frame(dft, golden_binning, "taxon")
+
+
+def test_large_data_mode_host_logic_against_reference_golden(monkeypatch, tmp_path):
+    """cluster_by_taxon_partitioning with the device work replaced by the numpy oracle (sweeps, normalise + PCA):
+    the walk over ranks and taxa, partition rules, the batching of a rank's sweeps, bin numbering, embedding
+    caches and checkpoints against the frames and file lists the unmodified reference produced
+    (tests/golden/ldm_golden.npz); the GPU suite runs the same comparison on the device path."""
+    import _cpu_sweep_standin as S
+    import _ldm_input
+    from autometa_b200.binning import large_data_mode as M
+
+    S.install_ldm(monkeypatch)
+    kw = dict(norm_method="am_clr", pca_dimensions=10, embed_dimensions=2, embed_method="bhsne", completeness=20.0,
+              purity=90.0, coverage_stddev=25.0, gc_content_stddev=5.0, starting_rank="superkingdom", method="dbscan")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ldm_golden.npz"))
+    main, counts, markers = _ldm_input.make_ldm_input()
+    df = M.cluster_by_taxon_partitioning(main.copy(), counts.copy(), markers, max_partition_size=10000, **kw)
+    _check_binning_frame(df, g, "ldm")
+    cache = str(tmp_path / "cache")
+    df2 = M.cluster_by_taxon_partitioning(main.copy(), counts.copy(), markers, max_partition_size=400, cache=cache, **kw)
+    _check_binning_frame(df2, g, "ldm400")
+    files = sorted(os.path.relpath(os.path.join(d, f), cache) for d, _, fs in os.walk(cache) for f in fs)
+    assert files == g["ldm400_cache_files"].tolist()
+    info = M.get_checkpoint_info(os.path.join(cache, "binning_checkpoints.tsv.gz"))
+    assert info["binning_checkpoints"].columns.tolist() == g["ldm400_checkpoint_columns"].tolist()
+    assert [info["starting_rank"], info["starting_rank_name_txt"]] == g["ldm400_checkpoint_rank"].tolist()
