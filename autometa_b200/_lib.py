@@ -103,6 +103,8 @@ _SIGS = {
     "am_metrics_work_bytes": (_i64, [_i64, _i32]),
     "am_cluster_metrics": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _i32, _p, _p, _f64, _f64, _f64, _f64,
                                      _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "am_counts_to_columns": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _i32]),
+    "am_columns_to_counts": (C.c_int, [_p, _p, _i32, _i64, _i64, _p, _p, _p, _i32]),
     "am_eps_grid": (C.c_int, [_f64, _p, _p, _i32, _p]),
     "am_eps_union_dyn": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p]),
     "am_sweep_args_size": (_i64, []),

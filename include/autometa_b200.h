@@ -447,6 +447,21 @@ int am_sweep_graph_destroy(void *graph);
 int am_sweep_advance_host(double *ctl, int32_t *rounds, int F, int n_clusters, double median);
 
 /* ---------------------------------------------------------------------------
+ * Host-side conversion between the row-major count matrix and the per-column (values, mask) arrays of the
+ * frame `count` returns (autometa/common/kmers.py:205,325-326: zero counts are pd.NA, contigs with L <= k are
+ * all-NA rows, :187-192).  Blocked and threaded (n_threads <= 0: all host threads).
+ *   am_counts_to_columns  values_t[c][r] = counts[r][c]; mask_t[c][r] = (counts[r][c] == 0 || !countable[r])
+ *                         (countable may be null: every row countable)
+ *   am_columns_to_counts  the inverse for `normalize`: column c has n_rows values of elem_size 4 (int32) or 8
+ *                         (int64) bytes and a byte mask; counts[r][c] = masked ? 0 : value, isna[r][c] = masked;
+ *                         *h_bad = number of unmasked values outside 0 .. 2^31-1 (the caller raises) */
+int am_counts_to_columns(const int32_t *h_counts, int64_t n_rows, int64_t n_cols, const uint8_t *h_countable,
+                         int32_t *h_values_t, uint8_t *h_mask_t, int n_threads);
+int am_columns_to_counts(const void *const *h_col_values, const uint8_t *const *h_col_masks, int elem_size,
+                         int64_t n_rows, int64_t n_cols, int32_t *h_counts, uint8_t *h_isna, int64_t *h_bad,
+                         int n_threads);
+
+/* ---------------------------------------------------------------------------
  * Host-side TSV I/O of the k-mer tables, all host threads.
  * Replaces `df.to_csv(out, sep="\t", index=True, header=True)` and
  * `pd.read_csv(fpath, sep="\t", index_col="contig")` at

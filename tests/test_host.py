@@ -679,3 +679,51 @@ def test_large_data_mode_host_logic_against_reference_golden(monkeypatch, tmp_pa
     info = M.get_checkpoint_info(os.path.join(cache, "binning_checkpoints.tsv.gz"))
     assert info["binning_checkpoints"].columns.tolist() == g["ldm400_checkpoint_columns"].tolist()
     assert [info["starting_rank"], info["starting_rank_name_txt"]] == g["ldm400_checkpoint_rank"].tolist()
+
+
+def test_counts_frame_and_back_through_the_threaded_host_conversions():
+    """count()'s frame (one nullable-integer array per k-mer column, zero / uncountable -> pd.NA, duplicate ids
+    merged as the reference's dict.update does) is built by am_counts_to_columns and read back for normalize by
+    am_columns_to_counts: both against their plain numpy definitions."""
+    from autometa_b200.common import kmers
+    from autometa_b200.common.exceptions import TableFormatError
+
+    rng = np.random.default_rng(11)
+    n, D = 1237, 136
+    counts = (rng.integers(0, 40, size=(n, D)) * (rng.random((n, D)) < 0.7)).astype(np.int32)
+    countable = rng.random(n) > 0.02
+    ids = [f"c{i}" for i in range(n)]
+    names = [f"k{j}" for j in range(D)]
+    df = kmers._counts_frame(ids, counts, countable, names)
+    want_na = (counts == 0) | ~countable[:, None]
+    assert df.shape == (n, D) and df.index.name == "contig" and list(df.columns) == names
+    assert all(str(t) == "Int32" for t in df.dtypes)
+    assert np.array_equal(df.isna().to_numpy(), want_na)
+    assert np.array_equal(df.fillna(0).to_numpy(dtype=np.int64), np.where(want_na, 0, counts))
+    back, isna = kmers._counts_matrix(df)
+    assert back.dtype == np.int32 and back.flags["C_CONTIGUOUS"] and isna.dtype == bool
+    assert np.array_equal(back, np.where(want_na, 0, counts)) and np.array_equal(isna, want_na)
+    # the same answers as the generic conversion (float / NaN frame, as kmers.load returns)
+    fl = df.astype("float64")
+    b2, i2 = kmers._counts_matrix(fl)
+    assert np.array_equal(b2, back) and np.array_equal(i2, isna)
+    # Int64 columns; a frame that is not all nullable integers takes the generic path
+    b3, i3 = kmers._counts_matrix(df.astype("Int64"))
+    assert np.array_equal(b3, back) and np.array_equal(i3, isna)
+    mixed = df.copy()
+    mixed[names[0]] = mixed[names[0]].astype("float64")
+    b4, i4 = kmers._counts_matrix(mixed)
+    assert np.array_equal(b4, back) and np.array_equal(i4, isna)
+    bad = df.astype("Int64")
+    bad.iloc[5, 7] = -3
+    with pytest.raises(TableFormatError):
+        kmers._counts_matrix(bad)
+    # duplicate ids: the later record's values at the first record's position (kmers.py:155-157)
+    ids2 = list(ids)
+    ids2[10] = ids2[3]
+    d2 = kmers._counts_frame(ids2, counts, countable, names)
+    assert d2.shape[0] == n - 1 and d2.index[3] == ids[3] and ids[10] not in d2.index
+    assert np.array_equal(d2.iloc[3].fillna(0).to_numpy(dtype=np.int64), np.where(want_na[10], 0, counts[10]))
+    # empty table
+    e = kmers._counts_frame([], np.zeros((0, D), dtype=np.int32), np.zeros(0, dtype=bool), names)
+    assert e.shape == (0, D)
