@@ -237,7 +237,9 @@ def normalize(
     logger.debug(f"Transforming k-mer counts using {method}")
     choices = {"ilr", "clr", "am_clr"}
     if method == "am_clr":
-        norm_df = autometa_clr(df, device=device)
+        counts, isna = _counts_matrix(df)
+        vals, row_keep, col_keep = _normalize_array(counts, isna, "am_clr", device)
+        norm_df = pd.DataFrame(vals, index=df.index[row_keep], columns=df.columns[col_keep])  # = autometa_clr(df)
     elif method in choices:
         counts, isna = _counts_matrix(df)
         vals, _, _ = _normalize_array(counts, isna, method, device)
@@ -245,7 +247,7 @@ def normalize(
     else:
         raise ValueError(f"Normalize Method not available! {method}. choices: {', '.join(choices)}")
     if out_specified and (force or not out_exists):
-        _tsv.write_frame(norm_df, out)
+        _tsv.write_frame(norm_df, out, values=vals)  # the matrix the frame was built from: no transposing copy
     return norm_df
 
 
