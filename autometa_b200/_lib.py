@@ -49,6 +49,7 @@ _SIGS = {
     "am_kmer_column_lut": (C.c_int, [_i32, _p]),
     "am_kmer_column_names": (C.c_int, [_i32, _p]),
     "am_fasta_index": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _p]),
+    "am_fasta_index_mt": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i32]),
     "am_pack_plan": (C.c_int, [_p, _i64, _p, _p, _p]),
     "am_pack_code_words": (_i64, [_i64]),
     "am_pack_bitmap_words": (_i64, [_i64]),

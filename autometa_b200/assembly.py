@@ -74,11 +74,13 @@ def parse_fasta_bytes(raw: bytes) -> HostAssembly:
     buf = np.frombuffer(raw, dtype=np.uint8)
     n = len(buf)
     seq = np.empty(n + 64, dtype=np.uint8)
-    cap = max(16, raw.count(b">"))
+    nrec = np.zeros(1, dtype=np.int64)
+    if n:  # the number of records from the library's own (threaded) header count, not from a scan in Python
+        L.check(L.lib.am_fasta_index_mt(L.np_ptr(buf), n, None, None, None, None, 0, L.np_ptr(nrec), 0))
+    cap = max(16, int(nrec[0]))
     offsets = np.zeros(cap + 1, dtype=np.int64)
     idb = np.zeros(cap, dtype=np.int64)
     ide = np.zeros(cap, dtype=np.int64)
-    nrec = np.zeros(1, dtype=np.int64)
     L.check(
         L.lib.am_fasta_index(
             L.np_ptr(buf) if n else None, n, L.np_ptr(seq), L.np_ptr(offsets), L.np_ptr(idb),

@@ -82,6 +82,13 @@ int am_kmer_column_names(int k, char *h_names);
 int am_fasta_index(const uint8_t *h_buf, int64_t len, uint8_t *h_seq_out,
                    int64_t *h_offsets, int64_t *h_id_begin, int64_t *h_id_end,
                    int64_t cap, int64_t *n_records);
+/* the same with an explicit thread count (<= 0: all host threads; 1: one pass on the calling thread): the buffer
+ * is cut at line starts, headers and sequence bytes are counted per range, then every range writes from its
+ * prefix-summed record number and output position. am_fasta_index = am_fasta_index_mt(..., 0).  With all four
+ * output pointers null only the records are counted (*n_records), so the caller can size its arrays. */
+int am_fasta_index_mt(const uint8_t *h_buf, int64_t len, uint8_t *h_seq_out,
+                   int64_t *h_offsets, int64_t *h_id_begin, int64_t *h_id_end,
+                   int64_t cap, int64_t *n_records, int n_threads);
 
 /* ---------------------------------------------------------------------------
  * 2-bit packing.  Layout in HBM ("packed assembly"):

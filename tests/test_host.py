@@ -727,3 +727,59 @@ def test_counts_frame_and_back_through_the_threaded_host_conversions():
     # empty table
     e = kmers._counts_frame([], np.zeros((0, D), dtype=np.int32), np.zeros(0, dtype=bool), names)
     assert e.shape == (0, D)
+
+
+def test_threaded_fasta_index_equals_single_pass(tmp_path):
+    """am_fasta_index_mt cuts the buffer at line starts and parses the ranges in parallel (two passes): same ids,
+    offsets and sequence bytes as one pass on one thread, on inputs with CRLF, blanks inside and after lines,
+    empty lines, text before the first header, '>' inside titles and no final newline; and the one-thread pass
+    equals the oracle's FASTA restatement."""
+    from autometa_b200 import _lib as L
+
+    rng = np.random.default_rng(77)
+    alphabet = np.frombuffer(b"ACGTacgtNRY", dtype=np.uint8)
+
+    def make(n_records, lead=b"", final_newline=True):
+        parts = [lead]
+        for i in range(n_records):
+            title = b">" + (b" " if i % 97 == 0 else b"") + b"rec%d" % i + (b" some > text\tmore" if i % 5 == 0 else b"")
+            parts.append(title + (b"\r\n" if i % 3 == 0 else b"\n"))
+            for _ in range(int(rng.integers(0, 6))):
+                ln = int(rng.integers(0, 90))
+                line = alphabet[rng.integers(0, len(alphabet), size=ln)].tobytes()
+                if ln > 10 and rng.random() < 0.1:
+                    line = line[:5] + b" " + line[5:]
+                tail = [b"", b" ", b"\r", b" \t ", b"\r"][int(rng.integers(0, 5))]
+                parts.append(line + tail + b"\n")
+            if rng.random() < 0.05:
+                parts.append(b"\n")
+        raw = b"".join(parts)
+        return raw if final_newline else raw.rstrip(b"\n")
+
+    def index(raw, threads):
+        buf = np.frombuffer(raw, dtype=np.uint8)
+        cap = max(16, raw.count(b">"))
+        seq = np.zeros(len(buf) + 64, dtype=np.uint8)
+        offsets = np.zeros(cap + 1, dtype=np.int64)
+        idb, ide = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64)
+        n = np.zeros(1, dtype=np.int64)
+        L.check(L.lib.am_fasta_index_mt(L.np_ptr(buf), len(buf), L.np_ptr(seq), L.np_ptr(offsets), L.np_ptr(idb),
+                                        L.np_ptr(ide), cap, L.np_ptr(n), threads))
+        k = int(n[0])
+        ids = [raw[int(b):int(e)] for b, e in zip(idb[:k], ide[:k])]
+        return ids, offsets[: k + 1].copy(), seq[: int(offsets[k])].tobytes()
+
+    cases = [make(40_000), make(30_000, lead=b"junk line\nACGT\n"), make(25_000, final_newline=False)]
+    assert all(len(c) > 3 << 20 for c in cases)  # several 1 MB ranges each
+    for raw in cases:
+        one = index(raw, 1)
+        for threads in (2, 5, 8):
+            many = index(raw, threads)
+            assert many[0] == one[0] and np.array_equal(many[1], one[1]) and many[2] == one[2]
+    small = make(300, lead=b"not a record\n")
+    path = tmp_path / "x.fna"
+    path.write_bytes(small)
+    ids, seqs = O.read_fasta(str(path))
+    got = index(small, 1)
+    assert [i.decode() for i in got[0]] == ids
+    assert [got[2][a:b] for a, b in zip(got[1][:-1], got[1][1:])] == seqs
