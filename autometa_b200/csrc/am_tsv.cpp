@@ -93,18 +93,25 @@ int write_table(const char *path, const uint8_t *header, int64_t header_len, con
     return am::fail(AM_EINVAL, "am_tsv_write: short write");
   }
   n_threads = std::max(1, std::min(n_threads, 256));
-  const int64_t rows_per_job = 1024;
+  const int64_t rows_per_job = 128;  // 1.7 MB of text per job at 512 columns: the buffers stay cache-resident
   const int64_t wave = rows_per_job * n_threads;
-  std::vector<std::string> bufs((size_t)n_threads);
-  bool ok = true;
-  for (int64_t r0 = 0; r0 < n_rows && ok; r0 += wave) {
+  // two sets of per-thread buffers: wave w is written to the file (one writer thread, in order) while wave w + 1 is
+  // being formatted on all threads
+  std::vector<std::string> bufs[2] = {std::vector<std::string>((size_t)n_threads),
+                                      std::vector<std::string>((size_t)n_threads)};
+  std::vector<size_t> used[2] = {std::vector<size_t>((size_t)n_threads, 0), std::vector<size_t>((size_t)n_threads, 0)};
+  std::atomic<bool> ok{true};
+  std::thread writer;
+  int set = 0;
+  for (int64_t r0 = 0; r0 < n_rows && ok.load(); r0 += wave, set ^= 1) {
     const int64_t r1 = std::min(n_rows, r0 + wave);
+    std::vector<std::string> &cur = bufs[set];
     auto job = [&](int t) {
       const int64_t a = std::min(r1, r0 + t * rows_per_job), b = std::min(r1, a + rows_per_job);
-      std::string &out = bufs[(size_t)t];
+      std::string &out = cur[(size_t)t];
       size_t need = 0;
       for (int64_t r = a; r < b; ++r) need += (size_t)(id_offsets[r + 1] - id_offsets[r]) + (size_t)n_cols * 26 + 2;
-      out.resize(need);
+      if (out.size() < need) out.resize(need);  // grows once; never shrunk (no zero-fill per wave)
       char *p = out.data();
       for (int64_t r = a; r < b; ++r) {
         const size_t len = (size_t)(id_offsets[r + 1] - id_offsets[r]);
@@ -116,18 +123,24 @@ int write_table(const char *path, const uint8_t *header, int64_t header_len, con
         }
         *p++ = '\n';
       }
-      out.resize((size_t)(p - out.data()));
+      used[set][(size_t)t] = (size_t)(p - out.data());
     };
     std::vector<std::thread> pool;
     for (int t = 1; t < n_threads; ++t) pool.emplace_back(job, t);
     job(0);
     for (auto &th : pool) th.join();
-    for (int t = 0; t < n_threads && ok; ++t)
-      if (!bufs[(size_t)t].empty())
-        ok = fwrite(bufs[(size_t)t].data(), 1, bufs[(size_t)t].size(), fh) == bufs[(size_t)t].size();
+    if (writer.joinable()) writer.join();  // the previous wave is on disk; its buffers are free for wave w + 1
+    writer = std::thread([&, set]() {
+      for (int t = 0; t < n_threads && ok.load(); ++t) {
+        const size_t n = used[set][(size_t)t];
+        if (n && fwrite(bufs[set][(size_t)t].data(), 1, n, fh) != n) ok.store(false);
+        used[set][(size_t)t] = 0;
+      }
+    });
   }
-  if (fclose(fh) != 0) ok = false;
-  return ok ? AM_OK : am::fail(AM_EINVAL, "am_tsv_write: short write");
+  if (writer.joinable()) writer.join();
+  if (fclose(fh) != 0) ok.store(false);
+  return ok.load() ? AM_OK : am::fail(AM_EINVAL, "am_tsv_write: short write");
 }
 
 // ---- reader --------------------------------------------------------------------------
