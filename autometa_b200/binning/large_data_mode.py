@@ -23,18 +23,17 @@ import os
 import re
 from datetime import datetime
 from types import SimpleNamespace
-from typing import Dict, Iterable, List, Optional, Union
+from typing import Dict, List, Optional, Union
 
 import numpy as np
 import pandas as pd
 
 from .. import _lib as L
-from .. import device as _dev
 from .. import pipeline as _pipe
 from .. import tsv as _tsv
 from ..common import kmers
-from ..common.exceptions import BinningError, TableFormatError
-from .recursive_dbscan import get_clusters, get_clusters_many
+from ..common.exceptions import BinningError
+from .recursive_dbscan import get_clusters_many
 from .utilities import reindex_bin_names, zero_pad_bin_names
 
 logger = logging.getLogger(__name__)

@@ -35,7 +35,6 @@ from .utilities import (
     METRICS,
     add_metrics,
     apply_binning_metrics_filter,
-    cluster_metrics_arrays,
     markers_coo,
     passing_mask,
     reindex_bin_names,
